@@ -1,0 +1,125 @@
+// hb_common.cuh -- shared device / host helpers for the sm_100a kernel-model kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/homonim_b200.h"
+
+// ---- error plumbing (thread-local message, C-ABI returns non-zero) -------------------------------------------------
+void hb_set_error(const char *fmt, ...);
+void hb_count_launch(int n = 1);
+
+#define HB_CUDA_OK(call)                                                                                     \
+    do {                                                                                                     \
+        cudaError_t err__ = (call);                                                                          \
+        if (err__ != cudaSuccess) {                                                                          \
+            hb_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(err__));    \
+            return 1;                                                                                        \
+        }                                                                                                    \
+    } while (0)
+
+#define HB_LAUNCH_OK(name)                                                                                   \
+    do {                                                                                                     \
+        cudaError_t err__ = cudaGetLastError();                                                              \
+        if (err__ != cudaSuccess) {                                                                          \
+            hb_set_error("launch of %s failed at %s:%d: %s", name, __FILE__, __LINE__,                       \
+                         cudaGetErrorString(err__));                                                         \
+            return 1;                                                                                        \
+        }                                                                                                    \
+        hb_count_launch();                                                                                   \
+    } while (0)
+
+#define HB_REQUIRE(cond, ...)                                                                                \
+    do {                                                                                                     \
+        if (!(cond)) {                                                                                       \
+            hb_set_error(__VA_ARGS__);                                                                       \
+            return 2;                                                                                        \
+        }                                                                                                    \
+    } while (0)
+
+static inline size_t hb_dtype_size(int dtype) { return dtype == HB_U8 ? 1 : (dtype == HB_U16 ? 2 : 4); }
+
+// ---- nodata ---------------------------------------------------------------------------------------------------------
+// A pixel is invalid iff it equals the nodata value, or both are NaN (homonim/utils.py:54-56).  The comparison is
+// done in float32, as numpy does for a float32 array against a Python float (NEP 50 weak scalar).
+struct NoData {
+    int has;       // 0: every pixel valid
+    int is_nan;    // nodata is NaN
+    float value;   // nodata as float32
+    int int_ok;    // nodata is an integer in [0, 65535]: only then can a uint8 / uint16 pixel equal it
+    int ivalue;    // nodata as integer (when int_ok)
+};
+
+static inline NoData hb_make_nodata(int has, double nodata)
+{
+    NoData nd;
+    nd.has = has ? 1 : 0;
+    nd.is_nan = (has && isnan(nodata)) ? 1 : 0;
+    nd.value = (float)nodata;
+    nd.int_ok = (has && !nd.is_nan && nodata >= 0.0 && nodata <= 65535.0 && nodata == floor(nodata)) ? 1 : 0;
+    nd.ivalue = nd.int_ok ? (int)nodata : -1;
+    return nd;
+}
+
+__device__ __forceinline__ bool hb_valid(float v, const NoData &nd)
+{
+    if (!nd.has) return true;
+    return nd.is_nan ? !isnan(v) : (v != nd.value);
+}
+// integer storage: compare as integers (exact; a uint8 / uint16 pixel can only equal an in-range integer nodata)
+__device__ __forceinline__ bool hb_valid_int(uint32_t v, const NoData &nd) { return !(nd.int_ok && (int)v == nd.ivalue); }
+
+// ---- storage dtype -> float32 (what the reference's reader does with out_dtype='float32') -------------------------
+template <typename T> __device__ __forceinline__ float hb_to_f32(T v) { return (float)v; }
+// exact small-integer -> float without the (slow) I2F pipe: 2^23 + v has v in its mantissa
+template <> __device__ __forceinline__ float hb_to_f32<uint8_t>(uint8_t v)
+{
+    return __uint_as_float(0x4B000000u | (uint32_t)v) - 8388608.0f;
+}
+template <> __device__ __forceinline__ float hb_to_f32<uint16_t>(uint16_t v)
+{
+    return __uint_as_float(0x4B000000u | (uint32_t)v) - 8388608.0f;
+}
+
+// ---- streaming loads / stores (read-once data: keep it out of L1) -------------------------------------------------
+__device__ __forceinline__ uint4 hb_ldg_stream16(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 hb_ldg_stream8(const void *p)
+{
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t hb_ldg_stream4(const void *p)
+{
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void hb_stg_stream16(void *p, float4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+static inline int hb_sm_count()
+{
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;
+    }
+    return sms;
+}

@@ -1,0 +1,250 @@
+"""
+RasterFuse for B200: the caller of the kernel-model path, for in-memory rasters.
+
+Mirrors the user-facing surface of ``homonim.RasterFuse`` that reaches the hot path
+(/root/reference/homonim/fuse.py:44-149 config factories, :295-408 ``_process_block`` / ``process``;
+raster_pair.py:194-225 ``proc_crs`` resolution, :280-296 processing windows): same constructor and ``process``
+signatures, config dictionaries, model selection (``SrcSpaceModel if proc_crs == src else RefSpaceModel``,
+fuse.py:376-377) and per-band fit -> apply flow (fuse.py:304-307).
+
+Out of scope: GeoTIFF file I/O, overviews, metadata, band matching by wavelength.  Sources
+and references are therefore :class:`~homonim_b200.raster_array.RasterArray` objects (host numpy or CUDA tensors)
+and ``process`` RETURNS the corrected (and optionally parameter) rasters instead of writing files.  The reference's
+block grid exists to bound host memory (raster_pair.py:227-269); on a 180 GB B200 a whole band is one block, which is
+also the reference's own result for ``max_block_mem`` large enough.
+"""
+import threading
+import warnings
+from multiprocessing import cpu_count
+from typing import Dict, List, Optional, Tuple, Union
+
+import numpy as np
+
+from homonim_b200.enums import Model, ProcCrs
+from homonim_b200.errors import ConfigWarning, ImageContentError, IoError
+from homonim_b200.geometry import Affine
+from homonim_b200.kernel_model import KernelModel, RefSpaceModel, SrcSpaceModel, overlap_for_kernel
+from homonim_b200.raster_array import RasterArray, is_tensor
+
+try:
+    import torch
+except ImportError:  # pragma: no cover
+    torch = None
+
+
+def _validate_threads(threads: int) -> int:
+    """ Reference utils.validate_threads (utils.py:156-164). """
+    _cpu_count = cpu_count()
+    threads = _cpu_count if threads == 0 else threads
+    if threads > _cpu_count:
+        raise ValueError(f"'threads' is limited to the number of processors ({_cpu_count})")
+    return threads
+
+
+def _band(ra: RasterArray, index: int) -> RasterArray:
+    """ Single-band (2D) RasterArray view of 1-based band ``index`` (bands are read singly, raster_pair.py:333-339). """
+    array = ra.array if ra.array.ndim == 2 else ra.array[index - 1]
+    return RasterArray(array, ra.crs, ra.transform, nodata=ra.nodata)
+
+
+def ref_window_for_src(src_ra: RasterArray, ref_ra: RasterArray) -> Tuple[int, int, int, int]:
+    """
+    (row_off, col_off, height, width) of the reference window covering the source extent, expanded to whole
+    reference pixels (raster_pair.py:292-296, utils.expand_window_to_grid) and clipped to the reference raster.
+    """
+    left, bottom, right, top = src_ra.bounds
+    inv = ~ref_ra.transform
+    c0, r0 = inv * (left, top)
+    c1, r1 = inv * (right, bottom)
+    col0, col1 = int(np.floor(min(c0, c1))), int(np.ceil(max(c0, c1)))
+    row0, row1 = int(np.floor(min(r0, r1))), int(np.ceil(max(r0, r1)))
+    col0, row0 = max(col0, 0), max(row0, 0)
+    col1, row1 = min(col1, ref_ra.width), min(row1, ref_ra.height)
+    if col1 <= col0 or row1 <= row0:
+        raise ImageContentError('The reference image does not overlap the source image.')
+    return row0, col0, row1 - row0, col1 - col0
+
+
+class RasterFuse:
+
+    def __init__(self, src: RasterArray, ref: RasterArray, proc_crs: ProcCrs = ProcCrs.auto,
+                 src_bands: Optional[List[int]] = None, ref_bands: Optional[List[int]] = None, force: bool = False):
+        """
+        Correct a source raster to surface reflectance by fusion with a reference (reference fuse.py:46-87,
+        matched_pair.py:38-83).  ``src`` / ``ref`` are RasterArrays on north-up grids of the same CRS; ``src_bands`` /
+        ``ref_bands`` are 1-based band indexes (default: all bands, matched in order).
+        """
+        if not isinstance(src, RasterArray) or not isinstance(ref, RasterArray):
+            raise NotImplementedError(
+                'homonim_b200.RasterFuse takes in-memory RasterArray objects; GeoTIFF file I/O is outside the B200 '
+                'kernel-model path (read the files with rasterio and wrap the arrays in RasterArray)'
+            )
+        if src.crs != ref.crs:
+            raise NotImplementedError('source and reference must share a CRS (CRS re-projection is out of scope)')
+        self._src, self._ref = src, ref
+        self._src_bands = list(src_bands) if src_bands is not None else list(range(1, src.count + 1))
+        self._ref_bands = list(ref_bands) if ref_bands is not None else list(range(1, ref.count + 1))
+        if len(self._ref_bands) < len(self._src_bands):
+            raise ImageContentError(
+                f'The reference has fewer bands ({len(self._ref_bands)}) than the source ({len(self._src_bands)}).'
+            )
+        self._ref_bands = self._ref_bands[:len(self._src_bands)]
+        self._proc_crs = self._resolve_proc_crs(src, ref, ProcCrs(proc_crs))
+        self._closed = True
+        self._corr_lock = threading.Lock()
+        self._param_lock = threading.Lock()
+
+    @staticmethod
+    def _resolve_proc_crs(src: RasterArray, ref: RasterArray, proc_crs: ProcCrs = ProcCrs.auto) -> ProcCrs:
+        """ Reference raster_pair.py:194-225. """
+        src_pixel_smaller = np.prod(np.abs(src.res)) <= np.prod(np.abs(ref.res))
+        if proc_crs == ProcCrs.auto:
+            proc_crs = ProcCrs.ref if src_pixel_smaller else ProcCrs.src
+        elif (proc_crs == ProcCrs.src and src_pixel_smaller) or (proc_crs == ProcCrs.ref and not src_pixel_smaller):
+            rec = ProcCrs.ref if src_pixel_smaller else ProcCrs.src
+            cmp_str = 'smaller' if src_pixel_smaller else 'larger'
+            warnings.warn(
+                f'proc_crs={rec} is recommended when the source pixel size is {cmp_str} than the reference.',
+                category=ConfigWarning
+            )
+        return proc_crs
+
+    # ---- context management (reference raster_pair.py:271-311) ----------------------------------------------------
+    @property
+    def proc_crs(self) -> ProcCrs:
+        return self._proc_crs
+
+    @property
+    def src_bands(self) -> Tuple[int, ...]:
+        return tuple(self._src_bands)
+
+    @property
+    def ref_bands(self) -> Tuple[int, ...]:
+        return tuple(self._ref_bands)
+
+    @property
+    def closed(self) -> bool:
+        return self._closed
+
+    def open(self):
+        self._closed = False
+
+    def close(self):
+        self._closed = True
+
+    def __enter__(self):
+        self.open()
+        return self
+
+    def __exit__(self, exc_type, exc_val, exc_tb):
+        self.close()
+
+    def _assert_open(self):
+        if self.closed:
+            raise IoError('The raster pair has not been opened: use `with RasterFuse(...) as fuse:` or `open()`')
+
+    # ---- configuration factories (reference fuse.py:89-149) -------------------------------------------------------
+    create_model_config = KernelModel.create_config
+
+    @staticmethod
+    def create_block_config(threads: int = 0, max_block_mem: float = 100) -> Dict:
+        return dict(threads=_validate_threads(threads), max_block_mem=max_block_mem)
+
+    @staticmethod
+    def create_out_profile(driver: str = 'GTiff', dtype: str = RasterArray.default_dtype,
+                           nodata: float = RasterArray.default_nodata, creation_options: Optional[Dict] = None) -> Dict:
+        creation_options = creation_options or dict(
+            tiled=True, blockxsize=512, blockysize=512, compress='deflate', interleave='band', photometric=None
+        )
+        return dict(driver=driver, dtype=dtype, nodata=nodata, **creation_options)
+
+    # ---- the hot path ----------------------------------------------------------------------------------------------
+    def _ref_block(self, band_i: int) -> RasterArray:
+        """ Reference band cropped to the window covering the source (raster_pair.py:292-296). """
+        ref_ra = _band(self._ref, self._ref_bands[band_i])
+        row0, col0, height, width = ref_window_for_src(self._src, ref_ra)
+        if (row0, col0, height, width) == (0, 0, ref_ra.height, ref_ra.width):
+            return ref_ra
+        array = ref_ra.array[row0:row0 + height, col0:col0 + width]
+        transform = ref_ra.transform * Affine.translation(col0, row0)
+        return RasterArray(array, ref_ra.crs, transform, nodata=ref_ra.nodata)
+
+    def _process_band(self, band_i: int, model: KernelModel) -> Tuple[RasterArray, RasterArray]:
+        """ One band of reference fuse.py:295-319 (``_process_block`` with a single block): read -> fit -> apply. """
+        src_ra = _band(self._src, self._src_bands[band_i])
+        ref_ra = self._ref_block(band_i)
+        param_ra = model.fit(src_ra, ref_ra)          # fuse.py:306
+        corr_ra = model.apply(src_ra, param_ra)       # fuse.py:307
+        return corr_ra, param_ra
+
+    def process(self, corr_filename=None, model: Model = KernelModel.default_model,
+                kernel_shape: Tuple[int, int] = KernelModel.default_kernel_shape, param_filename=None,
+                build_ovw: bool = True, overwrite: bool = False, model_config: Optional[Dict] = None,
+                out_profile: Optional[Dict] = None, block_config: Optional[Dict] = None
+                ) -> Tuple[RasterArray, Optional[RasterArray]]:
+        """
+        Correct the source to surface reflectance (reference fuse.py:321-408).  Same arguments as the reference;
+        ``corr_filename`` / ``param_filename`` only act as switches here (``param_filename is not None`` turns on the
+        R2 band and returns the parameter raster, as ``find_r2=param_filename is not None`` does at fuse.py:377).
+
+        Returns ``(corr_ra, param_ra or None)``: ``corr_ra`` has one band per source band on the source grid;
+        ``param_ra`` interleaves parameters band-major as the reference's parameter file does
+        (index = param_i * n_bands + band_i, fuse.py:315).
+        """
+        self._assert_open()
+        model_type = Model(model)
+        _ = overlap_for_kernel(kernel_shape)           # fuse.py:371 (single block per band: no overlap is needed)
+        model_config = RasterFuse.create_model_config(**(model_config or {}))
+        block_config = RasterFuse.create_block_config(**(block_config or {}))
+        out_profile = RasterFuse.create_out_profile(**(out_profile or {}))
+
+        model_cls = SrcSpaceModel if self.proc_crs == ProcCrs.src else RefSpaceModel          # fuse.py:376
+        kernel_model = model_cls(model_type, kernel_shape, find_r2=param_filename is not None, **model_config)
+
+        n_bands = len(self._src_bands)
+        corr_planes, param_planes = [], []
+        for band_i in range(n_bands):                  # bands outermost, raster_pair.py:379-381
+            corr_ra, param_ra = self._process_band(band_i, kernel_model)
+            corr_planes.append(_convert_dtype(corr_ra, out_profile['dtype'], out_profile['nodata']))
+            param_planes.append(param_ra)
+
+        stack = torch.stack if is_tensor(corr_planes[0]) else np.stack
+        corr = RasterArray(stack(corr_planes), self._src.crs, self._src.transform, nodata=out_profile['nodata'])
+        params = None
+        if param_filename is not None:
+            n_params = param_planes[0].count
+            planes = [param_planes[b].array[p] for p in range(n_params) for b in range(n_bands)]
+            params = RasterArray(stack(planes), param_planes[0].crs, param_planes[0].transform, nodata=float('nan'))
+        return corr, params
+
+
+def _convert_dtype(ra: RasterArray, dtype: str, nodata):
+    """
+    Output dtype conversion of ``RasterArray._convert_array_dtype`` (raster_array.py:353-387): round half-to-even and
+    clip when going to an integer type, then substitute the output nodata.  float32 / NaN output is a no-op.
+    """
+    array = ra.array
+    is_nan_nd = nodata is not None and isinstance(nodata, float) and np.isnan(nodata)
+    if dtype in ('float32', None) and (nodata is None or is_nan_nd):
+        return array
+    if is_tensor(array):
+        mask = ~torch.isnan(array)
+        out = array
+        tdtype = getattr(torch, dtype)
+        if not tdtype.is_floating_point:
+            info = torch.iinfo(tdtype)
+            out = torch.clamp(torch.round(out), info.min, info.max)
+        out = torch.nan_to_num(out, nan=0.0).to(tdtype)
+        if nodata is not None:
+            out[~mask] = nodata
+        return out
+    mask = ~np.isnan(array)
+    out = array
+    if np.issubdtype(np.dtype(dtype), np.integer):
+        info = np.iinfo(dtype)
+        out = np.clip(np.round(out), info.min, info.max)
+    with np.errstate(invalid='ignore'):
+        out = np.nan_to_num(out, nan=0.0).astype(dtype)
+    if nodata is not None:
+        out[~mask] = nodata
+    return out

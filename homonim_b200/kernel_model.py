@@ -1,0 +1,409 @@
+"""
+KernelModel / RefSpaceModel / SrcSpaceModel for B200: the host-side mirror of homonim's kernel-model API.
+
+Same class names, constructor arguments, config keys, return layouts and exceptions as
+/root/reference/homonim/kernel_model.py (KernelModel :35-463, RefSpaceModel :466-503, SrcSpaceModel :506-535), so that
+``RasterFuse.process`` (fuse.py:376-377, 304-307) and the reference's tests can use these classes unchanged.  All
+pixel arithmetic runs in the sm_100a CUDA library behind ``include/homonim_b200.h`` (``_native.py``); there is no
+CPU implementation here and none is fallen back to.
+
+Differences from the reference, all deliberate:
+  * ``fit`` does not mutate its inputs (the reference zeroes invalid pixels in place, kernel_model.py:246-247).
+  * rasters may be host numpy arrays (copied to the device and back) or torch CUDA tensors (stay on the device);
+    uint8 / uint16 sources may be passed in their stored dtype.
+  * ``RefSpaceModel.apply`` never materialises the up-sampled parameters: up-sampling and gain*src+offset are one
+    kernel.
+  * only the default resampling pair (average down / cubic_spline up) plus nearest are implemented natively; other
+    ``downsampling`` / ``upsampling`` choices raise NotImplementedError rather than silently using something else.
+"""
+import threading
+import warnings
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from homonim_b200 import _native
+from homonim_b200.enums import Model, Resampling
+from homonim_b200.errors import ConfigWarning
+from homonim_b200.geometry import grid_map
+from homonim_b200.raster_array import RasterArray, is_tensor
+
+try:
+    import torch
+except ImportError:  # pragma: no cover
+    torch = None
+
+NAN = float('nan')
+_DTYPE_CODES = {'uint8': _native.HB_U8, 'uint16': _native.HB_U16, 'float32': _native.HB_F32}
+_MODEL_CODES = {
+    Model.gain: _native.HB_MODEL_GAIN,
+    Model.gain_blk_offset: _native.HB_MODEL_GAIN_BLK_OFFSET,
+    Model.gain_offset: _native.HB_MODEL_GAIN_OFFSET,
+}
+MAX_SEARCH_DISTANCE = 100.0   # rasterio.fill.fillnodata default used by the reference (kernel_model.py:366)
+
+
+def validate_kernel_shape(kernel_shape: Tuple[int, int], model: Model = Model.gain_blk_offset) -> Tuple[int, int]:
+    """ Reference utils.validate_kernel_shape (utils.py:104-133): same checks, messages and warning. """
+    kernel_shape = np.array(kernel_shape).astype(int)
+    if not np.all(np.mod(kernel_shape, 2) == 1):
+        raise ValueError('`kernel_shape` must be odd in both dimensions.')
+    if model == Model.gain_offset:
+        if np.prod(kernel_shape) < 2:
+            raise ValueError('`kernel_shape` area should contain at least 2 elements for the gain-offset model.')
+        elif np.prod(kernel_shape) < 25:
+            warnings.warn(
+                'A `kernel_shape` of at least 25 elements is recommended for the gain-offset model.',
+                category=ConfigWarning
+            )
+    if not np.all(kernel_shape >= 1):
+        raise ValueError('`kernel_shape` must be a minimum of one in both dimensions.')
+    return tuple(int(k) for k in kernel_shape)
+
+
+def overlap_for_kernel(kernel_shape: Tuple[int, int]) -> Tuple[int, int]:
+    """ Reference utils.overlap_for_kernel (utils.py:136-153): block overlap = ceil(kernel / 2). """
+    kernel_shape = np.array(kernel_shape).astype(int)
+    return tuple(int(v) for v in np.ceil(kernel_shape / 2).astype('int'))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# device plumbing (torch owns device memory and streams; the kernels are ours)
+# ---------------------------------------------------------------------------------------------------------------------
+def _require_torch():
+    if torch is None:
+        raise _native.NativeLibraryError('torch is required for device memory management')
+    _native.require_device()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _nodata_args(nodata) -> Tuple[int, float]:
+    return (0, 0.0) if nodata is None else (1, float(nodata))
+
+
+def _to_device(array, device=None):
+    """ Contiguous CUDA tensor for a numpy array / tensor; float64 is narrowed to float32, other dtypes are kept. """
+    if is_tensor(array):
+        t = array if array.is_cuda else array.to(device or 'cuda', non_blocking=True)
+    else:
+        array = np.ascontiguousarray(array)
+        if array.dtype == np.float64:
+            array = array.astype('float32')
+        elif array.dtype == np.bool_:
+            array = array.astype('uint8')
+        t = torch.from_numpy(array).to(device or 'cuda', non_blocking=True)
+    if t.dtype == torch.float64:
+        t = t.float()
+    return t.contiguous()
+
+
+def _plane_code(t) -> int:
+    name = str(t.dtype).replace('torch.', '')
+    if name not in _DTYPE_CODES:
+        raise TypeError(f'unsupported raster dtype {name!r}: expected uint8, uint16 or float32')
+    return _DTYPE_CODES[name]
+
+
+def _as_f32_plane(t, nodata):
+    """ float32 view / copy of a plane for the same-grid kernels (integer planes are widened on the device). """
+    if t.dtype == torch.float32:
+        return t
+    return t.to(torch.float32)
+
+
+def _as_nan_nodata_f32(t, nodata):
+    """ float32 plane whose nodata is NaN (input convention of the cubic-spline up-sampler). """
+    f = t.to(torch.float32) if t.dtype != torch.float32 else t
+    if nodata is None or (isinstance(nodata, float) and np.isnan(nodata)):
+        return f
+    return torch.where(f == float(nodata), torch.full_like(f, NAN), f)
+
+
+def _result(array_dev, like_device: bool):
+    """ Return results where the caller's rasters live. """
+    if like_device:
+        return array_dev
+    return array_dev.cpu().numpy()
+
+
+class KernelModel:
+    default_kernel_shape = (5, 5)           # reference kernel_model.py:37
+    default_model = Model.gain_blk_offset   # reference kernel_model.py:38
+
+    def __init__(self, model: Model = default_model, kernel_shape: Tuple[int, int] = default_kernel_shape,
+                 find_r2: bool = False, **kwargs):
+        self._model = Model(model)
+        self._kernel_shape = validate_kernel_shape(kernel_shape, model=model)
+        self._find_r2 = find_r2
+        config = self.create_config(**kwargs)     # unknown keys raise TypeError, as in the reference
+        self._r2_inpaint_thresh: Optional[float] = config['r2_inpaint_thresh']
+        self._mask_partial: bool = config['mask_partial']
+        self._downsampling = config['downsampling']
+        self._upsampling = config['upsampling']
+        self._lock = threading.Lock()
+
+    @property
+    def model(self) -> Model:
+        return self._model
+
+    @property
+    def kernel_shape(self) -> Tuple[int, int]:
+        return tuple(self._kernel_shape)
+
+    @property
+    def find_r2(self) -> bool:
+        return self._find_r2
+
+    @staticmethod
+    def create_config(r2_inpaint_thresh: float = 0.25, mask_partial: bool = False,
+                      downsampling=Resampling.average, upsampling=Resampling.cubic_spline) -> Dict:
+        """ Reference kernel_model.py:98-136: same keys and defaults. """
+        return dict(r2_inpaint_thresh=r2_inpaint_thresh, mask_partial=mask_partial, downsampling=downsampling,
+                    upsampling=upsampling)
+
+    def _get_resampling(self, from_res, to_res) -> Resampling:
+        """ Reference kernel_model.py:138-140. """
+        choice = self._downsampling if np.prod(np.abs(from_res)) <= np.prod(np.abs(to_res)) else self._upsampling
+        return Resampling.coerce(choice)
+
+    # ---- native steps on device tensors ---------------------------------------------------------------------------
+    def _wants_r2(self) -> bool:
+        return bool(self._find_r2 or (self._model == Model.gain_offset and self._r2_inpaint_thresh is not None))
+
+    def _fit_planes(self, src_t, src_nodata, ref_t, ref_nodata):
+        """ Same-grid fit of two float32 device planes -> float32 [2|3, H, W] parameter tensor. """
+        lib = _native.lib()
+        h, w = int(src_t.shape[-2]), int(src_t.shape[-1])
+        src_t, ref_t = _as_f32_plane(src_t, src_nodata).contiguous(), _as_f32_plane(ref_t, ref_nodata).contiguous()
+        want_r2 = self._wants_r2()
+        inpaint = self._model == Model.gain_offset and self._r2_inpaint_thresh is not None
+        params = torch.empty((3 if want_r2 else 2, h, w), dtype=torch.float32, device=src_t.device)
+        s_has, s_nd = _nodata_args(src_nodata)
+        r_has, r_nd = _nodata_args(ref_nodata)
+        stream = _stream()
+        norm_ptr = None
+        if self._model == Model.gain_blk_offset:
+            norm = torch.empty(2, dtype=torch.float64, device=src_t.device)
+            ws_bytes = lib.hb_block_norm_workspace_bytes(h * w)
+            work = torch.empty(ws_bytes, dtype=torch.uint8, device=src_t.device)
+            _native.check(lib.hb_block_norm(src_t.data_ptr(), s_has, s_nd, ref_t.data_ptr(), r_has, r_nd, h * w,
+                                            norm.data_ptr(), work.data_ptr(), ws_bytes, stream), 'hb_block_norm')
+            norm_ptr = norm.data_ptr()
+        sums = torch.empty((3, h, w), dtype=torch.float32, device=src_t.device) if inpaint else None
+        kh, kw = self._kernel_shape
+        _native.check(lib.hb_fit_same_grid(src_t.data_ptr(), s_has, s_nd, ref_t.data_ptr(), r_has, r_nd, h, w,
+                                           _MODEL_CODES[self._model], kh, kw, int(want_r2), norm_ptr,
+                                           params.data_ptr(), sums.data_ptr() if inpaint else None, stream),
+                      'hb_fit_same_grid')
+        if inpaint:
+            ws_bytes = lib.hb_inpaint_workspace_bytes(h, w)
+            work = torch.empty(ws_bytes, dtype=torch.uint8, device=src_t.device)
+            _native.check(lib.hb_inpaint_refit(params.data_ptr(), sums.data_ptr(), h, w,
+                                               float(self._r2_inpaint_thresh), MAX_SEARCH_DISTANCE, work.data_ptr(),
+                                               ws_bytes, stream), 'hb_inpaint_refit')
+        return params
+
+    def _full_coverage_mask(self, in_mask_t, in_transform, params_t, param_transform):
+        """ Reference kernel_model.py:375-409 on device: uint8 [hp, wp] mask on the parameter grid. """
+        lib = _native.lib()
+        hp, wp = int(params_t.shape[-2]), int(params_t.shape[-1])
+        hi, wi = int(in_mask_t.shape[-2]), int(in_mask_t.shape[-1])
+        gm = grid_map(in_transform, param_transform)          # param grid -> in_mask grid
+        out = torch.empty((hp, wp), dtype=torch.uint8, device=params_t.device)
+        work = torch.empty((hp, wp), dtype=torch.uint8, device=params_t.device)
+        kh, kw = self._kernel_shape
+        _native.check(lib.hb_full_coverage_mask(in_mask_t.data_ptr(), hi, wi, params_t.data_ptr(), hp, wp, gm.sx,
+                                                gm.ox, gm.sy, gm.oy, kh, kw, out.data_ptr(), work.data_ptr(),
+                                                _stream()), 'hb_full_coverage_mask')
+        return out
+
+    @staticmethod
+    def _valid_mask_u8(t, nodata):
+        lib = _native.lib()
+        has, nd = _nodata_args(nodata)
+        mask = torch.empty(tuple(t.shape[-2:]), dtype=torch.uint8, device=t.device)
+        _native.check(lib.hb_valid_mask(t.data_ptr(), _plane_code(t), t.numel(), has, nd, mask.data_ptr(), _stream()),
+                      'hb_valid_mask')
+        return mask
+
+    # ---- public API (reference kernel_model.py:411-463) -----------------------------------------------------------
+    def fit(self, src_ra: RasterArray, ref_ra: RasterArray) -> RasterArray:
+        if (ref_ra.transform != src_ra.transform) or (ref_ra.shape != src_ra.shape):
+            raise ValueError("'ref_ra' and 'src_ra' must have the same CRS, transform and shape")
+        _require_torch()
+        on_device = src_ra.is_device and ref_ra.is_device
+        src_t, ref_t = _to_device(src_ra.array), _to_device(ref_ra.array)
+        params = self._fit_planes(src_t, src_ra.nodata, ref_t, ref_ra.nodata)
+        return RasterArray(_result(params, on_device), src_ra.crs, src_ra.transform, nodata=NAN)
+
+    def apply(self, src_ra: RasterArray, param_ra: RasterArray) -> RasterArray:
+        if (param_ra.transform != src_ra.transform) or (param_ra.shape != src_ra.shape):
+            raise ValueError("'param_ra' and 'src_ra' must have the same CRS, transform and shape")
+        _require_torch()
+        on_device = src_ra.is_device and param_ra.is_device
+        src_t, par_t = _to_device(src_ra.array), _to_device(param_ra.array)
+        corr = self._apply_planes(src_t, src_ra.nodata, par_t, mask_src=False)
+        return RasterArray(_result(corr, on_device), param_ra.crs, param_ra.transform, nodata=param_ra.nodata)
+
+    @staticmethod
+    def _apply_planes(src_t, src_nodata, par_t, mask_src: bool):
+        lib = _native.lib()
+        if par_t.ndim != 3 or par_t.shape[0] < 2 or par_t.dtype != torch.float32:
+            raise ValueError("'param_ra' must hold at least 2 float32 bands (gain, offset)")
+        h, w = int(src_t.shape[-2]), int(src_t.shape[-1])
+        corr = torch.empty((h, w), dtype=torch.float32, device=src_t.device)
+        has, nd = _nodata_args(src_nodata)
+        _native.check(lib.hb_apply_same_grid(src_t.data_ptr(), _plane_code(src_t), has, nd, int(mask_src),
+                                             par_t.data_ptr(), h, w, corr.data_ptr(), _stream()),
+                      'hb_apply_same_grid')
+        return corr
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# resampling between grids (reference RasterArray.reproject, raster_array.py:526-578)
+# ---------------------------------------------------------------------------------------------------------------------
+def _downsample_average(src_t, src_transform, src_nodata, dst_shape, dst_transform):
+    """ float32 [hd, wd] (NaN nodata) average of a uint8 / uint16 / float32 plane. """
+    lib = _native.lib()
+    gm = grid_map(src_transform, dst_transform)
+    hs, ws = int(src_t.shape[-2]), int(src_t.shape[-1])
+    hd, wd = int(dst_shape[0]), int(dst_shape[1])
+    dst = torch.empty((hd, wd), dtype=torch.float32, device=src_t.device)
+    has, nd = _nodata_args(src_nodata)
+    _native.check(lib.hb_downsample_average(src_t.data_ptr(), _plane_code(src_t), hs, ws, has, nd, dst.data_ptr(), hd,
+                                            wd, gm.sx, gm.ox, gm.sy, gm.oy, _stream()), 'hb_downsample_average')
+    return dst
+
+
+def _resample_up(src_t, src_transform, src_nodata, dst_shape, dst_transform, method=_native.HB_UP_CUBIC_SPLINE):
+    """ float32 [nb, hd, wd] (NaN nodata) up-sampling of 1 or 2 float32 bands. """
+    lib = _native.lib()
+    gm = grid_map(src_transform, dst_transform)
+    squeeze = src_t.ndim == 2
+    src3 = src_t[None] if squeeze else src_t
+    if method == _native.HB_UP_CUBIC_SPLINE:
+        src3 = _as_nan_nodata_f32(src3, src_nodata).contiguous()
+        has, nd = 1, NAN
+    else:
+        src3 = src3.to(torch.float32).contiguous()
+        has, nd = _nodata_args(src_nodata)
+    nb, hs, ws = (int(v) for v in src3.shape)
+    hd, wd = int(dst_shape[0]), int(dst_shape[1])
+    dst = torch.empty((nb, hd, wd), dtype=torch.float32, device=src_t.device)
+    for b0 in range(0, nb, 2):     # the native up-sampler takes 1 or 2 bands per call
+        nbc = min(2, nb - b0)
+        _native.check(lib.hb_resample_up(src3[b0:b0 + nbc].data_ptr(), nbc, hs, ws, has, nd, dst[b0:].data_ptr(), hd,
+                                         wd, gm.sx, gm.ox, gm.sy, gm.oy, method, _stream()), 'hb_resample_up')
+    return dst[0] if squeeze else dst
+
+
+def _resample_plane(t, transform, nodata, dst_shape, dst_transform, resampling: Resampling):
+    """ Resample one plane to a float32, NaN-nodata plane on the destination grid. """
+    if resampling == Resampling.average:
+        return _downsample_average(t, transform, nodata, dst_shape, dst_transform)
+    if resampling == Resampling.cubic_spline:
+        return _resample_up(t, transform, nodata, dst_shape, dst_transform, _native.HB_UP_CUBIC_SPLINE)
+    if resampling == Resampling.nearest:
+        return _resample_up(t, transform, nodata, dst_shape, dst_transform, _native.HB_UP_NEAREST)
+    raise NotImplementedError(
+        f'resampling {resampling.value!r} has no sm_100a kernel yet (available: average, cubic_spline, nearest)'
+    )
+
+
+def reproject_raster(ra: RasterArray, crs=None, transform=None, shape=None, nodata=NAN, dtype='float32',
+                     resampling='average') -> RasterArray:
+    """ GPU stand-in for RasterArray.reproject on axis-aligned grids of one CRS (raster_array.py:526-578). """
+    if transform is not None and shape is None:
+        raise ValueError('If `transform` is specified, `shape` is required')
+    if crs is not None and crs != ra.crs:
+        raise NotImplementedError('re-projection between different CRSs is outside the B200 kernel-model path')
+    _require_torch()
+    transform = ra.transform if transform is None else transform
+    shape = ra.shape if shape is None else shape
+    resampling = Resampling.coerce(resampling)
+    src_t = _to_device(ra.array)
+    planes = [src_t] if src_t.ndim == 2 else list(src_t)
+    out = torch.stack([_resample_plane(p.contiguous(), ra.transform, ra.nodata, shape, transform, resampling)
+                       for p in planes])
+    if nodata is not None and not np.isnan(nodata):
+        out = torch.where(torch.isnan(out), torch.full_like(out, float(nodata)), out)
+    elif nodata is None:
+        out = torch.nan_to_num(out, nan=0.0)
+    if dtype not in (None, 'float32'):
+        out = out.to(getattr(torch, str(dtype)))
+    out = out[0] if src_t.ndim == 2 else out
+    return RasterArray(_result(out, ra.is_device), ra.crs, transform, nodata=nodata)
+
+
+class RefSpaceModel(KernelModel):
+    """ Fit on the reference grid, apply on the source grid (reference kernel_model.py:466-503). """
+
+    def fit(self, src_ra: RasterArray, ref_ra: RasterArray) -> RasterArray:
+        _require_torch()
+        on_device = src_ra.is_device and ref_ra.is_device
+        resampling = self._get_resampling(src_ra.res, ref_ra.res)                            # :478
+        src_t, ref_t = _to_device(src_ra.array), _to_device(ref_ra.array)
+        src_ds = _resample_plane(src_t, src_ra.transform, src_ra.nodata, ref_ra.shape, ref_ra.transform,
+                                 resampling)                                                 # :480
+        params = self._fit_planes(src_ds, NAN, ref_t, ref_ra.nodata)                         # :482
+        return RasterArray(_result(params, on_device), ref_ra.crs, ref_ra.transform, nodata=NAN)
+
+    def apply(self, src_ra: RasterArray, param_ra: RasterArray) -> RasterArray:
+        _require_torch()
+        lib = _native.lib()
+        on_device = src_ra.is_device and param_ra.is_device
+        src_t, par_t = _to_device(src_ra.array), _to_device(param_ra.array)
+        if par_t.ndim != 3 or par_t.shape[0] < 2 or par_t.dtype != torch.float32:
+            raise ValueError("'param_ra' must hold at least 2 float32 bands (gain, offset)")
+        par2 = par_t[:2].contiguous()                                                        # :487
+        resampling = self._get_resampling(param_ra.res, src_ra.res)                          # :489
+        hs, ws = src_ra.shape
+        cover = None
+        if self._mask_partial:
+            src_mask = self._valid_mask_u8(src_t, src_ra.nodata)
+            cover = self._full_coverage_mask(src_mask, src_ra.transform, par2, param_ra.transform)   # :495
+        if resampling == Resampling.cubic_spline:
+            # fused up-sample + apply (:491, :497-503): the up-sampled parameters never reach memory
+            gm = grid_map(param_ra.transform, src_ra.transform)       # source grid -> param grid
+            hp, wp = int(par2.shape[-2]), int(par2.shape[-1])
+            corr = torch.empty((hs, ws), dtype=torch.float32, device=src_t.device)
+            has, nd = _nodata_args(src_ra.nodata)
+            _native.check(lib.hb_upsample_apply(src_t.data_ptr(), _plane_code(src_t), hs, ws, has, nd,
+                                                par2.data_ptr(), hp, wp, gm.sx, gm.ox, gm.sy, gm.oy,
+                                                cover.data_ptr() if cover is not None else None, corr.data_ptr(),
+                                                _stream()), 'hb_upsample_apply')
+        else:
+            # parameters finer than (or as fine as) the source: resample them, then the same-grid apply
+            par_us = torch.stack([_resample_plane(par2[b], param_ra.transform, NAN, (hs, ws), src_ra.transform,
+                                                  resampling) for b in range(2)])
+            if cover is not None:
+                cover_us = _resample_up(cover.to(torch.float32), param_ra.transform, None, (hs, ws),
+                                        src_ra.transform, _native.HB_UP_NEAREST)
+                par_us[:, ~(cover_us > 0)] = NAN                                             # :497-498
+                corr = self._apply_planes(src_t, src_ra.nodata, par_us, mask_src=False)
+            else:
+                corr = self._apply_planes(src_t, src_ra.nodata, par_us, mask_src=True)       # :500
+        return RasterArray(_result(corr, on_device), src_ra.crs, src_ra.transform, nodata=NAN)
+
+
+class SrcSpaceModel(KernelModel):
+    """ Fit and apply on the source grid (reference kernel_model.py:506-535). """
+
+    def fit(self, src_ra: RasterArray, ref_ra: RasterArray) -> RasterArray:
+        _require_torch()
+        on_device = src_ra.is_device and ref_ra.is_device
+        resampling = self._get_resampling(ref_ra.res, src_ra.res)                            # :518
+        src_t, ref_t = _to_device(src_ra.array), _to_device(ref_ra.array)
+        ref_us = _resample_plane(ref_t, ref_ra.transform, ref_ra.nodata, src_ra.shape, src_ra.transform,
+                                 resampling)                                                 # :520
+        params = self._fit_planes(src_t, src_ra.nodata, ref_us, NAN)                         # :524
+        if self._mask_partial:
+            ref_mask = self._valid_mask_u8(ref_t, ref_ra.nodata)
+            cover = self._full_coverage_mask(ref_mask, ref_ra.transform, params[:2].contiguous(),
+                                             src_ra.transform)                               # :528-530
+            params[:, cover == 0] = NAN                                                      # :531
+        # (:533 -- re-masking with the source mask is a no-op: the fit already wrote NaN wherever src is invalid)
+        return RasterArray(_result(params, on_device), src_ra.crs, src_ra.transform, nodata=NAN)

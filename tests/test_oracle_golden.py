@@ -1,0 +1,53 @@
+"""
+CPU tier: the oracle port (oracle/kernel_model_np.py) is pinned BIT-FOR-BIT against the golden vectors that
+oracle/make_golden.py generated from the unmodified reference (/root/reference/homonim/kernel_model.py).
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+from oracle import kernel_model_np as kmnp
+
+
+def _same(a, b):
+    return a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize('name', golden_names('same'))
+def test_same_grid_port_matches_reference(name):
+    meta, g = load_golden(name)
+    params = kmnp.fit_same_grid(g['src'], meta['src_nodata'], g['ref'], meta['ref_nodata'], meta['model'],
+                                meta['kernel_shape'], meta['find_r2'], meta['r2_inpaint_thresh'])
+    assert _same(params, g['params'])
+    corr = kmnp.apply_same_grid(g['src'], params)
+    assert _same(corr, g['corr'])
+
+
+@pytest.mark.parametrize('name', golden_names('refspace'))
+def test_refspace_port_matches_reference(name):
+    meta, g = load_golden(name)
+    params, param_tf, corr = kmnp.fuse_band_blocks(
+        g['src'], meta['src_transform'], meta['src_nodata'], g['ref'], meta['ref_transform'], meta['ref_nodata'],
+        meta['model'], meta['kernel_shape'], 'ref', meta['find_r2'], meta['r2_inpaint_thresh'], meta['mask_partial'])
+    assert np.allclose(param_tf, meta['param_transform'])
+    assert _same(params, g['params'])
+    assert _same(corr.astype('float32'), g['corr'].astype('float32'))
+
+
+@pytest.mark.parametrize('name', golden_names('srcspace'))
+def test_srcspace_port_matches_reference(name):
+    meta, g = load_golden(name)
+    params, _, corr = kmnp.fuse_band_blocks(
+        g['src'], meta['src_transform'], meta['src_nodata'], g['ref'], meta['ref_transform'], meta['ref_nodata'],
+        meta['model'], meta['kernel_shape'], 'src', meta['find_r2'], meta['r2_inpaint_thresh'], meta['mask_partial'])
+    assert _same(params, g['params'])
+    assert _same(corr, g['corr'])
+
+
+def test_golden_fixture_inventory():
+    # every reference model, R2 on/off, in-painting, all dtypes and both processing grids are pinned
+    names = golden_names()
+    assert len(names) >= 26
+    for token in ('gain_k', 'gain-blk-offset', 'gain-offset', '_r2', '_inp', 'uint8', 'uint16', 'float32', 'partial',
+                  'refspace', 'srcspace', 'conftest'):
+        assert any(token in n for n in names), token
