@@ -122,12 +122,13 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
         }
     };
 
+    const bool single_row = (g.kh == 1), single_col = (g.kw == 1);
     const long e_first = y0 - hh, e_last = y1 - 1 + hh;
     for (long e = e_first; e <= e_last; e++) {
         // ---- vertical running sums: entering row e, leaving row e - kh ---------------------------------------------
         const long l = e - g.kh;
         const bool has_e = (e >= 0) && (e < g.h);
-        const bool has_l = (l >= e_first) && (l >= 0) && (l < g.h);
+        const bool has_l = !single_row && (l >= e_first) && (l >= 0) && (l < g.h);
         float se[C], re[C], sl[C], rl[C];
         if (has_e) load_row(e, se, re);
         if (has_l) load_row(l, sl, rl);
@@ -139,9 +140,19 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
                 ve = col_in[i] && hb_valid(se[i], nd_s) && hb_valid(re[i], nd_r);
                 pixel_terms<NQ, NORM>(se[i], re[i], ve, n0, n1, q, cnt);
                 ve = cnt != 0;
+                if (single_row) {                                    // kh == 1: the window IS this row (exact)
 #pragma unroll
-                for (int k = 0; k < NQ; k++) V[i][k] = __dadd_rn(V[i][k], q[k]);
-                VN[i] += cnt;
+                    for (int k = 0; k < NQ; k++) V[i][k] = q[k];
+                    VN[i] = cnt;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NQ; k++) V[i][k] = __dadd_rn(V[i][k], q[k]);
+                    VN[i] += cnt;
+                }
+            } else if (single_row) {
+#pragma unroll
+                for (int k = 0; k < NQ; k++) V[i][k] = 0.0;
+                VN[i] = 0;
             }
             vring[i] = (vring[i] << 1) | (ve ? 1ull : 0ull);
             if (has_l) {
@@ -158,6 +169,8 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
         const int buf = (int)(y & 1);
 
         // ---- horizontal window sums: prefix over this thread's columns, warp scan of thread totals ----------------
+        // (kw == 1: the window sum is the column sum itself -- exact, and no exchange is needed)
+        if (!single_col) {
         double pre[C][NQ];
         int pren[C];
 #pragma unroll
@@ -201,6 +214,7 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
             if (HAS_N) s_n[buf][t * C + i] = excl_n + pren[i];
         }
         __syncthreads();        // (double-buffered: the next row writes the other buffer, so one barrier per row)
+        }
 
         if (!out_thread) continue;
         float o_gain[C], o_off[C], o_r2[C], o_rs[C], o_ss[C], o_n[C];
@@ -211,18 +225,24 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
             const int wa = a / WCOLS, wb = (b >= 0) ? b / WCOLS : 0;
             double W[NQ];
             int N = 0;
+            if (single_col) {
 #pragma unroll
-            for (int k = 0; k < NQ; k++) {
-                double v = s_q[buf][k][a];
-                for (int ww = wb; ww < wa; ww++) v += s_tot[buf][k][ww];
-                if (b >= 0) v -= s_q[buf][k][b];
-                W[k] = v;
-            }
-            if (HAS_N) {
-                int v = s_n[buf][a];
-                for (int ww = wb; ww < wa; ww++) v += s_ntot[buf][ww];
-                if (b >= 0) v -= s_n[buf][b];
-                N = v;
+                for (int k = 0; k < NQ; k++) W[k] = V[i][k];
+                N = VN[i];
+            } else {
+#pragma unroll
+                for (int k = 0; k < NQ; k++) {
+                    double v = s_q[buf][k][a];
+                    for (int ww = wb; ww < wa; ww++) v += s_tot[buf][k][ww];
+                    if (b >= 0) v -= s_q[buf][k][b];
+                    W[k] = v;
+                }
+                if (HAS_N) {
+                    int v = s_n[buf][a];
+                    for (int ww = wb; ww < wa; ww++) v += s_ntot[buf][ww];
+                    if (b >= 0) v -= s_n[buf][b];
+                    N = v;
+                }
             }
             const bool mask = ((vring[i] >> hh) & 1ull) != 0ull;     // centre pixel valid in both images
 

@@ -408,10 +408,17 @@ upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ 
         if (cy == g.hp) cy--;
         bool cok = (srcy >= 0.0) && cy >= 0 && cy < g.hp && col_inside;
         if (cok) {
-            const int j = (int)(cy - (ky - 1));                   // cy is ky or ky + 1 -> tap row 1 or 2
-            bool any = (j == 1) ? tap_ok[0][1] : tap_ok[0][2];
-            if (NB > 1) any = any || ((j == 1) ? tap_ok[1][1] : tap_ok[1][2]);
-            cok = any && (j == 1 || j == 2);
+            // cy is ky or ky + 1 (tap row 1 or 2), or ky - 1 (tap row 0) when clamped at the bottom edge
+            const int j = (int)(cy - (ky - 1));
+            bool any = false;
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                if (jj == j) {
+                    any = tap_ok[0][jj];
+                    if (NB > 1) any = any || tap_ok[1][jj];
+                }
+            }
+            cok = any;
             if (cok && cover != nullptr) cok = cover[cy * g.wp + my_col] != 0;
         }
         s_cokA[buf * ncols + t] = cok ? 1 : 0;

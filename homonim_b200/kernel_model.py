@@ -80,6 +80,48 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class KernelTimer:
+    """
+    Optional per-launch device timing of the C-ABI calls (used by bench.py for the roofline numbers): while active,
+    every native call is bracketed by CUDA events on the launching stream.  ``results()`` synchronises and returns
+    {entry point: [milliseconds per call]}.
+    """
+    active: Optional['KernelTimer'] = None
+
+    def __init__(self):
+        self._events = []
+
+    def __enter__(self):
+        KernelTimer.active = self
+        return self
+
+    def __exit__(self, *exc):
+        KernelTimer.active = None
+
+    def record(self, name, fn, args):
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        rc = fn(*args)
+        end.record()
+        self._events.append((name, start, end))
+        return rc
+
+    def results(self) -> Dict[str, list]:
+        torch.cuda.synchronize()
+        out: Dict[str, list] = {}
+        for name, start, end in self._events:
+            out.setdefault(name, []).append(start.elapsed_time(end))
+        return out
+
+
+def _call(name: str, *args):
+    """ Invoke C-ABI entry point ``name`` and raise on failure. """
+    fn = getattr(_native.lib(), name)
+    timer = KernelTimer.active
+    rc = timer.record(name, fn, args) if timer is not None else fn(*args)
+    _native.check(rc, name)
+
+
 def _nodata_args(nodata) -> Tuple[int, float]:
     return (0, 0.0) if nodata is None else (1, float(nodata))
 
@@ -189,21 +231,20 @@ class KernelModel:
             norm = torch.empty(2, dtype=torch.float64, device=src_t.device)
             ws_bytes = lib.hb_block_norm_workspace_bytes(h * w)
             work = torch.empty(ws_bytes, dtype=torch.uint8, device=src_t.device)
-            _native.check(lib.hb_block_norm(src_t.data_ptr(), s_has, s_nd, ref_t.data_ptr(), r_has, r_nd, h * w,
-                                            norm.data_ptr(), work.data_ptr(), ws_bytes, stream), 'hb_block_norm')
+            _call('hb_block_norm', src_t.data_ptr(), s_has, s_nd, ref_t.data_ptr(), r_has, r_nd, h * w,
+                                            norm.data_ptr(), work.data_ptr(), ws_bytes, stream)
             norm_ptr = norm.data_ptr()
         sums = torch.empty((3, h, w), dtype=torch.float32, device=src_t.device) if inpaint else None
         kh, kw = self._kernel_shape
-        _native.check(lib.hb_fit_same_grid(src_t.data_ptr(), s_has, s_nd, ref_t.data_ptr(), r_has, r_nd, h, w,
+        _call('hb_fit_same_grid', src_t.data_ptr(), s_has, s_nd, ref_t.data_ptr(), r_has, r_nd, h, w,
                                            _MODEL_CODES[self._model], kh, kw, int(want_r2), norm_ptr,
-                                           params.data_ptr(), sums.data_ptr() if inpaint else None, stream),
-                      'hb_fit_same_grid')
+                                           params.data_ptr(), sums.data_ptr() if inpaint else None, stream)
         if inpaint:
             ws_bytes = lib.hb_inpaint_workspace_bytes(h, w)
             work = torch.empty(ws_bytes, dtype=torch.uint8, device=src_t.device)
-            _native.check(lib.hb_inpaint_refit(params.data_ptr(), sums.data_ptr(), h, w,
+            _call('hb_inpaint_refit', params.data_ptr(), sums.data_ptr(), h, w,
                                                float(self._r2_inpaint_thresh), MAX_SEARCH_DISTANCE, work.data_ptr(),
-                                               ws_bytes, stream), 'hb_inpaint_refit')
+                                               ws_bytes, stream)
         return params
 
     def _full_coverage_mask(self, in_mask_t, in_transform, params_t, param_transform):
@@ -215,9 +256,9 @@ class KernelModel:
         out = torch.empty((hp, wp), dtype=torch.uint8, device=params_t.device)
         work = torch.empty((hp, wp), dtype=torch.uint8, device=params_t.device)
         kh, kw = self._kernel_shape
-        _native.check(lib.hb_full_coverage_mask(in_mask_t.data_ptr(), hi, wi, params_t.data_ptr(), hp, wp, gm.sx,
+        _call('hb_full_coverage_mask', in_mask_t.data_ptr(), hi, wi, params_t.data_ptr(), hp, wp, gm.sx,
                                                 gm.ox, gm.sy, gm.oy, kh, kw, out.data_ptr(), work.data_ptr(),
-                                                _stream()), 'hb_full_coverage_mask')
+                                                _stream())
         return out
 
     @staticmethod
@@ -225,8 +266,7 @@ class KernelModel:
         lib = _native.lib()
         has, nd = _nodata_args(nodata)
         mask = torch.empty(tuple(t.shape[-2:]), dtype=torch.uint8, device=t.device)
-        _native.check(lib.hb_valid_mask(t.data_ptr(), _plane_code(t), t.numel(), has, nd, mask.data_ptr(), _stream()),
-                      'hb_valid_mask')
+        _call('hb_valid_mask', t.data_ptr(), _plane_code(t), t.numel(), has, nd, mask.data_ptr(), _stream())
         return mask
 
     # ---- public API (reference kernel_model.py:411-463) -----------------------------------------------------------
@@ -256,9 +296,8 @@ class KernelModel:
         h, w = int(src_t.shape[-2]), int(src_t.shape[-1])
         corr = torch.empty((h, w), dtype=torch.float32, device=src_t.device)
         has, nd = _nodata_args(src_nodata)
-        _native.check(lib.hb_apply_same_grid(src_t.data_ptr(), _plane_code(src_t), has, nd, int(mask_src),
-                                             par_t.data_ptr(), h, w, corr.data_ptr(), _stream()),
-                      'hb_apply_same_grid')
+        _call('hb_apply_same_grid', src_t.data_ptr(), _plane_code(src_t), has, nd, int(mask_src),
+                                             par_t.data_ptr(), h, w, corr.data_ptr(), _stream())
         return corr
 
 
@@ -273,8 +312,8 @@ def _downsample_average(src_t, src_transform, src_nodata, dst_shape, dst_transfo
     hd, wd = int(dst_shape[0]), int(dst_shape[1])
     dst = torch.empty((hd, wd), dtype=torch.float32, device=src_t.device)
     has, nd = _nodata_args(src_nodata)
-    _native.check(lib.hb_downsample_average(src_t.data_ptr(), _plane_code(src_t), hs, ws, has, nd, dst.data_ptr(), hd,
-                                            wd, gm.sx, gm.ox, gm.sy, gm.oy, _stream()), 'hb_downsample_average')
+    _call('hb_downsample_average', src_t.data_ptr(), _plane_code(src_t), hs, ws, has, nd, dst.data_ptr(), hd,
+                                            wd, gm.sx, gm.ox, gm.sy, gm.oy, _stream())
     return dst
 
 
@@ -295,8 +334,8 @@ def _resample_up(src_t, src_transform, src_nodata, dst_shape, dst_transform, met
     dst = torch.empty((nb, hd, wd), dtype=torch.float32, device=src_t.device)
     for b0 in range(0, nb, 2):     # the native up-sampler takes 1 or 2 bands per call
         nbc = min(2, nb - b0)
-        _native.check(lib.hb_resample_up(src3[b0:b0 + nbc].data_ptr(), nbc, hs, ws, has, nd, dst[b0:].data_ptr(), hd,
-                                         wd, gm.sx, gm.ox, gm.sy, gm.oy, method, _stream()), 'hb_resample_up')
+        _call('hb_resample_up', src3[b0:b0 + nbc].data_ptr(), nbc, hs, ws, has, nd, dst[b0:].data_ptr(), hd,
+                                         wd, gm.sx, gm.ox, gm.sy, gm.oy, method, _stream())
     return dst[0] if squeeze else dst
 
 
@@ -371,10 +410,10 @@ class RefSpaceModel(KernelModel):
             hp, wp = int(par2.shape[-2]), int(par2.shape[-1])
             corr = torch.empty((hs, ws), dtype=torch.float32, device=src_t.device)
             has, nd = _nodata_args(src_ra.nodata)
-            _native.check(lib.hb_upsample_apply(src_t.data_ptr(), _plane_code(src_t), hs, ws, has, nd,
+            _call('hb_upsample_apply', src_t.data_ptr(), _plane_code(src_t), hs, ws, has, nd,
                                                 par2.data_ptr(), hp, wp, gm.sx, gm.ox, gm.sy, gm.oy,
                                                 cover.data_ptr() if cover is not None else None, corr.data_ptr(),
-                                                _stream()), 'hb_upsample_apply')
+                                                _stream())
         else:
             # parameters finer than (or as fine as) the source: resample them, then the same-grid apply
             par_us = torch.stack([_resample_plane(par2[b], param_ra.transform, NAN, (hs, ws), src_ra.transform,

@@ -365,14 +365,16 @@ def fuse_band_blocks(src, src_transform, src_nodata, ref, ref_transform, ref_nod
     One band of RasterFuse.process with a single block (fuse.py:295-319): block windows -> fit -> apply -> crop the
     corrected block to the source extent (fuse.py:311).  Returns (params, param_transform, corr).
     """
-    if proc_crs == 'src':
-        params = srcspace_fit(src, src_transform, src_nodata, ref, ref_transform, ref_nodata, model, kernel_shape,
-                              find_r2, r2_inpaint_thresh, mask_partial)
-        return params, tuple(src_transform[:6]), srcspace_apply(src, params)
     src_blk, src_blk_tf, ref_blk, ref_blk_tf, (r0, c0) = block_windows(src, src_transform, src_nodata, ref,
                                                                        ref_transform)
+    hs, ws = np.shape(src)
+    if proc_crs == 'src':
+        params = srcspace_fit(src_blk, src_blk_tf, src_nodata, ref_blk, ref_blk_tf, ref_nodata, model, kernel_shape,
+                              find_r2, r2_inpaint_thresh, mask_partial)
+        corr = srcspace_apply(src_blk, params)
+        return (np.ascontiguousarray(params[:, r0:r0 + hs, c0:c0 + ws]), tuple(src_transform[:6]),
+                np.ascontiguousarray(corr[r0:r0 + hs, c0:c0 + ws]))
     params = refspace_fit(src_blk, src_blk_tf, src_nodata, ref_blk, ref_blk_tf, ref_nodata, model, kernel_shape,
                           find_r2, r2_inpaint_thresh)
     corr = refspace_apply(src_blk, src_blk_tf, src_nodata, params, ref_blk_tf, kernel_shape, mask_partial)
-    hs, ws = np.shape(src)
     return params, ref_blk_tf, np.ascontiguousarray(corr[r0:r0 + hs, c0:c0 + ws])

@@ -1,0 +1,282 @@
+"""
+GPU tier: each C-ABI entry point of include/homonim_b200.h against the matching oracle function, plus
+size-independent properties at BASELINE.json's full raster sizes (where the oracle would take too long).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import RTOL, assert_same_mask, check_corr, rel_err
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+from homonim_b200 import Affine, _native   # noqa: E402
+from homonim_b200 import kernel_model as hkm   # noqa: E402
+
+NAN = float('nan')
+TF_LO = Affine(10, 0, 2000, 0, -10, 9000)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _oracle():
+    from oracle import gdal_restate, kernel_model_np
+    return gdal_restate, kernel_model_np
+
+
+def _rand_src(rng, h, w, dtype, nodata, holes=True):
+    if dtype == 'float32':
+        a = rng.normal(0.3, 0.1, (h, w)).astype('float32')
+    else:
+        a = rng.integers(1, np.iinfo(dtype).max, (h, w)).astype(dtype)
+    if holes:
+        a[rng.integers(0, h, 50), rng.integers(0, w, 50)] = nodata
+        a[h // 3:h // 3 + 7, w // 4:w // 4 + 9] = nodata
+    return a
+
+
+@pytest.mark.parametrize('dtype, nodata, ratio, shift, hw', [
+    ('uint16', 0, 20, (0, 0), (30, 37)),          # C2 geometry: aligned, exact integer sums -> bit-exact
+    ('uint8', 0, 4, (0, 0), (50, 64)),
+    ('float32', NAN, 20, (0, 0), (30, 37)),
+    ('float32', NAN, 2, (0, 0), (100, 91)),
+    ('uint16', 0, 5, (1.3, 2.6), (40, 33)),       # mis-aligned: fractional edge weights
+    ('float32', NAN, 3, (0.5, 0.25), (41, 50)),
+    ('float32', -9999.0, 2.5, (0.2, 0.7), (40, 44)),   # non-integer ratio, value nodata
+])
+def test_downsample_average(dtype, nodata, ratio, shift, hw):
+    gr, _ = _oracle()
+    rng = np.random.default_rng(1)
+    hd, wd = hw
+    hs, ws = int(hd * ratio) - 3, int(wd * ratio) - 5          # source does not quite cover the last cells
+    src = _rand_src(rng, hs, ws, dtype, nodata)
+    src_tf = TF_LO * Affine.scale(1.0 / ratio) * Affine.translation(*shift)
+    expected = gr.reproject_array(src, tuple(src_tf), nodata, (hd, wd), tuple(TF_LO), NAN, 'average')
+    got = hkm._downsample_average(torch.from_numpy(src).cuda(), src_tf, nodata, (hd, wd), TF_LO).cpu().numpy()
+    inside = np.ones((hd, wd), bool)      # cells whose footprint leaves the raster follow the padded-source convention
+    gm = hkm.grid_map(src_tf, TF_LO)
+    jj, ii = np.meshgrid(np.arange(wd), np.arange(hd))
+    inside &= (gm.sx * jj + gm.ox >= 0) & (gm.sx * (jj + 1) + gm.ox <= ws)
+    inside &= (gm.sy * ii + gm.oy >= 0) & (gm.sy * (ii + 1) + gm.oy <= hs)
+    assert inside.mean() > 0.8
+    assert_same_mask(got[inside], expected[inside], 'average')
+    if dtype != 'float32' and shift == (0, 0):
+        assert np.array_equal(got[inside], expected[inside], equal_nan=True)       # bit-exact
+    else:
+        assert rel_err(got[inside], expected[inside], 1e-3 * np.nanmean(np.abs(expected))) <= 1e-6
+
+
+@pytest.mark.parametrize('nb', [1, 2])
+@pytest.mark.parametrize('ratio, shift', [(20, (0, 0)), (2, (0, 0)), (4, (1.3, 2.6)), (3, (0.5, 0.25)), (1.6, (0, 0))])
+def test_resample_up_cubic_spline(nb, ratio, shift):
+    gr, _ = _oracle()
+    rng = np.random.default_rng(2)
+    hp, wp = 40, 33
+    coarse = rng.normal(1.0, 0.2, (nb, hp, wp)).astype('float32')
+    coarse[:, 10:13, 5:9] = NAN
+    coarse[0, 30, 20] = NAN                                    # invalid in one band only
+    coarse[:, :, -1] = NAN
+    hd, wd = int(hp * ratio) + 3, int(wp * ratio) + 2          # destination slightly larger than the coarse raster
+    dst_tf = TF_LO * Affine.scale(1.0 / ratio) * Affine.translation(*shift)
+    arr = coarse if nb == 2 else coarse[0]
+    expected = gr.reproject_array(arr, tuple(TF_LO), NAN, (hd, wd), tuple(dst_tf), NAN, 'cubic_spline')
+    got = hkm._resample_up(torch.from_numpy(arr).cuda(), TF_LO, NAN, (hd, wd), dst_tf).cpu().numpy()
+    assert_same_mask(got, expected, 'cubic_spline')
+    assert rel_err(got, expected, 1e-3) <= 1e-6
+
+
+def test_resample_up_nearest():
+    gr, _ = _oracle()
+    rng = np.random.default_rng(3)
+    coarse = rng.normal(1.0, 0.2, (25, 31)).astype('float32')
+    coarse[3:6, 4:8] = NAN
+    dst_tf = TF_LO * Affine.scale(1.0 / 3) * Affine.translation(0.5, 0.25)
+    expected = gr.reproject_array(coarse, tuple(TF_LO), NAN, (80, 95), tuple(dst_tf), NAN, 'nearest')
+    got = hkm._resample_up(torch.from_numpy(coarse).cuda(), TF_LO, NAN, (80, 95), dst_tf,
+                           _native.HB_UP_NEAREST).cpu().numpy()
+    assert np.array_equal(got, expected, equal_nan=True)
+
+
+@pytest.mark.parametrize('dtype, nodata, ratio, shift, partial', [
+    ('uint16', 0, 20, (0, 0), False), ('uint8', 0, 4, (0, 0), True), ('float32', NAN, 5, (1.3, 2.6), False),
+    ('float32', NAN, 2, (0, 0), True), ('uint16', 0, 3, (0.5, 0.25), True),
+])
+def test_upsample_apply(dtype, nodata, ratio, shift, partial):
+    """ hb_upsample_apply (+ hb_valid_mask + hb_full_coverage_mask) against RefSpaceModel.apply of the oracle. """
+    _, kmnp = _oracle()
+    rng = np.random.default_rng(4)
+    hp, wp = 36, 30
+    hs, ws = hp * ratio - 2, wp * ratio - 3
+    src = _rand_src(rng, hs, ws, dtype, nodata)
+    params = np.stack([rng.normal(0.7, 0.1, (hp, wp)), rng.normal(20.0, 50.0, (hp, wp))]).astype('float32')
+    params[:, 8:12, 10:15] = NAN
+    params[:, :2, :] = NAN
+    src_tf = TF_LO * Affine.scale(1.0 / ratio) * Affine.translation(*shift)
+    # the reference reads its source block boundlessly (nodata beyond the raster, raster_array.py:175-199): give the
+    # oracle the padded block, and compare on the un-padded extent
+    pad = 2 * ratio
+    src_pad = np.full((hs + 2 * pad, ws + 2 * pad), nodata, dtype=src.dtype)
+    src_pad[pad:pad + hs, pad:pad + ws] = src
+    pad_tf = src_tf * Affine.translation(-pad, -pad)
+    expected = kmnp.refspace_apply(src_pad, tuple(pad_tf), nodata, params, tuple(TF_LO), (3, 5),
+                                   mask_partial=partial)[pad:pad + hs, pad:pad + ws]
+    from homonim_b200 import CRS, Model, RasterArray, RefSpaceModel
+    crs = CRS.from_epsg(3857)
+    km = RefSpaceModel(Model.gain_blk_offset, (3, 5), mask_partial=partial)
+    got = km.apply(RasterArray(src, crs, src_tf, nodata=nodata), RasterArray(params, crs, TF_LO, nodata=NAN)).array
+    check_corr(got, expected.astype('float32'), 'upsample_apply')
+
+
+def test_block_norm():
+    _, kmnp = _oracle()
+    lib = _native.lib()
+    rng = np.random.default_rng(5)
+    for n, nodata in ((1, NAN), (7, NAN), (1000, NAN), (250_000, 0.0), (1_000_003, NAN)):
+        src = rng.normal(3000, 900, n).astype('float32')
+        ref = (0.7 * src + 100 + rng.normal(0, 30, n)).astype('float32')
+        bad = rng.random(n) < 0.05
+        src[bad & (np.arange(n) % 2 == 0)] = nodata
+        ref[bad & (np.arange(n) % 2 == 1)] = NAN
+        if n < 10:
+            src[:] = np.abs(src) + 1
+            ref[:] = np.abs(ref) + 1
+        mask = ~kmnp.nan_equals(src, nodata) & ~np.isnan(ref)
+        with np.errstate(all='ignore'):
+            expected = kmnp.block_norm(src, ref, mask)
+        s, r = torch.from_numpy(src).cuda(), torch.from_numpy(ref).cuda()
+        norm = torch.zeros(2, dtype=torch.float64, device='cuda')
+        nbytes = lib.hb_block_norm_workspace_bytes(n)
+        work = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+        _native.check(lib.hb_block_norm(s.data_ptr(), 1, nodata, r.data_ptr(), 1, NAN, n, norm.data_ptr(),
+                                        work.data_ptr(), nbytes, _stream()))
+        got = norm.cpu().numpy()
+        if n == 1:
+            assert np.isnan(got[0]) == np.isnan(expected[0])      # std == 0 -> 0/0
+            continue
+        # norm[0]: numpy's float32 np.std is good to ~1e-6; norm[1] = P1(ref) - P1(src) * norm[0] is a difference of
+        # O(3000 * 0.7) terms, so its error scales with those terms, not with its own size
+        assert got[0] == pytest.approx(expected[0], rel=2e-6), (n, got, expected)
+        scale = max(abs(np.percentile(ref[mask], 1)), abs(np.percentile(src[mask], 1) * expected[0]))
+        assert abs(got[1] - expected[1]) <= 4e-6 * scale, (n, got, expected)
+
+
+def test_block_norm_empty_mask():
+    lib = _native.lib()
+    s = torch.full((100,), NAN, device='cuda')
+    norm = torch.ones(2, dtype=torch.float64, device='cuda')
+    nbytes = lib.hb_block_norm_workspace_bytes(100)
+    work = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+    _native.check(lib.hb_block_norm(s.data_ptr(), 1, NAN, s.data_ptr(), 1, NAN, 100, norm.data_ptr(), work.data_ptr(),
+                                    nbytes, _stream()))
+    assert norm.cpu().tolist() == [0.0, 0.0]                       # kernel_model.py:223-226
+
+
+def test_fuse_refspace_host_entry_point():
+    """ hb_fuse_refspace_host with HOST buffers equals the device-pointer pipeline and the oracle. """
+    _, kmnp = _oracle()
+    lib = _native.lib()
+    from homonim_b200.synthetic import make_pair
+    src_ra, ref_ra = make_pair(60, 52, 10, bands=1, dtype='uint16', seed=9, device='cpu', src_nodata=0, ref_pad=0)
+    src = np.ascontiguousarray(src_ra.array[0].numpy())
+    ref = np.ascontiguousarray(ref_ra.array[0].numpy())
+    gm = hkm.grid_map(src_ra.transform, ref_ra.transform)
+    corr = np.empty(src.shape, 'float32')
+    params = np.empty((3,) + ref.shape, 'float32')
+    _native.check(lib.hb_fuse_refspace_host(
+        src.ctypes.data, _native.HB_U16, src.shape[0], src.shape[1], 1, 0.0, ref.ctypes.data, ref.shape[0],
+        ref.shape[1], 1, NAN, gm.sx, gm.ox, gm.sy, gm.oy, _native.HB_MODEL_GAIN_OFFSET, 15, 15, 1, 1, 0.25,
+        corr.ctypes.data, params.ctypes.data, _stream()))
+    exp_params, _, exp_corr = kmnp.fuse_band_blocks(src, tuple(src_ra.transform), 0, ref, tuple(ref_ra.transform), NAN,
+                                                    'gain-offset', (15, 15), 'ref', True, 0.25)
+    from conftest import check_params
+    check_params(params, exp_params, float(src[src != 0].mean()), 'host entry params')
+    check_corr(corr, exp_corr.astype('float32'), 'host entry corr')
+
+
+def test_error_reporting():
+    lib = _native.lib()
+    a = torch.zeros((8, 8), device='cuda')
+    rc = lib.hb_fit_same_grid(a.data_ptr(), 0, 0.0, a.data_ptr(), 0, 0.0, 8, 8, 0, 4, 4, 0, None, a.data_ptr(), None,
+                              _stream())
+    assert rc != 0 and b'odd' in lib.hb_last_error()
+    with pytest.raises(_native.NativeLibraryError):
+        _native.check(rc, 'hb_fit_same_grid')
+    before = lib.hb_launch_count()
+    m = torch.empty(64, dtype=torch.uint8, device='cuda')
+    _native.check(lib.hb_valid_mask(a.data_ptr(), _native.HB_F32, 64, 1, 0.0, m.data_ptr(), _stream()))
+    assert lib.hb_launch_count() == before + 1 and int(m.sum()) == 0
+
+
+# ---- size-independent properties at the full sizes of BASELINE.json ----------------------------------------------------
+def test_full_size_refspace_properties():
+    """
+    10 000 x 10 000 uint16 band against a 10 m reference (BASELINE.json configs[1]): with ref = 2 * avg(src) the
+    gain model must return gain == 2 exactly on every valid proc pixel, the corrected band 2 * src where the spline
+    sees constant parameters, and NaN exactly on the source nodata.
+    """
+    from homonim_b200 import CRS, Model, RasterArray, RefSpaceModel
+    hp = wp = 500
+    ratio = 20
+    g = torch.Generator(device='cuda').manual_seed(1)
+    src = torch.randint(1, 5000, (hp * ratio, wp * ratio), generator=g, device='cuda', dtype=torch.int32)
+    src[:777, :1234] = 0
+    src = src.to(torch.uint16)
+    crs = CRS.from_epsg(32735)
+    src_tf = Affine(0.5, 0, 0, 0, -0.5, 0)
+    ref_tf = Affine(10, 0, 0, 0, -10, 0)
+    src_ra = RasterArray(src, crs, src_tf, nodata=0)
+    avg = hkm._downsample_average(src, src_tf, 0, (hp, wp), ref_tf)
+    blocks = src.view(hp, ratio, wp, ratio).to(torch.float64)
+    cnt = (blocks != 0).sum(dim=(1, 3))
+    mean = blocks.sum(dim=(1, 3)) / cnt
+    assert torch.equal(torch.isnan(avg), cnt == 0)
+    assert torch.equal(avg[cnt > 0], mean[cnt > 0].to(torch.float32))            # exact integer sums
+    ref_ra = RasterArray((2 * avg).nan_to_num(1.0), crs, ref_tf, nodata=NAN)
+    km = RefSpaceModel(Model.gain, (1, 1))
+    param_ra = km.fit(src_ra, ref_ra)
+    gain = param_ra.array[0]
+    assert torch.equal(torch.isnan(gain), cnt == 0)
+    assert bool((gain[cnt > 0] == 2).all()) and bool((param_ra.array[1][cnt > 0] == 0).all())
+    corr = km.apply(src_ra, param_ra).array
+    assert torch.equal(torch.isnan(corr), src == 0)
+    # away from the nodata block and from the raster edge every spline tap is present and equal: exactly 2 * src
+    # (within 2 coarse pixels of an edge GDAL drops the out-of-range taps and, when their weight is < 1e-5, does not
+    # renormalise -- the corrected value is then 2 * src * (1 - O(1e-6)), which the oracle tests cover)
+    interior = torch.zeros_like(src, dtype=torch.bool)
+    interior[900:-60, 1400:-60] = src[900:-60, 1400:-60] != 0
+    assert torch.equal(corr[interior], 2 * src.to(torch.int32)[interior].to(torch.float32))
+
+
+def test_full_size_same_grid_properties():
+    """
+    8 192 x 8 192 float32 planes on one grid (the C3 / C5b regime): with ref = 0.5 * src + 0.125 (exact in float32) the
+    gain-offset fit is exact up to float32 cancellation, R2 ~ 1, and a shifted band decomposition gives the same
+    parameters (row-band / column-strip independence of the kernel).
+    """
+    from homonim_b200 import CRS, KernelModel, Model, RasterArray
+    n = 8192
+    g = torch.Generator(device='cuda').manual_seed(2)
+    src = (torch.rand((n, n), generator=g, device='cuda') * 0.5 + 0.25)
+    src = (src * 1024).round() / 1024
+    ref = 0.5 * src + 0.125
+    src[4000:4100, 100:300] = NAN
+    crs, tf = CRS.from_epsg(32735), Affine(1, 0, 0, 0, -1, 0)
+    km = KernelModel(Model.gain_offset, (15, 15), find_r2=True, r2_inpaint_thresh=None)
+    p = km.fit(RasterArray(src, crs, tf), RasterArray(ref, crs, tf)).array
+    valid = ~torch.isnan(src)
+    assert torch.equal(torch.isnan(p[0]), ~valid)
+    assert float((p[0][valid] - 0.5).abs().max()) < 2e-3
+    assert float((p[2][valid] - 1).abs().max()) < 1e-2
+    # a crop with its own tiling must reproduce the full-raster parameters away from the crop border
+    y0, x0, m = 3000, 2001, 2048
+    pc = km.fit(RasterArray(src[y0:y0 + m, x0:x0 + m].contiguous(), crs, tf),
+                RasterArray(ref[y0:y0 + m, x0:x0 + m].contiguous(), crs, tf)).array
+    a, b = p[:, y0 + 8:y0 + m - 8, x0 + 8:x0 + m - 8], pc[:, 8:-8, 8:-8]
+    same = (a == b) | (torch.isnan(a) & torch.isnan(b))
+    assert float(same.float().mean()) > 0.999
+    fin = torch.isfinite(a) & torch.isfinite(b)
+    assert float(((a - b).abs()[fin] / a.abs()[fin].clamp_min(1e-3)).max()) <= RTOL

@@ -1,0 +1,248 @@
+"""
+GPU tier: parity of the sm_100a CUDA path against (i) the golden vectors generated from the unmodified reference and
+(ii) the oracle port on larger seeded synthetic rasters.  Tolerance (BASELINE.json north_star): parameter and
+corrected-pixel max rel err <= 1e-4 (see conftest.check_params for the floors), nodata masks identical.
+"""
+import numpy as np
+import pytest
+
+from conftest import RTOL, assert_same_mask, check_corr, check_params, golden_names, load_golden, rel_err
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+from homonim_b200 import (CRS, KernelModel, Model, ProcCrs, RasterArray, RasterFuse, RefSpaceModel,   # noqa: E402
+                          SrcSpaceModel)
+from homonim_b200.synthetic import make_pair   # noqa: E402
+
+CRS0 = CRS.from_epsg(3857)
+
+
+def _model_kwargs(meta):
+    kw = dict(find_r2=meta['find_r2'], r2_inpaint_thresh=meta['r2_inpaint_thresh'])
+    if 'mask_partial' in meta:
+        kw['mask_partial'] = meta['mask_partial']
+    return kw
+
+
+@pytest.mark.parametrize('device_resident', [False, True])
+@pytest.mark.parametrize('name', golden_names('same'))
+def test_same_grid_vs_reference_golden(name, device_resident):
+    meta, g = load_golden(name)
+    model = KernelModel(meta['model'], meta['kernel_shape'], **_model_kwargs(meta))
+    src_ra = RasterArray(g['src'].copy(), CRS0, meta['transform'], nodata=meta['src_nodata'])
+    ref_ra = RasterArray(g['ref'].copy(), CRS0, meta['transform'], nodata=meta['ref_nodata'])
+    if device_resident:
+        src_ra, ref_ra = src_ra.to_device(), ref_ra.to_device()
+    param_ra = model.fit(src_ra, ref_ra)
+    assert param_ra.is_device == device_resident
+    # inputs are not mutated
+    assert np.array_equal(src_ra.to_host().array, g['src'], equal_nan=True)
+    corr_ra = model.apply(src_ra, param_ra)
+    params, corr = param_ra.to_host().array, corr_ra.to_host().array
+    valid = g['src'][~np.isnan(g['params'][0])]
+    check_params(params, g['params'], float(np.mean(valid)) if valid.size else 1.0, name)
+    check_corr(corr, g['corr'], name)
+    assert param_ra.transform == src_ra.transform and np.isnan(param_ra.nodata)
+
+
+@pytest.mark.parametrize('name', golden_names('refspace'))
+def test_refspace_vs_reference_golden(name):
+    meta, g = load_golden(name)
+    src_ra = RasterArray(g['src'].copy(), CRS0, meta['src_transform'], nodata=meta['src_nodata'])
+    ref_ra = RasterArray(g['ref'].copy(), CRS0, meta['ref_transform'], nodata=meta['ref_nodata'])
+    fuse = RasterFuse(src_ra, ref_ra, proc_crs=ProcCrs.ref)
+    model = RefSpaceModel(meta['model'], meta['kernel_shape'], **_model_kwargs(meta))
+    corr_ra, param_ra = fuse._process_band(0, model)
+    assert np.allclose(tuple(param_ra.transform), meta['param_transform'])
+    src_f = g['src'].astype('float32')
+    check_params(param_ra.array, g['params'], float(np.mean(src_f[np.isfinite(src_f) & (src_f != 0)])), name)
+    check_corr(corr_ra.array, g['corr'].astype('float32'), name)
+    assert corr_ra.shape == src_ra.shape and corr_ra.transform == src_ra.transform
+
+
+@pytest.mark.parametrize('name', golden_names('srcspace'))
+def test_srcspace_vs_reference_golden(name):
+    meta, g = load_golden(name)
+    src_ra = RasterArray(g['src'].copy(), CRS0, meta['src_transform'], nodata=meta['src_nodata'])
+    ref_ra = RasterArray(g['ref'].copy(), CRS0, meta['ref_transform'], nodata=meta['ref_nodata'])
+    model = SrcSpaceModel(meta['model'], meta['kernel_shape'], **_model_kwargs(meta))
+    param_ra = model.fit(src_ra, ref_ra)
+    corr_ra = model.apply(src_ra, param_ra)
+    check_params(param_ra.array, g['params'], float(np.nanmean(g['src'])), name)
+    check_corr(corr_ra.array, g['corr'], name)
+
+
+# ---- larger seeded rasters against the oracle port ------------------------------------------------------------------
+def _oracle():
+    from oracle import kernel_model_np as kmnp
+    return kmnp
+
+
+@pytest.mark.parametrize('model, kernel_shape, find_r2, thresh', [
+    (Model.gain, (1, 1), False, None),
+    (Model.gain, (7, 7), True, None),
+    (Model.gain_blk_offset, (5, 5), True, None),
+    (Model.gain_blk_offset, (15, 15), False, None),
+    (Model.gain_offset, (15, 15), True, None),
+    (Model.gain_offset, (31, 31), False, None),
+    (Model.gain_offset, (15, 15), False, 0.25),
+])
+def test_same_grid_1k_vs_oracle(model, kernel_shape, find_r2, thresh):
+    """ 1000 x 1200 float32 planes on one grid (the SrcSpace / C3 regime), incl. a width that is not a multiple of 4. """
+    kmnp = _oracle()
+    src_ra, ref_ra = make_pair(1000, 1203, 1, bands=1, dtype='float32', mu=0.3, seed=11, device='cuda',
+                               src_nodata=float('nan'), ref_pad=0)
+    src_ra = RasterArray(src_ra.array[0].contiguous(), src_ra.crs, src_ra.transform, nodata=src_ra.nodata)
+    ref_ra = RasterArray(ref_ra.array[0].contiguous(), ref_ra.crs, src_ra.transform, nodata=ref_ra.nodata)
+    km = KernelModel(model, kernel_shape, find_r2=find_r2, r2_inpaint_thresh=thresh)
+    param_ra = km.fit(src_ra, ref_ra)
+    corr_ra = km.apply(src_ra, param_ra)
+    src, ref = src_ra.to_host().array, ref_ra.to_host().array
+    exp_params = kmnp.fit_same_grid(src, float('nan'), ref, float('nan'), model, kernel_shape, find_r2, thresh)
+    exp_corr = kmnp.apply_same_grid(src, exp_params)
+    blk = model == Model.gain_blk_offset
+    bad = check_params(param_ra.to_host().array, exp_params, float(np.nanmean(src)), 'params', r2_robust=blk)
+    check_corr(corr_ra.to_host().array, exp_corr, 'corr', bad=bad)
+    if not blk:
+        # most pixels are bit-identical, not merely within tolerance (gain-blk-offset differs by ~1 ulp throughout:
+        # numpy's float32 np.std of the block is not correctly rounded, ours is)
+        got = param_ra.to_host().array[0]
+        same = (got == exp_params[0]) | (np.isnan(got) & np.isnan(exp_params[0]))
+        assert same.mean() > 0.99
+
+
+@pytest.mark.parametrize('dtype, nodata, ratio, model, kernel_shape, thresh', [
+    ('uint16', 0, 20, Model.gain, (1, 1), None),
+    ('uint16', 0, 20, Model.gain_offset, (15, 15), 0.25),
+    ('uint8', 0, 8, Model.gain_blk_offset, (5, 5), None),
+    ('float32', float('nan'), 20, Model.gain_blk_offset, (15, 15), None),
+    ('float32', float('nan'), 3, Model.gain_offset, (5, 5), None),
+])
+def test_refspace_fuse_vs_oracle(dtype, nodata, ratio, model, kernel_shape, thresh):
+    """ RasterFuse.process (proc_crs=ref) on a 2-band source against the oracle's single-block fuse of each band. """
+    kmnp = _oracle()
+    hp, wp = 120, 101
+    mu = 120.0 if dtype == 'uint8' else (0.3 if dtype == 'float32' else 3000.0)
+    src_ra, ref_ra = make_pair(hp, wp, ratio, bands=2, dtype=dtype, mu=mu, seed=5, device='cuda', src_nodata=nodata)
+    with RasterFuse(src_ra, ref_ra) as fuse:
+        assert fuse.proc_crs == ProcCrs.ref
+        corr_ra, param_ra = fuse.process(model=model, kernel_shape=kernel_shape, param_filename='params',
+                                         model_config=dict(r2_inpaint_thresh=thresh))
+    src, ref = src_ra.to_host(), ref_ra.to_host()
+    n_params = param_ra.count // 2
+    for b in range(2):
+        exp_params, _, exp_corr = kmnp.fuse_band_blocks(
+            src.array[b], tuple(src.transform), nodata, ref.array[b], tuple(ref.transform), float('nan'), model,
+            kernel_shape, 'ref', True, thresh)
+        got_params = np.stack([param_ra.to_host().array[p * 2 + b] for p in range(n_params)])
+        valid_src = src.array[b][src.array[b] != nodata] if not np.isnan(nodata) else src.array[b]
+        if kernel_shape == (1, 1):
+            # R2 of a one-pixel window is 1 - 0/0: both sides return the rounding residue of N*sum(r^2) - sum(r)^2
+            # (kernel_model.py:179); require bit-identity almost everywhere instead of a tolerance
+            r2_same = (got_params[2] == exp_params[2]) | (np.isnan(got_params[2]) & np.isnan(exp_params[2]))
+            assert r2_same.mean() > 0.999
+            got_params, exp_params = got_params[:2], exp_params[:2]
+        check_params(got_params, exp_params, float(np.nanmean(valid_src.astype('float64'))), f'band {b} params',
+                     r2_robust=model == Model.gain_blk_offset)
+        check_corr(corr_ra.to_host().array[b], exp_corr.astype('float32'), f'band {b} corr')
+
+
+def test_srcspace_fuse_vs_oracle():
+    """ proc_crs=src: reference 2x coarser, cubic-spline up-sampled, gain-offset 31x31 (the C3 configuration). """
+    kmnp = _oracle()
+    src_ra, ref_ra = make_pair(300, 260, 2, bands=1, dtype='float32', mu=0.3, seed=3, device='cuda',
+                               src_nodata=float('nan'))
+    with RasterFuse(src_ra, ref_ra, proc_crs=ProcCrs.src) as fuse:
+        with pytest.warns(Warning):
+            RasterFuse(src_ra, ref_ra, proc_crs=ProcCrs.src)
+        corr_ra, param_ra = fuse.process(model=Model.gain_offset, kernel_shape=(31, 31), param_filename='p',
+                                         model_config=dict(r2_inpaint_thresh=None))
+    src, ref = src_ra.to_host(), ref_ra.to_host()
+    exp_params, _, exp_corr = kmnp.fuse_band_blocks(
+        src.array[0], tuple(src.transform), float('nan'), ref.array[0], tuple(ref.transform), float('nan'),
+        Model.gain_offset, (31, 31), 'src', True, None)
+    check_params(param_ra.to_host().array, exp_params, float(np.nanmean(src.array[0])), 'params')
+    check_corr(corr_ra.to_host().array[0], exp_corr, 'corr')
+
+
+# ---- reference known-answer tests, run against the CUDA path (tests/test_kernel_model.py of the reference) ----------
+def _conftest_rasters():
+    a100 = np.array(range(1, 201), dtype='float32').reshape(20, 10)
+    a100[:, [0, -1]] = np.nan
+    a100[[0, -1], :] = np.nan
+    a50 = np.kron(a100, np.ones((2, 2))).astype('float32')
+    a50[:, [0, 1, -2, -1]] = np.nan
+    a50[[0, 1, -2, -1], :] = np.nan
+    from homonim_b200 import Affine
+    tf100 = Affine(1, 0, 0, 0, -1, 0) * Affine.translation(5, 5)
+    tf50 = tf100 * Affine.scale(0.5)
+    return (RasterArray(a100, CRS0, tf100, nodata=float('nan')), RasterArray(a50, CRS0, tf50, nodata=float('nan')))
+
+
+@pytest.mark.parametrize('model, kernel_shape', [
+    (Model.gain, (1, 1)), (Model.gain, (3, 3)), (Model.gain_blk_offset, (1, 1)), (Model.gain_blk_offset, (5, 5)),
+    (Model.gain_offset, (5, 5)),
+])
+def test_ref_and_src_basic_fit(model, kernel_shape):
+    """ reference tests/test_kernel_model.py:41-81: same surface at two resolutions => gain ~ 1, offset ~ 0. """
+    ra100, ra50 = _conftest_rasters()
+    for cls, src_ra, ref_ra in ((RefSpaceModel, ra50, ra100), (SrcSpaceModel, ra100, ra50)):
+        km = cls(model, kernel_shape, mask_partial=False, r2_inpaint_thresh=0.25)
+        param_ra = km.fit(src_ra, ref_ra.copy())
+        proc_ra = ref_ra if cls is RefSpaceModel else src_ra
+        assert param_ra.shape == proc_ra.shape and param_ra.transform == proc_ra.transform
+        assert (proc_ra.mask == param_ra.mask).all()
+        assert param_ra.array[0, param_ra.mask] == pytest.approx(1, abs=1e-2)
+        assert param_ra.array[1, param_ra.mask] == pytest.approx(0, abs=1e-2)
+
+
+def test_ref_basic_apply_and_masking():
+    """ reference tests/test_kernel_model.py:84-117, 206-242. """
+    import cv2
+    ra100, ra50 = _conftest_rasters()
+    for kernel_shape, mask_partial in [((5, 5), False), ((1, 1), True), ((3, 3), True), ((3, 5), True), ((5, 5), True)]:
+        km = RefSpaceModel(Model.gain_blk_offset, kernel_shape, mask_partial=mask_partial)
+        param_ra = ra100.copy()
+        mask = param_ra.mask
+        param_ra.array = np.ones((2, *param_ra.shape), dtype='float32')
+        param_ra.mask = mask
+        out_ra = km.apply(ra50, param_ra)
+        assert out_ra.shape == ra50.shape and out_ra.transform == ra50.transform
+        if not mask_partial:
+            assert (ra50.mask == out_ra.mask).all()
+            assert out_ra.array[out_ra.mask] == pytest.approx(ra50.array[out_ra.mask] + 1, abs=1e-2)
+        else:
+            assert ra50.mask.sum() > out_ra.mask.sum() and ra50.mask[out_ra.mask].all()
+            covered = (ra50.mask.reshape(20, 2, 10, 2).mean(axis=(1, 3)) >= 1).astype('uint8') & mask
+            eroded = cv2.erode(covered, np.ones(np.add(kernel_shape, 2)), borderType=cv2.BORDER_CONSTANT, borderValue=0)
+            assert (np.kron(eroded, np.ones((2, 2))).astype(bool) == out_ra.mask).all()
+
+
+@pytest.mark.parametrize('kernel_shape', [(5, 5), (5, 7), (9, 9)])
+def test_r2_inpainting(kernel_shape):
+    """ reference tests/test_kernel_model.py:166-203. """
+    _, ra50 = _conftest_rasters()
+    src_ra, ref_ra = ra50, ra50.copy()
+    loc = np.floor(np.array(ref_ra.shape) / 2).astype(int)
+    ul = (loc - np.floor(np.array(kernel_shape) / 2)).astype(int)
+    low = np.zeros(ref_ra.shape, bool)
+    low[ul[0]:ul[0] + kernel_shape[0], ul[1]:ul[1] + kernel_shape[1]] = True
+    ref_ra.array[loc[0], loc[1]] = -100
+    no_inp = RefSpaceModel(Model.gain_offset, kernel_shape=kernel_shape, r2_inpaint_thresh=-np.inf).fit(src_ra, ref_ra)
+    inp = RefSpaceModel(Model.gain_offset, kernel_shape=kernel_shape, r2_inpaint_thresh=0.5).fit(src_ra, ref_ra)
+    for param_ra in (no_inp, inp):
+        assert param_ra.array[2, ~low & ref_ra.mask] == pytest.approx(1, abs=1e-3)
+        assert (param_ra.array[2, low] < .5).all()
+    assert no_inp.array[1, no_inp.mask] != pytest.approx(0, abs=1e-1)
+    assert inp.array[1, inp.mask] == pytest.approx(0, abs=1e-1)
+    assert inp.array[0, inp.mask].var() < no_inp.array[0, no_inp.mask].var()
+
+
+def test_grid_mismatch_raises():
+    ra100, ra50 = _conftest_rasters()
+    km = KernelModel(Model.gain, (3, 3))
+    with pytest.raises(ValueError):
+        km.fit(ra50, ra100)
+    with pytest.raises(ValueError):
+        km.apply(ra50, ra100)
