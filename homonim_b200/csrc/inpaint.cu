@@ -18,28 +18,61 @@ struct FillTables {
     uint8_t *r2m;    // the r2_mask
 };
 
-// thread per column: one sweep down, one sweep up (coalesced across the warp's columns)
-__global__ void inpaint_scan_kernel(const float *__restrict__ params, const float *__restrict__ sums, long h, long w,
-                                    float thresh, FillTables tb)
+// "Last source pixel at or above / below" tables.  One CTA = 32 columns (lane = column, coalesced 128-byte rows) x 32
+// warps; warp w owns the row chunk [w*rc, (w+1)*rc).  Pass 1: every warp scans its chunk down and up, writes the
+// r2_mask and publishes the chunk's last / first source pixel per column in shared memory.  Pass 2: every warp takes
+// its carry-in from the nearest chunk above / below that has a source pixel and re-scans, writing the tables.
+constexpr int kScanWarps = 32;
+
+__global__ void __launch_bounds__(kScanWarps * 32)
+inpaint_scan_kernel(const float *__restrict__ params, const float *__restrict__ sums, long h, long w, float thresh,
+                    FillTables tb)
 {
-    const long x = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= w) return;
+    __shared__ int s_dn_y[kScanWarps][32], s_up_y[kScanWarps][32];
+    __shared__ float s_dn_v[kScanWarps][32], s_up_v[kScanWarps][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long x = (long)blockIdx.x * 32 + lane;
+    const bool col_ok = x < w;
     const long plane = h * w;
+    const long rc = (h + kScanWarps - 1) / kScanWarps;
+    const long ya = min((long)warp * rc, h), yb = min(ya + rc, h);
+
+    // pass 1: r2_mask, and the chunk's own last (scanning down) / first (scanning up) source pixel
+    int dn_y = -1, up_y = -1;
+    float dn_v = 0.f, up_v = 0.f;
+    if (col_ok) {
+        for (long y = ya; y < yb; y++) {
+            const long i = y * w + x;
+            const float gain = params[i], off = params[plane + i], r2 = params[2 * plane + i];
+            const bool mask = sums[2 * plane + i] >= 0.f;            // count plane holds -1 outside the mask
+            const bool m = mask && (r2 > thresh) && (gain > 0.f);    // comparisons with nan are false (:363)
+            tb.r2m[i] = m ? 1 : 0;
+            if (m) {
+                dn_y = (int)y; dn_v = off;
+                if (up_y < 0) { up_y = (int)y; up_v = off; }
+            }
+        }
+    }
+    s_dn_y[warp][lane] = dn_y; s_dn_v[warp][lane] = dn_v;
+    s_up_y[warp][lane] = up_y; s_up_v[warp][lane] = up_v;
+    __syncthreads();
+    if (!col_ok) return;
+    // pass 2: carry-in from the other chunks, then the tables
     int ly = -1;
     float lv = 0.f;
-    for (long y = 0; y < h; y++) {
+    for (int ww = warp - 1; ww >= 0; ww--)
+        if (s_dn_y[ww][lane] >= 0) { ly = s_dn_y[ww][lane]; lv = s_dn_v[ww][lane]; break; }
+    for (long y = ya; y < yb; y++) {
         const long i = y * w + x;
-        const float gain = params[i], off = params[plane + i], r2 = params[2 * plane + i];
-        const bool mask = sums[2 * plane + i] >= 0.f;            // count plane holds -1 outside the mask
-        const bool m = mask && (r2 > thresh) && (gain > 0.f);    // comparisons with nan are false (:363)
-        tb.r2m[i] = m ? 1 : 0;
-        if (m) { ly = (int)y; lv = off; }
+        if (tb.r2m[i]) { ly = (int)y; lv = params[plane + i]; }
         tb.top_y[i] = ly;
         tb.top_v[i] = lv;
     }
     ly = -1;
     lv = 0.f;
-    for (long y = h - 1; y >= 0; y--) {
+    for (int ww = warp + 1; ww < kScanWarps; ww++)
+        if (s_up_y[ww][lane] >= 0) { ly = s_up_y[ww][lane]; lv = s_up_v[ww][lane]; break; }
+    for (long y = yb - 1; y >= ya; y--) {
         const long i = y * w + x;
         if (tb.r2m[i]) { ly = (int)y; lv = params[plane + i]; }
         tb.bot_y[i] = ly;
@@ -134,7 +167,7 @@ extern "C" int hb_inpaint_refit(float *params_dev, const float *sums_dev, long h
     tb.r2m = (uint8_t *)(tb.bot_v + n);
     // numpy compares the float32 R2 plane with a Python float: the threshold is used as float32 (NEP 50)
     const float thresh = (float)r2_thresh;
-    inpaint_scan_kernel<<<(unsigned)((w + 127) / 128), 128, 0, st>>>(params_dev, sums_dev, h, w, thresh, tb);
+    inpaint_scan_kernel<<<(unsigned)((w + 31) / 32), kScanWarps * 32, 0, st>>>(params_dev, sums_dev, h, w, thresh, tb);
     HB_LAUNCH_OK("inpaint_scan_kernel");
     long blocks = ((long)n + 255) / 256;
     const long cap = (long)hb_sm_count() * 16;

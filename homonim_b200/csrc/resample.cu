@@ -7,6 +7,9 @@
 //   * hb_apply_same_grid, hb_valid_mask, hb_full_coverage_mask                (kernel_model.py:375-409, 442-463)
 //
 // The GDAL algorithms restated here are specified in oracle/gdal_restate.c (GDAL itself is not in this image).
+#include <limits.h>
+#include <type_traits>
+
 #include "hb_common.cuh"
 
 namespace {
@@ -82,7 +85,7 @@ __device__ __forceinline__ void ds_fetch(const T *row, long c, long ws, T (&v)[8
 // <= 2 fractionally covered rows are added in double).  Phase 2: one thread per destination pixel combines its
 // footprint columns from shared memory with the fractional edge weights.
 template <typename T, bool ALIGNED>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 downsample_average_kernel(const T *__restrict__ src, long hs, long ws, NoData nd, float *__restrict__ dst, long hd,
                           long wd, double sx, double ox, double sy, double oy, int ndc, int chunks)
 {
@@ -128,19 +131,77 @@ downsample_average_kernel(const T *__restrict__ src, long hs, long ws, NoData nd
         uint32_t isum[8], icnt[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) { isum[k] = 0; icnt[k] = 0; }
-#pragma unroll 4
-        for (long y = ya; y < yb; y++) {
-            T v[8]; uint32_t inb;
-            ds_fetch<T, ALIGNED>(src + y * ws, c, ws, v, inb);
+        if (ALIGNED && c >= 0 && c + 8 <= ws) {
+            // Fast path (every vector of this thread lies inside the raster).  Sum ALL pixels with one integer
+            // dot-product instruction per pixel (IDP: dp2a / dp4a against a one-hot byte vector -- no unpacking), and
+            // only look for nodata with a packed "has a zero field" test on (word ^ nodata pattern); the exact
+            // per-pixel count of nodata pixels runs only for words that may contain one.  Afterwards
+            //     sum(valid) = sum(all) - nodata * count(nodata),  count(valid) = rows - count(nodata)   (exact).
+            constexpr int NW = (sizeof(T) == 2) ? 4 : 2;                   // 32-bit words per 8 pixels
+            constexpr uint32_t kOnes = (sizeof(T) == 2) ? 0x00010001u : 0x01010101u;
+            constexpr uint32_t kHigh = (sizeof(T) == 2) ? 0x80008000u : 0x80808080u;
+            const bool scan_nd = ndk.int_ok && (sizeof(T) == 2 || ndk.ivalue <= 255);
+            const uint32_t ndpat = scan_nd ? (uint32_t)ndk.ivalue * kOnes : 0u;
+            uint32_t ndc[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) ndc[k] = 0;
+            const T *p = src + ya * ws + c;
+#pragma unroll 10
+            for (long y = ya; y < yb; y++, p += ws) {
+                uint32_t w[4];
+                if (sizeof(T) == 2) {
+                    const uint4 v = hb_ldg_stream16(p);
+                    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+                } else {
+                    const uint2 v = hb_ldg_stream8(p);
+                    w[0] = v.x; w[1] = v.y; w[2] = 0; w[3] = 0;
+                }
+                uint32_t anyz = 0;
+#pragma unroll
+                for (int i = 0; i < NW; i++) {
+                    if (sizeof(T) == 2) {
+                        isum[2 * i] = __dp2a_lo(w[i], 0x0001u, isum[2 * i]);
+                        isum[2 * i + 1] = __dp2a_lo(w[i], 0x0100u, isum[2 * i + 1]);
+                    } else {
+                        isum[4 * i] = __dp4a(w[i], 0x00000001u, isum[4 * i]);
+                        isum[4 * i + 1] = __dp4a(w[i], 0x00000100u, isum[4 * i + 1]);
+                        isum[4 * i + 2] = __dp4a(w[i], 0x00010000u, isum[4 * i + 2]);
+                        isum[4 * i + 3] = __dp4a(w[i], 0x01000000u, isum[4 * i + 3]);
+                    }
+                    const uint32_t x = w[i] ^ ndpat;
+                    anyz |= (x - kOnes) & ~x;
+                }
+                if (scan_nd && (anyz & kHigh)) {                            // rare: some pixel may be nodata
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const uint32_t word = (sizeof(T) == 2) ? w[k >> 1] : w[k >> 2];
+                        const uint32_t v = (sizeof(T) == 2) ? ((word >> (16 * (k & 1))) & 0xFFFFu)
+                                                            : ((word >> (8 * (k & 3))) & 0xFFu);
+                        ndc[k] += (v == (uint32_t)ndk.ivalue) ? 1u : 0u;
+                    }
+                }
+            }
+            const uint32_t nrows = (uint32_t)(yb > ya ? yb - ya : 0);
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                const bool ok = ((inb >> k) & 1u) && ds_valid<T>(v[k], ndk);
-                isum[k] += ok ? (uint32_t)v[k] : 0u;
-                icnt[k] += ok ? 1u : 0u;
+                colsum[k] = (double)(isum[k] - (scan_nd ? (uint32_t)ndk.ivalue * ndc[k] : 0u));
+                colw[k] = (double)(nrows - ndc[k]);
             }
-        }
+        } else {
+#pragma unroll 4
+            for (long y = ya; y < yb; y++) {
+                T v[8]; uint32_t inb;
+                ds_fetch<T, ALIGNED>(src + y * ws, c, ws, v, inb);
 #pragma unroll
-        for (int k = 0; k < 8; k++) { colsum[k] = (double)isum[k]; colw[k] = (double)icnt[k]; }
+                for (int k = 0; k < 8; k++) {
+                    const bool ok = ((inb >> k) & 1u) && ds_valid<T>(v[k], ndk);
+                    isum[k] += ok ? (uint32_t)v[k] : 0u;
+                    icnt[k] += ok ? 1u : 0u;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) { colsum[k] = (double)isum[k]; colw[k] = (double)icnt[k]; }
+        }
     } else {
         uint32_t icnt[8];
 #pragma unroll
@@ -188,13 +249,18 @@ downsample_average_kernel(const T *__restrict__ src, long hs, long ws, NoData nd
         const long ix0 = max(ix0u, 0L), ix1 = min(ix1u, ws);
         float out = qnan;
         double total = 0.0, total_w = 0.0;
-        for (long x = ix0; x < ix1; x++) {
+        // neighbouring threads start `ratio` columns apart: rotate each thread's starting column so that the 64-bit
+        // shared-memory reads of a warp spread over the banks (the sum is over the same terms, in a fixed order)
+        const long ncol = ix1 - ix0;
+        long x = ix0 + ((ncol > 0) ? (long)(t % (int)ncol) : 0);
+        for (long i = 0; i < ncol; i++) {
             double wx = 1.0;
             if (x == ix0u) wx = (ix0u + 1 == ix1u) ? 1.0 : 1.0 - (x_min - (double)ix0u);
             else if (x + 1 == ix1u) wx = 1.0 - ((double)ix1u - x_max);
             const int s = (int)(x - c_base);
             total += wx * s_sum[s];
             total_w += wx * s_w[s];
+            if (++x == ix1) x = ix0;
         }
         if (total_w > 0.0) out = (float)(total / total_w);
         dst[i * wd + j] = out;
@@ -226,323 +292,365 @@ int launch_downsample(const void *src, long hs, long ws, NoData nd, float *dst, 
 // =====================================================================================================================
 // 2. cubic-spline up-sampling, optionally fused with the apply step
 // =====================================================================================================================
-// Per destination row the 4x4 B-spline interpolation is separated: (A) each coarse column is combined down its 4 tap
-// rows with the row's y-weights (invalid / out-of-range taps dropped, their weight tracked), (B) each coarse cell gets
-// the cubic polynomial in dx = frac(x) of its 4 tap columns -- value polynomials for both bands and, only when a tap
-// is missing, weight polynomials for GDAL's renormalisation -- and (C) every destination pixel evaluates its cell's
-// polynomial by Horner, fused with corr = gain*src + offset.  A/B for rows y+2 / y+1 overlap C for row y, one
-// __syncthreads per row.
-struct __align__(16) CellPoly {
-    double g[4];   // band 0 (gain) polynomial
-    double o[4];   // band 1 (offset) polynomial
+// GDAL GRA_CubicSpline (4x4 cubic B-spline taps, invalid / out-of-range taps dropped and the rest renormalised; spec in
+// oracle/gdal_restate.c) evaluated separably.  After a one-off per-CTA table of the rows' y-weights, every WARP is
+// autonomous (no further CTA barrier): it owns a 128-pixel-wide column strip (4 pixels per lane, vector stores) and
+// walks down it in batches of 4 rows:
+//   A. lane <-> coarse column (MC columns per lane when the ratio is small).  The column's 4 tap rows live in
+//      registers (invalid taps zeroed, validity kept as a bit mask) and are only re-fetched when the tap rows change
+//      (every `ratio` destination rows); per row the lane combines them with the row's y-weights into warp-private
+//      shared memory -- 8 FMAs when all taps are valid;
+//   C. lane <-> 4 destination pixels, whose source values arrive through a 4-deep cp.async ring (each lane copies and
+//      later reads only its own bytes): each pixel sums its 4 column combinations with its x-weights (registers, row
+//      invariant) and -- in APPLY mode -- writes gain*src + offset; the up-sampled parameters never exist in memory.
+// A warp-uniform "clean" flag (every tap of the batch valid and in range) selects a C phase without any flag or
+// renormalisation work; only batches touching nodata or the raster edge take the general path.
+struct __align__(16) Pair { double g, o; };          // band 0 (gain) and band 1 (offset)
+struct __align__(16) RowInfo {
+    double wy[4];     // y-weights of tap rows ky-1 .. ky+2
+    int ky;           // first tap row + 1
+    int jc;           // tap row hosting the centre pixel (1 or 2; 0 when clamped), -1: centre row out of range
+    int cy;           // coarse row of the centre pixel
+    int pad;
 };
-struct __align__(16) ColComb {
-    double ag, ao;   // sum_j wy_j * v_j over valid taps, per band
-    double mg, mo;   // sum_j wy_j over valid taps, per band
-};
 
-constexpr int kUpRows = 32;   // destination rows per CTA
+constexpr int kUpPpt = 4;                             // destination pixels per lane
+constexpr int kUpWarpW = 32 * kUpPpt;                 // destination columns per warp
+constexpr int kUpWarps = kThreads / 32;
+constexpr int kUpRb = 4;                              // rows per batch
+constexpr int kUpStages = 4;                          // batches of source rows in flight per warp (cp.async ring)
+constexpr int kUpMaxRows = 64;                        // destination rows per CTA (upper bound)
 
-__device__ __forceinline__ double bspline_w(int tap, double d)   // tap in {-1,0,1,2}, weight B(tap - d)
+__device__ __forceinline__ void bspline_weights(double d, double (&w)[4])   // taps -1, 0, 1, 2: B(tap - d)
 {
-    const double u = 1.0 - d;
-    switch (tap) {
-        case -1: return u * u * u * (1.0 / 6.0);
-        case 0: return (4.0 + d * d * (3.0 * d - 6.0)) * (1.0 / 6.0);
-        case 1: return (1.0 + d * (3.0 + d * (3.0 - 3.0 * d))) * (1.0 / 6.0);
-        default: return d * d * d * (1.0 / 6.0);
-    }
+    const double u = 1.0 - d, d2 = d * d, u2 = u * u;
+    w[0] = u2 * u * (1.0 / 6.0);
+    w[1] = (4.0 + d2 * (3.0 * d - 6.0)) * (1.0 / 6.0);
+    w[2] = (4.0 + u2 * (3.0 * u - 6.0)) * (1.0 / 6.0);
+    w[3] = d2 * d * (1.0 / 6.0);
 }
 
-__device__ __forceinline__ void poly_from_taps(double a_m1, double a_0, double a_1, double a_2, double (&p)[4])
+// asynchronous global -> shared copy of one lane's 4 source pixels (LDGSTS; completion via wait_group)
+template <int BYTES> __device__ __forceinline__ void cp_async_lane(uint32_t smem_dst, const void *gmem_src)
 {
-    p[0] = (a_m1 + 4.0 * a_0 + a_1) * (1.0 / 6.0);
-    p[1] = (a_1 - a_m1) * 0.5;
-    p[2] = (a_m1 - 2.0 * a_0 + a_1) * 0.5;
-    p[3] = ((a_2 - a_m1) + 3.0 * (a_0 - a_1)) * (1.0 / 6.0);
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_dst), "l"(gmem_src), "n"(BYTES) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ double horner3(const double (&p)[4], double d)
-{
-    return fma(fma(fma(p[3], d, p[2]), d, p[1]), d, p[0]);
-}
-
-template <typename T> struct SrcVec4;   // 4 consecutive source pixels -> float32
-template <> struct SrcVec4<uint16_t> {
-    static __device__ __forceinline__ void load(const uint16_t *p, float (&v)[4])
+// 4 source pixels of storage type T -> float32, plus their validity against the nodata value
+template <typename T> struct Src4;
+template <> struct Src4<uint16_t> {
+    static constexpr int kBytes = 8;
+    static __device__ __forceinline__ void get(const void *p, const NoData &nd, float (&v)[4], bool (&ok)[4])
     {
-        const uint2 w = hb_ldg_stream8(p);
-        v[0] = hb_to_f32<uint16_t>((uint16_t)(w.x & 0xFFFFu)); v[1] = hb_to_f32<uint16_t>((uint16_t)(w.x >> 16));
-        v[2] = hb_to_f32<uint16_t>((uint16_t)(w.y & 0xFFFFu)); v[3] = hb_to_f32<uint16_t>((uint16_t)(w.y >> 16));
-    }
-    static constexpr int kAlign = 8;
-};
-template <> struct SrcVec4<uint8_t> {
-    static __device__ __forceinline__ void load(const uint8_t *p, float (&v)[4])
-    {
-        const uint32_t w = hb_ldg_stream4(p);
+        const uint2 w = *reinterpret_cast<const uint2 *>(p);
+        const uint32_t r[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
 #pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = hb_to_f32<uint8_t>((uint8_t)((w >> (8 * k)) & 0xFFu));
+        for (int k = 0; k < 4; k++) {
+            v[k] = __uint_as_float(0x4B000000u | r[k]) - 8388608.0f;      // exact, no I2F
+            ok[k] = (int)r[k] != nd.ivalue;                                // ivalue = -1 when no integer nodata
+        }
     }
-    static constexpr int kAlign = 4;
 };
-template <> struct SrcVec4<float> {
-    static __device__ __forceinline__ void load(const float *p, float (&v)[4])
+template <> struct Src4<uint8_t> {
+    static constexpr int kBytes = 4;
+    static __device__ __forceinline__ void get(const void *p, const NoData &nd, float (&v)[4], bool (&ok)[4])
     {
-        const uint4 w = hb_ldg_stream16(p);
-        v[0] = __uint_as_float(w.x); v[1] = __uint_as_float(w.y); v[2] = __uint_as_float(w.z);
-        v[3] = __uint_as_float(w.w);
+        const uint32_t w = *reinterpret_cast<const uint32_t *>(p);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t r = (w >> (8 * k)) & 0xFFu;
+            v[k] = __uint_as_float(0x4B000000u | r) - 8388608.0f;
+            ok[k] = (int)r != nd.ivalue;
+        }
     }
-    static constexpr int kAlign = 16;
+};
+template <> struct Src4<float> {
+    static constexpr int kBytes = 16;
+    static __device__ __forceinline__ void get(const void *p, const NoData &nd, float (&v)[4], bool (&ok)[4])
+    {
+        const float4 w = *reinterpret_cast<const float4 *>(p);
+        v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
+#pragma unroll
+        for (int k = 0; k < 4; k++) ok[k] = hb_valid(v[k], nd);
+    }
 };
 
 struct UpGeom {
     long hs, ws;          // destination (fine) grid
     long hp, wp;          // coarse grid
     double sx, ox, sy, oy;
-    int ncols;            // coarse columns staged per CTA (cells + 3)
-    int tile_w;           // destination columns per CTA
+    int ncols;            // coarse columns staged per warp (cells + 3)
+    int rows_per_cta;
 };
 
-// T: storage type of the source plane (APPLY); NB: number of coarse bands (1 or 2); APPLY: fuse gain*src+offset
-template <typename T, int NB, bool APPLY, int PPT, bool ALIGNED>
-__global__ void __launch_bounds__(kThreads)
+// T: storage type of the source plane (APPLY); NB: coarse bands (1 or 2); APPLY: fuse gain*src+offset;
+// MC: coarse columns per lane (ncols <= 32 * MC)
+template <typename T, int NB, bool APPLY, bool ALIGNED, int MC>
+__global__ void __launch_bounds__(kThreads, 2)
 upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ coarse, UpGeom g,
                 const uint8_t *__restrict__ cover, float *__restrict__ out)
 {
+    constexpr int PPT = kUpPpt;
     constexpr int NOUT = (NB == 2 && !APPLY) ? 2 : 1;
+    constexpr int kLaneBytes = APPLY ? Src4<T>::kBytes : 0;
+    constexpr int kRowBytes = 32 * kLaneBytes;                            // one staged source row of the warp
+    constexpr int kRingBytes = kUpStages * kUpRb * kRowBytes;
+    constexpr unsigned kFullMask = (NB == 2) ? 0xFFu : 0x0Fu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ncols = g.ncols;
-    ColComb *s_col = reinterpret_cast<ColComb *>(smem_raw);            // [2][ncols]  stage A -> B
-    CellPoly *s_poly = reinterpret_cast<CellPoly *>(s_col + 2 * ncols);   // [2][ncols]  stage B -> C  (values)
-    CellPoly *s_wpoly = s_poly + 2 * ncols;                              // [2][ncols]  stage B -> C  (weights)
-    uint8_t *s_miss = reinterpret_cast<uint8_t *>(s_wpoly + 2 * ncols);  // [2][ncols]  A -> B: column has a missing tap
-    uint8_t *s_cokA = s_miss + 2 * ncols;                                // [2][ncols]  A -> B: centre pixel usable
-    uint8_t *s_norm = s_cokA + 2 * ncols;                                // [2][ncols]  B -> C: cell needs renormalising
-    uint8_t *s_cok = s_norm + 2 * ncols;                                 // [2][ncols]  B -> C: centre pixel usable
-
-    const int t = threadIdx.x;
-    const long Xt0 = (long)blockIdx.x * g.tile_w;                  // first destination column of the tile
-    const long X0 = Xt0 + (long)t * PPT;                           // first destination column of this thread
-    const bool px_thread = (t * PPT < g.tile_w) && (X0 < g.ws);
-    const long Y0 = (long)blockIdx.y * kUpRows;
-    const long Y1 = min(Y0 + (long)kUpRows, g.hs);
-    const long plane = g.hp * g.wp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long Y0 = (long)blockIdx.y * g.rows_per_cta;
+    const long Y1 = min(Y0 + (long)g.rows_per_cta, g.hs);
     const float qnan = __int_as_float(0x7fc00000);
 
-    // coarse column window of the tile: the taps of the tile's first pixel start at column kx - 1
-    const double srcx_t0 = g.sx * ((double)Xt0 + 0.5) + g.ox;
-    const long col_base = (long)floor(srcx_t0 - 0.5) - 1;
+    // ---- per-CTA row table: y-weights, tap rows and centre rows of the CTA's destination rows ---------------------
+    RowInfo *s_rows = reinterpret_cast<RowInfo *>(smem_raw);
+    if ((long)threadIdx.x < Y1 - Y0) {
+        const double srcy = g.sy * ((double)(Y0 + threadIdx.x) + 0.5) + g.oy;
+        const long ky = (long)floor(srcy - 0.5);
+        RowInfo ri;
+        bspline_weights(srcy - 0.5 - (double)ky, ri.wy);
+        long cy = (long)floor(srcy + 1e-10);
+        if (cy == g.hp) cy--;
+        const bool cy_ok = (srcy >= 0.0) && cy >= 0 && cy < g.hp;
+        ri.ky = (int)ky;
+        ri.jc = cy_ok ? (int)(cy - (ky - 1)) : -1;          // 1 or 2 (0 when clamped at the bottom edge)
+        ri.cy = (int)cy;
+        ri.pad = 0;
+        s_rows[threadIdx.x] = ri;
+    }
+    __syncthreads();                                        // the only CTA barrier
 
-    // per-pixel, row-invariant: cell (index of its first tap column in the window), dx, centre column in the window
-    int cell[PPT], ccol[PPT];
-    double dx[PPT];
+    // warp-private shared memory: values [RB][ncols], weights [RB][ncols], column flags [RB][ncols], source ring
+    const int comb_bytes = ((kUpRb * ncols * (2 * (int)sizeof(Pair) + 1)) + 15) / 16 * 16;
+    unsigned char *base = smem_raw + kUpMaxRows * sizeof(RowInfo) + warp * (comb_bytes + kRingBytes);
+    Pair *s_val = reinterpret_cast<Pair *>(base);
+    Pair *s_wgt = s_val + kUpRb * ncols;
+    uint8_t *s_colf = reinterpret_cast<uint8_t *>(s_wgt + kUpRb * ncols);   // bit0: a tap missing, bit1: centre usable
+    const unsigned char *s_ring = base + comb_bytes + lane * kLaneBytes;     // this lane's slot in a staged row
+    const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(s_ring);
+
+    const long Xw0 = ((long)blockIdx.x * kUpWarps + warp) * kUpWarpW;    // first destination column of the warp
+    if (Xw0 >= g.ws) return;
+    const long X0 = Xw0 + (long)lane * PPT;
+    const long plane = g.hp * g.wp;
+
+    // coarse column window of the warp: the taps of its first pixel start at column kx - 1
+    const double srcx_w0 = g.sx * ((double)Xw0 + 0.5) + g.ox;
+    const long col_base = (long)floor(srcx_w0 - 0.5) - 1;
+
+    // ---- per-pixel, row-invariant: x-weights, byte offset of the first tap column, where the centre sits ----------
+    double wx[PPT][4];
+    int voff[PPT];                                          // first tap column * sizeof(Pair)
+    int ctap[PPT];                                          // tap column hosting the centre (0..3), -1: none usable
 #pragma unroll
     for (int k = 0; k < PPT; k++) {
         const double srcx = g.sx * ((double)(X0 + k) + 0.5) + g.ox;
         const long kx = (long)floor(srcx - 0.5);
-        dx[k] = srcx - 0.5 - (double)kx;
+        bspline_weights(srcx - 0.5 - (double)kx, wx[k]);
         long cl = kx - 1 - col_base;
         long cx = (long)floor(srcx + 1e-10);
         if (cx == g.wp) cx--;
         const bool okx = (srcx >= 0.0) && (cx >= 0) && (cx < g.wp);
-        long cc = okx ? (cx - col_base) : -1;
-        if (cl < 0 || cl + 3 >= ncols || cc >= ncols) { cl = 0; cc = -1; }   // outside the staged window: X >= ws
-        cell[k] = (int)cl;
-        ccol[k] = (int)cc;
+        int ct = -1;
+        if (cl < 0 || cl + 3 >= ncols) cl = 0;              // only for X >= ws (never stored)
+        else if (okx) ct = (int)(cx - (kx - 1));            // 1 or 2 (0 when clamped at the right edge)
+        voff[k] = (int)cl * (int)sizeof(Pair);
+        ctap[k] = (ct >= 0 && ct < 4) ? ct : -1;
     }
 
-    // ---- stage A: combine coarse column (col_base + t) down the 4 tap rows of destination row Y -------------------
-    // the 4 tap rows are cached in registers and shifted when ky advances
-    float tap_v[NB][4];
-    bool tap_ok[NB][4];
+    // ---- per-lane coarse columns: the 4 tap rows are cached in registers, invalid taps as 0 + a validity mask -------
+    float tv[MC][NB][4];
+    unsigned tmask[MC];                                     // bit (b * 4 + j): tap row j of band b is valid
 #pragma unroll
-    for (int b = 0; b < NB; b++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) { tap_v[b][j] = qnan; tap_ok[b][j] = false; }
-    long cached_ky = -(1L << 60);
-    const long my_col = col_base + t;
-    const bool col_thread = (t < ncols);
-    const bool col_inside = col_thread && my_col >= 0 && my_col < g.wp;
+    for (int m = 0; m < MC; m++) tmask[m] = 0;
+    int cached_ky = INT_MIN;
+    const bool full_vec = (X0 + PPT <= g.ws);
+    const bool use_async = APPLY && ALIGNED && full_vec;    // this lane's pixels come through the cp.async ring
 
-    auto stage_a = [&](long Y, int buf) {
-        if (!col_thread) return;
-        const double srcy = g.sy * ((double)Y + 0.5) + g.oy;
-        const long ky = (long)floor(srcy - 0.5);
-        const double dy = srcy - 0.5 - (double)ky;
-        if (ky != cached_ky) {
-            const bool shift1 = (ky - cached_ky) == 1;
+    auto prefetch = [&](long Yp, int stage) {
+        if (use_async) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const long row = ky - 1 + j;
-                const bool inside = col_inside && row >= 0 && row < g.hp;
+            for (int rr = 0; rr < kUpRb; rr++)
+                if (Yp + rr < Y1)
+                    cp_async_lane<kLaneBytes>(ring_sa + (stage * kUpRb + rr) * kRowBytes, src + (Yp + rr) * g.ws + X0);
+        }
+        cp_async_commit();
+    };
+    if (APPLY) {
 #pragma unroll
-                for (int b = 0; b < NB; b++) {
-                    if (shift1 && j < 3) {
-                        tap_v[b][j] = tap_v[b][j + 1];
-                        tap_ok[b][j] = tap_ok[b][j + 1];
+        for (int st = 0; st < kUpStages - 1; st++) prefetch(Y0 + (long)st * kUpRb, st);
+    }
+
+    int batch = 0;
+    for (long Yb = Y0; Yb < Y1; Yb += kUpRb, batch++) {
+        const int nrows = (int)min((long)kUpRb, Y1 - Yb);
+        if (APPLY) prefetch(Yb + (long)(kUpStages - 1) * kUpRb, (batch + kUpStages - 1) % kUpStages);
+
+        // ---- phase A: column combinations for the rows of the batch -------------------------------------------------
+        bool clean = true;
+        for (int rr = 0; rr < nrows; rr++) {
+            const RowInfo ri = s_rows[Yb - Y0 + rr];
+            if (ri.ky != cached_ky) {                       // (warp-uniform) fetch / shift the tap rows
+                const bool shift1 = (ri.ky - cached_ky) == 1;
+#pragma unroll
+                for (int m = 0; m < MC; m++) {
+                    const long col = col_base + lane + 32 * m;
+                    const bool col_in = (lane + 32 * m < ncols) && col >= 0 && col < g.wp;
+                    unsigned mask = shift1 ? ((tmask[m] >> 1) & 0x77u) : 0u;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const long row = (long)ri.ky - 1 + j;
+                        const bool inside = col_in && row >= 0 && row < g.hp;
+#pragma unroll
+                        for (int b = 0; b < NB; b++) {
+                            if (shift1 && j < 3) {
+                                tv[m][b][j] = tv[m][b][j + 1];
+                            } else {
+                                const float v = inside ? __ldg(coarse + b * plane + row * g.wp + col) : qnan;
+                                const bool ok = !isnan(v);
+                                tv[m][b][j] = ok ? v : 0.f;
+                                if (ok) mask |= 1u << (b * 4 + j);
+                            }
+                        }
+                    }
+                    tmask[m] = mask;
+                }
+                cached_ky = ri.ky;
+            }
+#pragma unroll
+            for (int m = 0; m < MC; m++) {
+                const int c = lane + 32 * m;
+                if (c < ncols) {
+                    // invalid taps are stored as 0: the value sums need no predication
+                    Pair val;
+                    val.g = fma(ri.wy[3], (double)tv[m][0][3], fma(ri.wy[2], (double)tv[m][0][2],
+                            fma(ri.wy[1], (double)tv[m][0][1], ri.wy[0] * (double)tv[m][0][0])));
+                    val.o = 0.0;
+                    if (NB > 1)
+                        val.o = fma(ri.wy[3], (double)tv[m][1][3], fma(ri.wy[2], (double)tv[m][1][2],
+                                fma(ri.wy[1], (double)tv[m][1][1], ri.wy[0] * (double)tv[m][1][0])));
+                    s_val[rr * ncols + c] = val;
+                    const unsigned mask = tmask[m];
+                    const bool all_ok = (mask == kFullMask);
+                    // centre pixel: its coarse pixel must be in range and valid in any band (+ the coverage mask)
+                    bool c_ok = (ri.jc >= 0) && (((mask | (mask >> 4)) >> ri.jc) & 1u);
+                    if (c_ok && cover != nullptr) c_ok = cover[(long)ri.cy * g.wp + col_base + c] != 0;
+                    if (!all_ok) {
+                        // a band's tap counts iff that band is valid there (band-valid implies "any band" validity)
+                        Pair wgt = {0.0, 0.0};
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if ((mask >> j) & 1u) wgt.g += ri.wy[j];
+                            if (NB > 1 && ((mask >> (4 + j)) & 1u)) wgt.o += ri.wy[j];
+                        }
+                        s_wgt[rr * ncols + c] = wgt;
+                    }
+                    s_colf[rr * ncols + c] = (uint8_t)((all_ok ? 0 : 1) | (c_ok ? 2 : 0));
+                    clean = clean && all_ok && c_ok;
+                }
+            }
+        }
+        clean = __all_sync(0xffffffffu, clean);             // also orders the shared-memory writes above
+        __syncwarp();
+        if (APPLY) cp_async_wait<kUpStages - 1>();          // this batch's source rows have landed
+        const unsigned char *ring_b = s_ring + ((batch % kUpStages) * kUpRb) * kRowBytes;
+
+        // ---- phase C: destination pixels ----------------------------------------------------------------------------
+        auto phase_c = [&](auto clean_tag) {
+            constexpr bool CLEAN = decltype(clean_tag)::value;
+            const unsigned char *v_row = reinterpret_cast<const unsigned char *>(s_val);
+            float *orow = out + Yb * g.ws + X0;
+#pragma unroll 2
+            for (int rr = 0; rr < nrows; rr++, v_row += ncols * sizeof(Pair), orow += g.ws) {
+                float s[PPT];
+                bool ok[PPT];
+                if constexpr (APPLY) {
+                    if (use_async) {
+                        Src4<T>::get(ring_b + rr * kRowBytes, nd, s, ok);
                     } else {
-                        const float v = inside ? __ldg(coarse + b * plane + row * g.wp + my_col) : qnan;
-                        tap_v[b][j] = v;
-                        tap_ok[b][j] = inside && !isnan(v);
+                        const T *row = src + (Yb + rr) * g.ws;
+#pragma unroll
+                        for (int k = 0; k < PPT; k++) {
+                            const bool in_row = (X0 + k) < g.ws;
+                            s[k] = in_row ? hb_to_f32<T>(row[X0 + k]) : 0.f;
+                            ok[k] = in_row && hb_valid(s[k], nd);
+                        }
                     }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < PPT; k++) { s[k] = 0.f; ok[k] = (X0 + k) < g.ws; }
                 }
-            }
-            cached_ky = ky;
-        }
-        ColComb cc = {0.0, 0.0, 0.0, 0.0};
-        bool all_ok = true;
+                float res[NOUT][PPT];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const double wy = bspline_w(j - 1, dy);
-            // a band's tap counts iff that band is valid there (band-valid implies unified "any band" validity)
-            if (tap_ok[0][j]) { cc.ag = fma(wy, (double)tap_v[0][j], cc.ag); cc.mg += wy; } else all_ok = false;
-            if (NB > 1) {
-                if (tap_ok[1][j]) { cc.ao = fma(wy, (double)tap_v[1][j], cc.ao); cc.mo += wy; } else all_ok = false;
-            }
-        }
-        s_col[buf * ncols + t] = cc;
-        s_miss[buf * ncols + t] = all_ok ? 0 : 1;
-        // centre pixel: the coarse pixel containing the destination centre must be in range and valid in any band
-        long cy = (long)floor(srcy + 1e-10);
-        if (cy == g.hp) cy--;
-        bool cok = (srcy >= 0.0) && cy >= 0 && cy < g.hp && col_inside;
-        if (cok) {
-            // cy is ky or ky + 1 (tap row 1 or 2), or ky - 1 (tap row 0) when clamped at the bottom edge
-            const int j = (int)(cy - (ky - 1));
-            bool any = false;
-#pragma unroll
-            for (int jj = 0; jj < 4; jj++) {
-                if (jj == j) {
-                    any = tap_ok[0][jj];
-                    if (NB > 1) any = any || tap_ok[1][jj];
-                }
-            }
-            cok = any;
-            if (cok && cover != nullptr) cok = cover[cy * g.wp + my_col] != 0;
-        }
-        s_cokA[buf * ncols + t] = cok ? 1 : 0;
-    };
-
-    // ---- stage B: polynomials of the cell whose taps are staged columns t .. t+3 -----------------------------------
-    auto stage_b = [&](int buf) {
-        if (!col_thread) return;
-        s_cok[buf * ncols + t] = s_cokA[buf * ncols + t];
-        if (t + 3 >= ncols) return;
-        const ColComb *c = s_col + buf * ncols + t;
-        CellPoly p;
-        poly_from_taps(c[0].ag, c[1].ag, c[2].ag, c[3].ag, p.g);
-        if (NB > 1) poly_from_taps(c[0].ao, c[1].ao, c[2].ao, c[3].ao, p.o);
-        else { p.o[0] = p.o[1] = p.o[2] = p.o[3] = 0.0; }
-        s_poly[buf * ncols + t] = p;
-        const uint8_t *f = s_miss + buf * ncols + t;
-        const bool missing = (f[0] | f[1] | f[2] | f[3]) != 0;
-        if (missing) {
-            CellPoly w;
-            poly_from_taps(c[0].mg, c[1].mg, c[2].mg, c[3].mg, w.g);
-            if (NB > 1) poly_from_taps(c[0].mo, c[1].mo, c[2].mo, c[3].mo, w.o);
-            else { w.o[0] = w.o[1] = w.o[2] = w.o[3] = 0.0; }
-            s_wpoly[buf * ncols + t] = w;
-        }
-        s_norm[buf * ncols + t] = missing ? 1 : 0;
-    };
-
-    // software pipeline prologue
-    stage_a(Y0, 0);
-    __syncthreads();
-    stage_b(0);
-    if (Y0 + 1 < Y1) stage_a(Y0 + 1, 1);
-    __syncthreads();
-
-    for (long Y = Y0; Y < Y1; Y++) {
-        const int buf = (int)((Y - Y0) & 1);
-        // ---- stage C: destination pixels of row Y -------------------------------------------------------------------
-        if (px_thread) {
-            float s[PPT];
-            bool in_row[PPT];
-            const bool full_vec = (X0 + PPT <= g.ws);
-            if constexpr (APPLY) {
-                const T *row = src + Y * g.ws;
-                bool loaded = false;
-                if constexpr (ALIGNED && PPT == 4) {
-                    if (full_vec) {
-                        SrcVec4<T>::load(row + X0, s);
-#pragma unroll
-                        for (int k = 0; k < PPT; k++) in_row[k] = true;
-                        loaded = true;
-                    }
-                }
-                if (!loaded) {
-#pragma unroll
-                    for (int k = 0; k < PPT; k++) {
-                        in_row[k] = (X0 + k) < g.ws;
-                        s[k] = in_row[k] ? hb_to_f32<T>(row[X0 + k]) : 0.f;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < PPT; k++) { in_row[k] = (X0 + k) < g.ws; s[k] = 0.f; }
-            }
-            float res[NOUT][PPT];
-#pragma unroll
-            for (int k = 0; k < PPT; k++) {
-                float r0 = qnan, r1 = qnan;
-                bool ok = in_row[k] && ccol[k] >= 0 && s_cok[buf * ncols + (ccol[k] < 0 ? 0 : ccol[k])];
-                if (APPLY) ok = ok && hb_valid(s[k], nd);
-                if (ok) {
-                    const CellPoly &p = s_poly[buf * ncols + cell[k]];
-                    double gv = horner3(p.g, dx[k]);
-                    double ov = (NB > 1) ? horner3(p.o, dx[k]) : 0.0;
-                    bool g_ok = true, o_ok = true;
-                    if (s_norm[buf * ncols + cell[k]]) {
-                        // GDAL GWKResample: drop if sum(w) < 1e-6, divide unless sum(w) is within 1e-5 of 1
-                        const CellPoly &w = s_wpoly[buf * ncols + cell[k]];
-                        const double wg = horner3(w.g, dx[k]);
-                        if (wg < 0.000001) g_ok = false;
-                        else if (wg < 0.99999 || wg > 1.00001) gv /= wg;
-                        if (NB > 1) {
-                            const double wo = horner3(w.o, dx[k]);
-                            if (wo < 0.000001) o_ok = false;
-                            else if (wo < 0.99999 || wo > 1.00001) ov /= wo;
+                for (int k = 0; k < PPT; k++) {
+                    const Pair *v = reinterpret_cast<const Pair *>(v_row + voff[k]);
+                    const Pair a0 = v[0], a1 = v[1], a2 = v[2], a3 = v[3];
+                    double gv = fma(wx[k][3], a3.g, fma(wx[k][2], a2.g, fma(wx[k][1], a1.g, wx[k][0] * a0.g)));
+                    double ov = 0.0;
+                    if (NB > 1) ov = fma(wx[k][3], a3.o, fma(wx[k][2], a2.o, fma(wx[k][1], a1.o, wx[k][0] * a0.o)));
+                    bool g_ok = ok[k], o_ok = ok[k];
+                    if constexpr (!CLEAN) {                 // batches touching nodata / the raster edge
+                        const int cidx = rr * ncols + (voff[k] >> 4);
+                        const unsigned f0 = s_colf[cidx], f1 = s_colf[cidx + 1], f2 = s_colf[cidx + 2],
+                                       f3 = s_colf[cidx + 3];
+                        const unsigned fc = (ctap[k] == 0) ? f0 : (ctap[k] == 1) ? f1 : (ctap[k] == 2) ? f2
+                                          : (ctap[k] == 3) ? f3 : 0u;
+                        const bool centre_ok = (fc & 2u) != 0;
+                        g_ok = g_ok && centre_ok;
+                        o_ok = o_ok && centre_ok;
+                        if ((f0 | f1 | f2 | f3) & 1u) {
+                            // GDAL GWKResample: drop if sum(w) < 1e-6, divide unless sum(w) is within 1e-5 of 1.
+                            // (columns with all taps valid did not store their weight: it is sum(wy) == 1)
+                            const Pair *w = s_wgt + cidx;
+                            const RowInfo &ri = s_rows[Yb - Y0 + rr];
+                            const double wy_all = (ri.wy[0] + ri.wy[1]) + (ri.wy[2] + ri.wy[3]);
+                            const Pair one = {wy_all, wy_all};
+                            const Pair m0 = (f0 & 1u) ? w[0] : one, m1 = (f1 & 1u) ? w[1] : one,
+                                       m2 = (f2 & 1u) ? w[2] : one, m3 = (f3 & 1u) ? w[3] : one;
+                            const double wg =
+                                fma(wx[k][3], m3.g, fma(wx[k][2], m2.g, fma(wx[k][1], m1.g, wx[k][0] * m0.g)));
+                            if (wg < 0.000001) g_ok = false;
+                            else if (wg < 0.99999 || wg > 1.00001) gv /= wg;
+                            if (NB > 1) {
+                                const double wo =
+                                    fma(wx[k][3], m3.o, fma(wx[k][2], m2.o, fma(wx[k][1], m1.o, wx[k][0] * m0.o)));
+                                if (wo < 0.000001) o_ok = false;
+                                else if (wo < 0.99999 || wo > 1.00001) ov /= wo;
+                            }
                         }
                     }
                     const float gf = g_ok ? (float)gv : qnan;
                     const float of = o_ok ? (float)ov : qnan;
                     if (APPLY) {
-                        r0 = __fadd_rn(__fmul_rn(gf, s[k]), of);   // two roundings, as numpy (kernel_model.py:461)
+                        res[0][k] = __fadd_rn(__fmul_rn(gf, s[k]), of);   // two roundings, as numpy (kernel_model.py:461)
                     } else {
-                        r0 = gf;
-                        r1 = of;
+                        res[0][k] = gf;
+                        if constexpr (NOUT == 2) res[1][k] = of;
                     }
                 }
-                res[0][k] = r0;
-                if constexpr (NOUT == 2) res[1][k] = r1;
-            }
-            float *orow = out + Y * g.ws;
-            bool stored = false;
-            if constexpr (ALIGNED && PPT == 4) {
-                if (full_vec) {
-                    hb_stg_stream16(orow + X0, make_float4(res[0][0], res[0][1], res[0][2], res[0][3]));
+                if (ALIGNED && full_vec) {
+                    hb_stg_stream16(orow, make_float4(res[0][0], res[0][1], res[0][2], res[0][3]));
                     if constexpr (NOUT == 2)
-                        hb_stg_stream16(orow + g.hs * g.ws + X0,
-                                        make_float4(res[1][0], res[1][1], res[1][2], res[1][3]));
-                    stored = true;
-                }
-            }
-            if (!stored) {
+                        hb_stg_stream16(orow + g.hs * g.ws, make_float4(res[1][0], res[1][1], res[1][2], res[1][3]));
+                } else {
 #pragma unroll
-                for (int k = 0; k < PPT; k++) {
-                    if (in_row[k]) {
-                        orow[X0 + k] = res[0][k];
-                        if constexpr (NOUT == 2) orow[g.hs * g.ws + X0 + k] = res[1][k];
+                    for (int k = 0; k < PPT; k++) {
+                        if ((X0 + k) < g.ws) {
+                            orow[k] = res[0][k];
+                            if constexpr (NOUT == 2) orow[g.hs * g.ws + k] = res[1][k];
+                        }
                     }
                 }
             }
+        };
+        if (X0 < g.ws) {
+            if (clean) phase_c(std::true_type{}); else phase_c(std::false_type{});
         }
-        // ---- overlap: polynomials for row Y+1, column combination for row Y+2 ----------------------------------------
-        if (Y + 1 < Y1) stage_b(buf ^ 1);
-        if (Y + 2 < Y1) stage_a(Y + 2, buf);
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -553,31 +661,37 @@ int launch_upsample(const void *src, NoData nd, const float *coarse, long hs, lo
     HB_REQUIRE(sx > 0 && sy > 0 && sx <= 1.0 + 1e-9 && sy <= 1.0 + 1e-9,
                "cubic-spline up-sampling needs a destination grid at least as fine as the source (scale %.4f, %.4f)",
                sx, sy);
-    // 4 pixels per thread when the coarse window of a 1024-pixel tile fits the 256 staging threads, else 1
-    const bool wide = (1024.0 * sx + 6.0) <= (double)kThreads;
+    HB_REQUIRE(hp < 2147483000L && wp < 2147483000L, "coarse raster too large");
     UpGeom g;
     g.hs = hs; g.ws = ws; g.hp = hp; g.wp = wp; g.sx = sx; g.ox = ox; g.sy = sy; g.oy = oy;
-    g.tile_w = wide ? kThreads * 4 : kThreads - 6;
-    g.ncols = (int)ceil((double)g.tile_w * sx) + 5;
-    HB_REQUIRE(g.ncols <= kThreads, "up-sampling tile does not fit its coarse window");
-    const size_t smem = (size_t)g.ncols * 2 * (sizeof(ColComb) + 2 * sizeof(CellPoly) + 4);
-    dim3 grid((unsigned)((ws + g.tile_w - 1) / g.tile_w), (unsigned)((hs + kUpRows - 1) / kUpRows));
+    g.ncols = (int)ceil((double)kUpWarpW * sx) + 5;
+    // rows per CTA: a couple of coarse rows' worth, so that the register-cached tap rows are re-fetched rarely
+    long rpc = (long)ceil(2.0 / sy);
+    rpc = ((rpc + kUpRb - 1) / kUpRb) * kUpRb;
+    if (rpc < 16) rpc = 16;
+    if (rpc > kUpMaxRows) rpc = kUpMaxRows;
+    g.rows_per_cta = (int)rpc;
+    const size_t ring = APPLY ? (size_t)kUpStages * kUpRb * 32 * kUpPpt * sizeof(T) : 0;
+    const size_t per_warp = ((size_t)kUpRb * g.ncols * (2 * sizeof(Pair) + 1) + 15) / 16 * 16 + ring;
+    const size_t smem = kUpMaxRows * sizeof(RowInfo) + per_warp * kUpWarps;
+    const long cta_w = (long)kUpWarpW * kUpWarps;
+    dim3 grid((unsigned)((ws + cta_w - 1) / cta_w), (unsigned)((hs + rpc - 1) / rpc));
     HB_REQUIRE(grid.y <= 65535u, "up-sampling destination has too many rows (%ld)", hs);
-    const size_t align = APPLY ? SrcVec4<T>::kAlign : 16;
-    const bool aligned = wide && (!APPLY || (((ws * (long)sizeof(T)) % (long)align == 0) && (((uintptr_t)src) % align == 0))) &&
+    const size_t align = APPLY ? sizeof(T) * kUpPpt : 16;
+    const bool aligned = (!APPLY || (((ws * (long)sizeof(T)) % (long)align == 0) && (((uintptr_t)src) % align == 0))) &&
                          (ws % 4 == 0) && (((uintptr_t)out) % 16 == 0);
-#define HB_UP_LAUNCH(PPT_, AL_)                                                                                       \
+    NoData ndk = nd;
+    if (!ndk.int_ok) ndk.ivalue = -1;                       // integer sources: no pixel can equal it
+#define HB_UP_LAUNCH(AL_, MC_)                                                                                        \
     do {                                                                                                              \
-        auto kern = upsample_kernel<T, NB, APPLY, PPT_, AL_>;                                                         \
+        auto kern = upsample_kernel<T, NB, APPLY, AL_, MC_>;                                                          \
         if (smem > 48 * 1024)                                                                                         \
             HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-        kern<<<grid, kThreads, smem, stream>>>((const T *)src, nd, coarse, g, cover, out);                            \
+        kern<<<grid, kThreads, smem, stream>>>((const T *)src, ndk, coarse, g, cover, out);                           \
     } while (0)
-    if (wide) {
-        if (aligned) HB_UP_LAUNCH(4, true); else HB_UP_LAUNCH(4, false);
-    } else {
-        HB_UP_LAUNCH(1, false);
-    }
+    if (g.ncols <= 32) { if (aligned) HB_UP_LAUNCH(true, 1); else HB_UP_LAUNCH(false, 1); }
+    else if (g.ncols <= 96) { if (aligned) HB_UP_LAUNCH(true, 3); else HB_UP_LAUNCH(false, 3); }
+    else { if (aligned) HB_UP_LAUNCH(true, 5); else HB_UP_LAUNCH(false, 5); }
 #undef HB_UP_LAUNCH
     HB_LAUNCH_OK("upsample_kernel");
     return 0;
