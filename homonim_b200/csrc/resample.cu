@@ -293,32 +293,40 @@ int launch_downsample(const void *src, long hs, long ws, NoData nd, float *dst, 
 // 2. cubic-spline up-sampling, optionally fused with the apply step
 // =====================================================================================================================
 // GDAL GRA_CubicSpline (4x4 cubic B-spline taps, invalid / out-of-range taps dropped and the rest renormalised; spec in
-// oracle/gdal_restate.c) evaluated separably.  After a one-off per-CTA table of the rows' y-weights, every WARP is
-// autonomous (no further CTA barrier): it owns a 128-pixel-wide column strip (4 pixels per lane, vector stores) and
-// walks down it in batches of 4 rows:
-//   A. lane <-> coarse column (MC columns per lane when the ratio is small).  The column's 4 tap rows live in
-//      registers (invalid taps zeroed, validity kept as a bit mask) and are only re-fetched when the tap rows change
-//      (every `ratio` destination rows); per row the lane combines them with the row's y-weights into warp-private
-//      shared memory -- 8 FMAs when all taps are valid;
-//   C. lane <-> 4 destination pixels, whose source values arrive through a 4-deep cp.async ring (each lane copies and
-//      later reads only its own bytes): each pixel sums its 4 column combinations with its x-weights (registers, row
-//      invariant) and -- in APPLY mode -- writes gain*src + offset; the up-sampled parameters never exist in memory.
-// A warp-uniform "clean" flag (every tap of the batch valid and in range) selects a C phase without any flag or
-// renormalisation work; only batches touching nodata or the raster edge take the general path.
+// oracle/gdal_restate.c).  After a one-off per-CTA table of the rows' y-geometry, every WARP is autonomous (no further
+// CTA barrier): it owns a 128-pixel-wide column strip (4 pixels per lane, vector stores) and walks down it row by row.
+// Source pixels arrive through a 4-deep cp.async ring (each lane copies, and later reads, only its own bytes).
+//
+//   FAST rows (ratio >= 4, every tap of the warp's window valid and in range -- the overwhelming majority).
+//     Inside one coarse cell the interpolated surface is a bicubic polynomial.  When the tap rows change (once per
+//     `ratio` destination rows) every lane interpolates its 4 pixel COLUMNS through the 4 tap rows (x-weights) and
+//     converts the 4 results into the cubic in dy of that pixel column: 4 coefficients per pixel and band, in
+//     registers.  A destination row then costs one Horner evaluation per pixel and band (3 FMAs) -- no shared memory,
+//     no per-row weights -- fused with corr = gain*src + offset.  Mathematically identical to GDAL's sum of 16
+//     weighted taps (sum of weights == 1, so GDAL does not renormalise); evaluated in double like GDAL.
+//   GENERAL rows (windows touching nodata or the raster edge, and all rows when ratio < 4).
+//     A. lane <-> coarse column: combine the column's 4 tap rows (register cache, invalid taps zeroed + validity mask)
+//        with the row's y-weights into warp-private shared memory (values, weight sums, flags);
+//     C. lane <-> 4 pixels: sum the 4 column combinations with the pixel's x-weights, apply GDAL's centre-pixel and
+//        renormalisation rules.
+// In APPLY mode the up-sampled parameters never exist in memory.
 struct __align__(16) Pair { double g, o; };          // band 0 (gain) and band 1 (offset)
 struct __align__(16) RowInfo {
-    double wy[4];     // y-weights of tap rows ky-1 .. ky+2
+    double dy;        // fractional row position inside the cell row
     int ky;           // first tap row + 1
     int jc;           // tap row hosting the centre pixel (1 or 2; 0 when clamped), -1: centre row out of range
     int cy;           // coarse row of the centre pixel
     int pad;
 };
 
+#ifndef HB_UP_MIN_CTAS
+#define HB_UP_MIN_CTAS 2
+#endif
 constexpr int kUpPpt = 4;                             // destination pixels per lane
 constexpr int kUpWarpW = 32 * kUpPpt;                 // destination columns per warp
 constexpr int kUpWarps = kThreads / 32;
-constexpr int kUpRb = 4;                              // rows per batch
-constexpr int kUpStages = 4;                          // batches of source rows in flight per warp (cp.async ring)
+constexpr int kUpRb = 4;                              // rows per cp.async stage
+constexpr int kUpStages = 4;                          // stages of source rows in flight per warp
 constexpr int kUpMaxRows = 64;                        // destination rows per CTA (upper bound)
 
 __device__ __forceinline__ void bspline_weights(double d, double (&w)[4])   // taps -1, 0, 1, 2: B(tap - d)
@@ -384,15 +392,20 @@ struct UpGeom {
     double sx, ox, sy, oy;
     int ncols;            // coarse columns staged per warp (cells + 3)
     int rows_per_cta;
+    int fast;             // the column-polynomial path is worth it (ratio >= 4)
 };
 
 // T: storage type of the source plane (APPLY); NB: coarse bands (1 or 2); APPLY: fuse gain*src+offset;
-// MC: coarse columns per lane (ncols <= 32 * MC)
+// MC: coarse columns per lane (ncols <= 32 * MC).
+// list != nullptr: fix-up mode after upsample_fast_kernel -- every warp takes one (strip, cell row) segment from the
+// list the fast kernel appended to and re-does its rows (source pixels are read directly, not through the ring).
 template <typename T, int NB, bool APPLY, bool ALIGNED, int MC>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, HB_UP_MIN_CTAS)
 upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ coarse, UpGeom g,
-                const uint8_t *__restrict__ cover, float *__restrict__ out)
+                const uint8_t *__restrict__ cover, float *__restrict__ out, const int2 *__restrict__ list,
+                const int *__restrict__ list_count)
 {
+    constexpr bool FAST = false;
     constexpr int PPT = kUpPpt;
     constexpr int NOUT = (NB == 2 && !APPLY) ? 2 : 1;
     constexpr int kLaneBytes = APPLY ? Src4<T>::kBytes : 0;
@@ -402,38 +415,57 @@ upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ncols = g.ncols;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long Y0 = (long)blockIdx.y * g.rows_per_cta;
-    const long Y1 = min(Y0 + (long)g.rows_per_cta, g.hs);
     const float qnan = __int_as_float(0x7fc00000);
+    const bool list_mode = (list != nullptr);
 
-    // ---- per-CTA row table: y-weights, tap rows and centre rows of the CTA's destination rows ---------------------
-    RowInfo *s_rows = reinterpret_cast<RowInfo *>(smem_raw);
-    if ((long)threadIdx.x < Y1 - Y0) {
-        const double srcy = g.sy * ((double)(Y0 + threadIdx.x) + 0.5) + g.oy;
+    auto row_info = [&](long Y) {
+        const double srcy = g.sy * ((double)Y + 0.5) + g.oy;
         const long ky = (long)floor(srcy - 0.5);
-        RowInfo ri;
-        bspline_weights(srcy - 0.5 - (double)ky, ri.wy);
         long cy = (long)floor(srcy + 1e-10);
         if (cy == g.hp) cy--;
         const bool cy_ok = (srcy >= 0.0) && cy >= 0 && cy < g.hp;
+        RowInfo ri;
+        ri.dy = srcy - 0.5 - (double)ky;
         ri.ky = (int)ky;
         ri.jc = cy_ok ? (int)(cy - (ky - 1)) : -1;          // 1 or 2 (0 when clamped at the bottom edge)
         ri.cy = (int)cy;
         ri.pad = 0;
-        s_rows[threadIdx.x] = ri;
-    }
-    __syncthreads();                                        // the only CTA barrier
+        return ri;
+    };
 
-    // warp-private shared memory: values [RB][ncols], weights [RB][ncols], column flags [RB][ncols], source ring
-    const int comb_bytes = ((kUpRb * ncols * (2 * (int)sizeof(Pair) + 1)) + 15) / 16 * 16;
+    long Y0, Y1, strip;
+    RowInfo *s_rows = reinterpret_cast<RowInfo *>(smem_raw);
+    if (!list_mode) {
+        // ---- per-CTA row table: y-geometry of the CTA's destination rows -------------------------------------------
+        Y0 = (long)blockIdx.y * g.rows_per_cta;
+        Y1 = min(Y0 + (long)g.rows_per_cta, g.hs);
+        strip = (long)blockIdx.x * kUpWarps + warp;
+        if ((long)threadIdx.x < Y1 - Y0) s_rows[threadIdx.x] = row_info(Y0 + threadIdx.x);
+        __syncthreads();                                    // the only CTA barrier
+    } else {
+        // ---- fix-up mode: this warp's (strip, tap row) segment; its rows are those whose first tap row is ky - 1 ----
+        const long e = (long)blockIdx.x * kUpWarps + warp;
+        if (e >= *list_count) return;
+        const int2 seg = list[e];
+        strip = seg.x;
+        long ya = (long)floor(((double)seg.y + 0.5 - g.oy) / g.sy - 0.5) - 1;
+        if (ya < 0) ya = 0;
+        while (ya < g.hs && row_info(ya).ky < seg.y) ya++;
+        long yb = ya;
+        while (yb < g.hs && row_info(yb).ky == seg.y) yb++;
+        Y0 = ya; Y1 = yb;
+    }
+
+    // warp-private shared memory: values [ncols], weights [ncols], column flags [ncols] of ONE row, source ring
+    const int comb_bytes = ((ncols * (2 * (int)sizeof(Pair) + 1)) + 15) / 16 * 16;
     unsigned char *base = smem_raw + kUpMaxRows * sizeof(RowInfo) + warp * (comb_bytes + kRingBytes);
     Pair *s_val = reinterpret_cast<Pair *>(base);
-    Pair *s_wgt = s_val + kUpRb * ncols;
-    uint8_t *s_colf = reinterpret_cast<uint8_t *>(s_wgt + kUpRb * ncols);   // bit0: a tap missing, bit1: centre usable
-    const unsigned char *s_ring = base + comb_bytes + lane * kLaneBytes;     // this lane's slot in a staged row
+    Pair *s_wgt = s_val + ncols;
+    uint8_t *s_colf = reinterpret_cast<uint8_t *>(s_wgt + ncols);          // bit0: a tap missing, bit1: centre usable
+    const unsigned char *s_ring = base + comb_bytes + lane * kLaneBytes;   // this lane's slot in a staged row
     const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(s_ring);
 
-    const long Xw0 = ((long)blockIdx.x * kUpWarps + warp) * kUpWarpW;    // first destination column of the warp
+    const long Xw0 = strip * kUpWarpW;                      // first destination column of the warp
     if (Xw0 >= g.ws) return;
     const long X0 = Xw0 + (long)lane * PPT;
     const long plane = g.hp * g.wp;
@@ -442,34 +474,34 @@ upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ 
     const double srcx_w0 = g.sx * ((double)Xw0 + 0.5) + g.ox;
     const long col_base = (long)floor(srcx_w0 - 0.5) - 1;
 
-    // ---- per-pixel, row-invariant: x-weights, byte offset of the first tap column, where the centre sits ----------
-    double wx[PPT][4];
-    int voff[PPT];                                          // first tap column * sizeof(Pair)
-    int ctap[PPT];                                          // tap column hosting the centre (0..3), -1: none usable
-#pragma unroll
-    for (int k = 0; k < PPT; k++) {
+    // ---- per-pixel, row-invariant geometry (recomputed on demand: keeps it out of the hot loop's registers) ------------
+    auto px_geom = [&](int k, double &dxk, int &clk, int &ctk) {
         const double srcx = g.sx * ((double)(X0 + k) + 0.5) + g.ox;
         const long kx = (long)floor(srcx - 0.5);
-        bspline_weights(srcx - 0.5 - (double)kx, wx[k]);
-        long cl = kx - 1 - col_base;
+        dxk = srcx - 0.5 - (double)kx;                      // fractional column position inside the cell
+        long c = kx - 1 - col_base;                         // first tap column, relative to col_base
         long cx = (long)floor(srcx + 1e-10);
         if (cx == g.wp) cx--;
         const bool okx = (srcx >= 0.0) && (cx >= 0) && (cx < g.wp);
-        int ct = -1;
-        if (cl < 0 || cl + 3 >= ncols) cl = 0;              // only for X >= ws (never stored)
+        int ct = -1;                                        // tap column hosting the centre (0..3), -1: none usable
+        if (c < 0 || c + 3 >= ncols) c = 0;                 // only for X >= ws (never stored)
         else if (okx) ct = (int)(cx - (kx - 1));            // 1 or 2 (0 when clamped at the right edge)
-        voff[k] = (int)cl * (int)sizeof(Pair);
-        ctap[k] = (ct >= 0 && ct < 4) ? ct : -1;
-    }
+        clk = (int)c;
+        ctk = (ct >= 0 && ct < 4) ? ct : -1;
+    };
+    const bool full_vec = (X0 + PPT <= g.ws);
+    const bool use_async = APPLY && ALIGNED && full_vec && !list_mode;   // pixels come through the cp.async ring
 
-    // ---- per-lane coarse columns: the 4 tap rows are cached in registers, invalid taps as 0 + a validity mask -------
+    // ---- state of the FAST path: cubic in dy per pixel column and band ----------------------------------------------
+    double q[FAST ? PPT : 1][NB][4];
+    int q_ky = INT_MIN;
+    bool q_clean = false;
+    // ---- state of the GENERAL path when it is the main path (!FAST): tap rows cached per lane column ---------------------
     float tv[MC][NB][4];
-    unsigned tmask[MC];                                     // bit (b * 4 + j): tap row j of band b is valid
+    unsigned tmask[MC];
 #pragma unroll
     for (int m = 0; m < MC; m++) tmask[m] = 0;
-    int cached_ky = INT_MIN;
-    const bool full_vec = (X0 + PPT <= g.ws);
-    const bool use_async = APPLY && ALIGNED && full_vec;    // this lane's pixels come through the cp.async ring
+    int a_ky = INT_MIN;
 
     auto prefetch = [&](long Yp, int stage) {
         if (use_async) {
@@ -480,22 +512,156 @@ upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ 
         }
         cp_async_commit();
     };
-    if (APPLY) {
+    if (APPLY && !list_mode) {
 #pragma unroll
         for (int st = 0; st < kUpStages - 1; st++) prefetch(Y0 + (long)st * kUpRb, st);
     }
 
+    auto store_row = [&](float *orow, const float (&res)[NOUT][PPT]) {
+        if (ALIGNED && full_vec) {
+            hb_stg_stream16(orow, make_float4(res[0][0], res[0][1], res[0][2], res[0][3]));
+            if constexpr (NOUT == 2)
+                hb_stg_stream16(orow + g.hs * g.ws, make_float4(res[1][0], res[1][1], res[1][2], res[1][3]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < PPT; k++) {
+                if ((X0 + k) < g.ws) {
+                    orow[k] = res[0][k];
+                    if constexpr (NOUT == 2) orow[g.hs * g.ws + k] = res[1][k];
+                }
+            }
+        }
+    };
+    auto load_src = [&](long Y, const unsigned char *ring_row, float (&s)[PPT], bool (&ok)[PPT]) {
+        if constexpr (APPLY) {
+            if (use_async) {
+                Src4<T>::get(ring_row, nd, s, ok);
+            } else {
+                const T *row = src + Y * g.ws;
+#pragma unroll
+                for (int k = 0; k < PPT; k++) {
+                    const bool in_row = (X0 + k) < g.ws;
+                    s[k] = in_row ? hb_to_f32<T>(row[X0 + k]) : 0.f;
+                    ok[k] = in_row && hb_valid(s[k], nd);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < PPT; k++) { s[k] = 0.f; ok[k] = (X0 + k) < g.ws; }
+        }
+    };
+
     int batch = 0;
     for (long Yb = Y0; Yb < Y1; Yb += kUpRb, batch++) {
         const int nrows = (int)min((long)kUpRb, Y1 - Yb);
-        if (APPLY) prefetch(Yb + (long)(kUpStages - 1) * kUpRb, (batch + kUpStages - 1) % kUpStages);
+        if (APPLY && !list_mode) {
+            prefetch(Yb + (long)(kUpStages - 1) * kUpRb, (batch + kUpStages - 1) % kUpStages);
+            cp_async_wait<kUpStages - 1>();                 // this stage's source rows have landed
+        }
+        const unsigned char *ring_b = s_ring + ((batch % kUpStages) * kUpRb) * kRowBytes;
 
-        // ---- phase A: column combinations for the rows of the batch -------------------------------------------------
-        bool clean = true;
         for (int rr = 0; rr < nrows; rr++) {
-            const RowInfo ri = s_rows[Yb - Y0 + rr];
-            if (ri.ky != cached_ky) {                       // (warp-uniform) fetch / shift the tap rows
-                const bool shift1 = (ri.ky - cached_ky) == 1;
+            float *orow = out + (Yb + rr) * g.ws + X0;
+            const long Y = Yb + rr;
+            const RowInfo ri = list_mode ? row_info(Y) : s_rows[Y - Y0];
+
+            // ---- new cell row: rebuild the per-pixel-column cubics (FAST path) ---------------------------------------
+            if (FAST && ri.ky != q_ky) {                    // warp-uniform
+                double dxk[PPT];
+                int clk[PPT], ctk[PPT];
+                bool lane_clean = (cover == nullptr) && (ri.ky - 1 >= 0) && (ri.ky + 2 < g.hp);
+#pragma unroll
+                for (int k = 0; k < PPT; k++) {
+                    px_geom(k, dxk[k], clk[k], ctk[k]);
+                    lane_clean = lane_clean && (ctk[k] == 1 || ctk[k] == 2) && (clk[k] - clk[0] >= 0) &&
+                                 (clk[k] - clk[0] <= 1);
+                }
+                // the lane's 4 pixels use tap columns clk[0] .. clk[0] + 4 (their windows start 0 or 1 column in)
+                const long col0 = col_base + clk[0];
+                lane_clean = lane_clean && (col0 >= 0) && (col0 + 4 < g.wp);
+                if (lane_clean) {
+                    // x-weights of every pixel over the 5-column window (zero where the pixel's window does not reach)
+                    double w5[PPT][5];
+#pragma unroll
+                    for (int k = 0; k < PPT; k++) {
+                        double wx[4];
+                        bspline_weights(dxk[k], wx);
+                        const bool sh = (clk[k] != clk[0]);
+                        w5[k][0] = sh ? 0.0 : wx[0];
+                        w5[k][1] = sh ? wx[0] : wx[1];
+                        w5[k][2] = sh ? wx[1] : wx[2];
+                        w5[k][3] = sh ? wx[2] : wx[3];
+                        w5[k][4] = sh ? wx[3] : 0.0;
+                    }
+#pragma unroll
+                    for (int b = 0; b < NB; b++) {
+                        const float *p = coarse + b * plane + (long)(ri.ky - 1) * g.wp + col0;
+                        double r[PPT][4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            double t[5];
+#pragma unroll
+                            for (int i = 0; i < 5; i++) t[i] = (double)__ldg(p + j * g.wp + i);
+                            lane_clean = lane_clean && !isnan((t[0] + t[1]) + (t[2] + t[3]) + t[4]);
+#pragma unroll
+                            for (int k = 0; k < PPT; k++)   // x-interpolation of tap row j at pixel column k
+                                r[k][j] = fma(w5[k][4], t[4], fma(w5[k][3], t[3], fma(w5[k][2], t[2],
+                                          fma(w5[k][1], t[1], w5[k][0] * t[0]))));
+                        }
+#pragma unroll
+                        for (int k = 0; k < PPT; k++) {     // cubic B-spline through the 4 tap rows, as a polynomial in dy
+                            q[k][b][0] = (r[k][0] + 4.0 * r[k][1] + r[k][2]) * (1.0 / 6.0);
+                            q[k][b][1] = (r[k][2] - r[k][0]) * 0.5;
+                            q[k][b][2] = (r[k][0] - 2.0 * r[k][1] + r[k][2]) * 0.5;
+                            q[k][b][3] = ((r[k][3] - r[k][0]) + 3.0 * (r[k][1] - r[k][2])) * (1.0 / 6.0);
+                        }
+                    }
+                }
+                q_clean = __all_sync(0xffffffffu, lane_clean);
+                q_ky = ri.ky;
+            }
+
+            float s[PPT];
+            bool ok[PPT];
+            float res[NOUT][PPT];
+#ifdef HB_UP_SKELETON
+            if (true) {                                     // experiment: memory skeleton only (no interpolation)
+                load_src(Y, ring_b + rr * kRowBytes, s, ok);
+#pragma unroll
+                for (int k = 0; k < PPT; k++) res[0][k] = ok[k] ? s[k] * 2.0f : qnan;
+                store_row(orow, res);
+                continue;
+            }
+#endif
+            if (FAST && q_clean) {
+                // ---- FAST row: Horner in dy, fused apply --------------------------------------------------------------
+                load_src(Y, ring_b + rr * kRowBytes, s, ok);
+                const double dy = ri.dy;
+#pragma unroll
+                for (int k = 0; k < PPT; k++) {
+                    const double gv = fma(fma(fma(q[FAST ? k : 0][0][3], dy, q[FAST ? k : 0][0][2]), dy, q[FAST ? k : 0][0][1]), dy,
+                                          q[FAST ? k : 0][0][0]);
+                    double ov = 0.0;
+                    if (NB > 1) ov = fma(fma(fma(q[FAST ? k : 0][NB - 1][3], dy, q[FAST ? k : 0][NB - 1][2]), dy,
+                                             q[FAST ? k : 0][NB - 1][1]), dy, q[FAST ? k : 0][NB - 1][0]);
+                    const float gf = ok[k] ? (float)gv : qnan;
+                    const float of = ok[k] ? (float)ov : qnan;
+                    if (APPLY) {
+                        res[0][k] = __fadd_rn(__fmul_rn(gf, s[k]), of);   // two roundings, as numpy (kernel_model.py:461)
+                    } else {
+                        res[0][k] = gf;
+                        if constexpr (NOUT == 2) res[1][k] = of;
+                    }
+                }
+                store_row(orow, res);
+                continue;
+            }
+
+            // ---- GENERAL row, phase A: column combinations ------------------------------------------------------------
+            double wy[4];
+            bspline_weights(ri.dy, wy);
+            if (FAST || ri.ky != a_ky) {                    // (warp-uniform) fetch / shift the tap rows
+                const bool shift1 = !FAST && (ri.ky - a_ky) == 1;
 #pragma unroll
                 for (int m = 0; m < MC; m++) {
                     const long col = col_base + lane + 32 * m;
@@ -511,146 +677,248 @@ upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ 
                                 tv[m][b][j] = tv[m][b][j + 1];
                             } else {
                                 const float v = inside ? __ldg(coarse + b * plane + row * g.wp + col) : qnan;
-                                const bool ok = !isnan(v);
-                                tv[m][b][j] = ok ? v : 0.f;
-                                if (ok) mask |= 1u << (b * 4 + j);
+                                const bool okv = !isnan(v);
+                                tv[m][b][j] = okv ? v : 0.f;
+                                if (okv) mask |= 1u << (b * 4 + j);
                             }
                         }
                     }
                     tmask[m] = mask;
                 }
-                cached_ky = ri.ky;
+                a_ky = ri.ky;
             }
 #pragma unroll
             for (int m = 0; m < MC; m++) {
                 const int c = lane + 32 * m;
                 if (c < ncols) {
-                    // invalid taps are stored as 0: the value sums need no predication
-                    Pair val;
-                    val.g = fma(ri.wy[3], (double)tv[m][0][3], fma(ri.wy[2], (double)tv[m][0][2],
-                            fma(ri.wy[1], (double)tv[m][0][1], ri.wy[0] * (double)tv[m][0][0])));
+                    Pair val;                               // invalid taps are stored as 0: no predication needed
+                    val.g = fma(wy[3], (double)tv[m][0][3], fma(wy[2], (double)tv[m][0][2],
+                            fma(wy[1], (double)tv[m][0][1], wy[0] * (double)tv[m][0][0])));
                     val.o = 0.0;
                     if (NB > 1)
-                        val.o = fma(ri.wy[3], (double)tv[m][1][3], fma(ri.wy[2], (double)tv[m][1][2],
-                                fma(ri.wy[1], (double)tv[m][1][1], ri.wy[0] * (double)tv[m][1][0])));
-                    s_val[rr * ncols + c] = val;
+                        val.o = fma(wy[3], (double)tv[m][1][3], fma(wy[2], (double)tv[m][1][2],
+                                fma(wy[1], (double)tv[m][1][1], wy[0] * (double)tv[m][1][0])));
+                    s_val[c] = val;
                     const unsigned mask = tmask[m];
                     const bool all_ok = (mask == kFullMask);
                     // centre pixel: its coarse pixel must be in range and valid in any band (+ the coverage mask)
                     bool c_ok = (ri.jc >= 0) && (((mask | (mask >> 4)) >> ri.jc) & 1u);
                     if (c_ok && cover != nullptr) c_ok = cover[(long)ri.cy * g.wp + col_base + c] != 0;
-                    if (!all_ok) {
-                        // a band's tap counts iff that band is valid there (band-valid implies "any band" validity)
-                        Pair wgt = {0.0, 0.0};
+                    // a band's tap counts iff that band is valid there (band-valid implies "any band" validity)
+                    Pair wgt = {0.0, 0.0};
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            if ((mask >> j) & 1u) wgt.g += ri.wy[j];
-                            if (NB > 1 && ((mask >> (4 + j)) & 1u)) wgt.o += ri.wy[j];
-                        }
-                        s_wgt[rr * ncols + c] = wgt;
+                    for (int j = 0; j < 4; j++) {
+                        if ((mask >> j) & 1u) wgt.g += wy[j];
+                        if (NB > 1 && ((mask >> (4 + j)) & 1u)) wgt.o += wy[j];
                     }
-                    s_colf[rr * ncols + c] = (uint8_t)((all_ok ? 0 : 1) | (c_ok ? 2 : 0));
-                    clean = clean && all_ok && c_ok;
+                    s_wgt[c] = wgt;
+                    s_colf[c] = (uint8_t)((all_ok ? 0 : 1) | (c_ok ? 2 : 0));
                 }
             }
-        }
-        clean = __all_sync(0xffffffffu, clean);             // also orders the shared-memory writes above
-        __syncwarp();
-        if (APPLY) cp_async_wait<kUpStages - 1>();          // this batch's source rows have landed
-        const unsigned char *ring_b = s_ring + ((batch % kUpStages) * kUpRb) * kRowBytes;
+            __syncwarp();
 
-        // ---- phase C: destination pixels ----------------------------------------------------------------------------
-        auto phase_c = [&](auto clean_tag) {
-            constexpr bool CLEAN = decltype(clean_tag)::value;
-            const unsigned char *v_row = reinterpret_cast<const unsigned char *>(s_val);
-            float *orow = out + Yb * g.ws + X0;
-#pragma unroll 2
-            for (int rr = 0; rr < nrows; rr++, v_row += ncols * sizeof(Pair), orow += g.ws) {
-                float s[PPT];
-                bool ok[PPT];
-                if constexpr (APPLY) {
-                    if (use_async) {
-                        Src4<T>::get(ring_b + rr * kRowBytes, nd, s, ok);
-                    } else {
-                        const T *row = src + (Yb + rr) * g.ws;
-#pragma unroll
-                        for (int k = 0; k < PPT; k++) {
-                            const bool in_row = (X0 + k) < g.ws;
-                            s[k] = in_row ? hb_to_f32<T>(row[X0 + k]) : 0.f;
-                            ok[k] = in_row && hb_valid(s[k], nd);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < PPT; k++) { s[k] = 0.f; ok[k] = (X0 + k) < g.ws; }
-                }
-                float res[NOUT][PPT];
+            // ---- GENERAL row, phase C: destination pixels -------------------------------------------------------------
+            if (X0 < g.ws) {
+                load_src(Y, ring_b + rr * kRowBytes, s, ok);
 #pragma unroll
                 for (int k = 0; k < PPT; k++) {
-                    const Pair *v = reinterpret_cast<const Pair *>(v_row + voff[k]);
+                    double dxk, wx[4];
+                    int clk, ctk;
+                    px_geom(k, dxk, clk, ctk);
+                    bspline_weights(dxk, wx);
+                    const Pair *v = s_val + clk;
                     const Pair a0 = v[0], a1 = v[1], a2 = v[2], a3 = v[3];
-                    double gv = fma(wx[k][3], a3.g, fma(wx[k][2], a2.g, fma(wx[k][1], a1.g, wx[k][0] * a0.g)));
+                    double gv = fma(wx[3], a3.g, fma(wx[2], a2.g, fma(wx[1], a1.g, wx[0] * a0.g)));
                     double ov = 0.0;
-                    if (NB > 1) ov = fma(wx[k][3], a3.o, fma(wx[k][2], a2.o, fma(wx[k][1], a1.o, wx[k][0] * a0.o)));
-                    bool g_ok = ok[k], o_ok = ok[k];
-                    if constexpr (!CLEAN) {                 // batches touching nodata / the raster edge
-                        const int cidx = rr * ncols + (voff[k] >> 4);
-                        const unsigned f0 = s_colf[cidx], f1 = s_colf[cidx + 1], f2 = s_colf[cidx + 2],
-                                       f3 = s_colf[cidx + 3];
-                        const unsigned fc = (ctap[k] == 0) ? f0 : (ctap[k] == 1) ? f1 : (ctap[k] == 2) ? f2
-                                          : (ctap[k] == 3) ? f3 : 0u;
-                        const bool centre_ok = (fc & 2u) != 0;
-                        g_ok = g_ok && centre_ok;
-                        o_ok = o_ok && centre_ok;
-                        if ((f0 | f1 | f2 | f3) & 1u) {
-                            // GDAL GWKResample: drop if sum(w) < 1e-6, divide unless sum(w) is within 1e-5 of 1.
-                            // (columns with all taps valid did not store their weight: it is sum(wy) == 1)
-                            const Pair *w = s_wgt + cidx;
-                            const RowInfo &ri = s_rows[Yb - Y0 + rr];
-                            const double wy_all = (ri.wy[0] + ri.wy[1]) + (ri.wy[2] + ri.wy[3]);
-                            const Pair one = {wy_all, wy_all};
-                            const Pair m0 = (f0 & 1u) ? w[0] : one, m1 = (f1 & 1u) ? w[1] : one,
-                                       m2 = (f2 & 1u) ? w[2] : one, m3 = (f3 & 1u) ? w[3] : one;
-                            const double wg =
-                                fma(wx[k][3], m3.g, fma(wx[k][2], m2.g, fma(wx[k][1], m1.g, wx[k][0] * m0.g)));
-                            if (wg < 0.000001) g_ok = false;
-                            else if (wg < 0.99999 || wg > 1.00001) gv /= wg;
-                            if (NB > 1) {
-                                const double wo =
-                                    fma(wx[k][3], m3.o, fma(wx[k][2], m2.o, fma(wx[k][1], m1.o, wx[k][0] * m0.o)));
-                                if (wo < 0.000001) o_ok = false;
-                                else if (wo < 0.99999 || wo > 1.00001) ov /= wo;
-                            }
+                    if (NB > 1) ov = fma(wx[3], a3.o, fma(wx[2], a2.o, fma(wx[1], a1.o, wx[0] * a0.o)));
+                    const unsigned f0 = s_colf[clk], f1 = s_colf[clk + 1], f2 = s_colf[clk + 2], f3 = s_colf[clk + 3];
+                    const unsigned fc = (ctk == 0) ? f0 : (ctk == 1) ? f1 : (ctk == 2) ? f2 : (ctk == 3) ? f3 : 0u;
+                    bool g_ok = ok[k] && (fc & 2u), o_ok = g_ok;
+                    if ((f0 | f1 | f2 | f3) & 1u) {
+                        // GDAL GWKResample: drop if sum(w) < 1e-6, divide unless sum(w) is within 1e-5 of 1
+                        const Pair *w = s_wgt + clk;
+                        const Pair m0 = w[0], m1 = w[1], m2 = w[2], m3 = w[3];
+                        const double wg = fma(wx[3], m3.g, fma(wx[2], m2.g, fma(wx[1], m1.g, wx[0] * m0.g)));
+                        if (wg < 0.000001) g_ok = false;
+                        else if (wg < 0.99999 || wg > 1.00001) gv /= wg;
+                        if (NB > 1) {
+                            const double wo = fma(wx[3], m3.o, fma(wx[2], m2.o, fma(wx[1], m1.o, wx[0] * m0.o)));
+                            if (wo < 0.000001) o_ok = false;
+                            else if (wo < 0.99999 || wo > 1.00001) ov /= wo;
                         }
                     }
                     const float gf = g_ok ? (float)gv : qnan;
                     const float of = o_ok ? (float)ov : qnan;
                     if (APPLY) {
-                        res[0][k] = __fadd_rn(__fmul_rn(gf, s[k]), of);   // two roundings, as numpy (kernel_model.py:461)
+                        res[0][k] = __fadd_rn(__fmul_rn(gf, s[k]), of);
                     } else {
                         res[0][k] = gf;
                         if constexpr (NOUT == 2) res[1][k] = of;
                     }
                 }
-                if (ALIGNED && full_vec) {
-                    hb_stg_stream16(orow, make_float4(res[0][0], res[0][1], res[0][2], res[0][3]));
-                    if constexpr (NOUT == 2)
-                        hb_stg_stream16(orow + g.hs * g.ws, make_float4(res[1][0], res[1][1], res[1][2], res[1][3]));
-                } else {
+                store_row(orow, res);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---- FAST kernel (ratio >= ~5): per-pixel-column cubics in registers, nothing else ------------------------------------
+// One warp = 128-pixel strip x rows_per_cta rows, 4 pixels per lane.  At every change of tap rows the lane rebuilds,
+// for each of its 4 pixel columns and each band, the cubic in dy (4 double coefficients).  If any tap of the warp's
+// window is missing / out of range the whole (strip, tap row) segment is appended to `list` and skipped:
+// upsample_kernel re-does exactly those segments, one warp each, with GDAL's general rules.
+template <typename T, int NB, bool APPLY>
+__global__ void __launch_bounds__(kThreads, 2)
+upsample_fast_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ coarse, UpGeom g,
+                     float *__restrict__ out, int2 *__restrict__ list, int *__restrict__ list_count)
+{
+    constexpr int PPT = kUpPpt;
+    constexpr int NOUT = (NB == 2 && !APPLY) ? 2 : 1;
+    constexpr int kLaneBytes = APPLY ? Src4<T>::kBytes : 0;
+    constexpr int kRowBytes = 32 * kLaneBytes;
+    constexpr int kRingBytes = kUpStages * kUpRb * kRowBytes;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long Y0 = (long)blockIdx.y * g.rows_per_cta;
+    const long Y1 = min(Y0 + (long)g.rows_per_cta, g.hs);
+    const float qnan = __int_as_float(0x7fc00000);
+
+    // per-CTA row table: (dy, ky) of the CTA's destination rows
+    double2 *s_rows = reinterpret_cast<double2 *>(smem_raw);              // .x = dy, .y = (double)ky
+    if ((long)threadIdx.x < Y1 - Y0) {
+        const double srcy = g.sy * ((double)(Y0 + threadIdx.x) + 0.5) + g.oy;
+        const double ky = floor(srcy - 0.5);
+        s_rows[threadIdx.x] = make_double2(srcy - 0.5 - ky, ky);
+    }
+    __syncthreads();                                        // the only CTA barrier
+
+    const long strip = (long)blockIdx.x * kUpWarps + warp;
+    const long Xw0 = strip * kUpWarpW;
+    if (Xw0 >= g.ws) return;
+    const long X0 = Xw0 + (long)lane * PPT;                 // (ws % 4 == 0: a lane is wholly inside or outside)
+    const bool lane_in = X0 < g.ws;
+    const long plane = g.hp * g.wp;
+    const unsigned char *s_ring = smem_raw + kUpMaxRows * sizeof(double2) + warp * kRingBytes + lane * kLaneBytes;
+    const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(s_ring);
+
+    // cp.async ring of source rows: every lane copies, and later reads, only its own 4 pixels
+    const T *src_p = APPLY ? src + Y0 * g.ws + X0 : nullptr;               // next row to prefetch
+    long rows_left = Y1 - Y0;                                              // rows not yet prefetched
+    auto prefetch = [&](int stage) {
+        if (APPLY && lane_in) {
 #pragma unroll
-                    for (int k = 0; k < PPT; k++) {
-                        if ((X0 + k) < g.ws) {
-                            orow[k] = res[0][k];
-                            if constexpr (NOUT == 2) orow[g.hs * g.ws + k] = res[1][k];
+            for (int rr = 0; rr < kUpRb; rr++)
+                if (rr < rows_left) cp_async_lane<kLaneBytes>(ring_sa + (stage * kUpRb + rr) * kRowBytes, src_p + rr * g.ws);
+        }
+        src_p += kUpRb * g.ws;
+        rows_left -= kUpRb;
+        cp_async_commit();
+    };
+    if (APPLY) {
+#pragma unroll
+        for (int st = 0; st < kUpStages - 1; st++) prefetch(st);
+    }
+
+    double q[PPT][NB][4];                                   // cubic in dy per pixel column and band
+    double q_ky = -1e300;
+    bool q_clean = false;
+    float *orow = out + Y0 * g.ws + X0;
+    int stage = 0;
+    for (long Yb = Y0; Yb < Y1; Yb += kUpRb) {
+        const int nrows = (int)min((long)kUpRb, Y1 - Yb);
+        if (APPLY) {
+            prefetch((stage + kUpStages - 1) % kUpStages);
+            cp_async_wait<kUpStages - 1>();
+        }
+        const unsigned char *ring_b = s_ring + stage * kUpRb * kRowBytes;
+        stage = (stage + 1) % kUpStages;
+#pragma unroll 1
+        for (int rr = 0; rr < nrows; rr++, orow += g.ws) {
+            const double2 ri = s_rows[Yb - Y0 + rr];
+            if (ri.y != q_ky) {                             // (warp-uniform) new tap rows: rebuild the cubics
+                q_ky = ri.y;
+                const long ky = (long)ri.y;
+                bool lane_clean = (ky - 1 >= 0) && (ky + 2 < g.hp);
+                double w5[PPT][5];
+                long col0 = 0;
+#pragma unroll
+                for (int k = 0; k < PPT; k++) {
+                    const double srcx = g.sx * ((double)(X0 + k) + 0.5) + g.ox;
+                    const double kxd = floor(srcx - 0.5);
+                    const long kx = (long)kxd;
+                    if (k == 0) col0 = kx - 1;
+                    const long sh = (kx - 1) - col0;        // this pixel's window starts 0 or 1 column into the lane's
+                    long cx = (long)floor(srcx + 1e-10);
+                    const long ct = cx - (kx - 1);          // tap column hosting the centre: 1 or 2 away from the edges
+                    lane_clean = lane_clean && (sh == 0 || sh == 1) && (ct == 1 || ct == 2) && (srcx >= 0.0);
+                    double wx[4];
+                    bspline_weights(srcx - 0.5 - kxd, wx);
+                    w5[k][0] = sh ? 0.0 : wx[0];
+                    w5[k][1] = sh ? wx[0] : wx[1];
+                    w5[k][2] = sh ? wx[1] : wx[2];
+                    w5[k][3] = sh ? wx[2] : wx[3];
+                    w5[k][4] = sh ? wx[3] : 0.0;
+                }
+                lane_clean = (lane_clean && (col0 >= 0) && (col0 + 4 < g.wp)) || !lane_in;
+                if (lane_clean && lane_in) {
+#pragma unroll
+                    for (int b = 0; b < NB; b++) {
+                        const float *p = coarse + b * plane + (ky - 1) * g.wp + col0;
+                        double r[PPT][4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            double t[5];
+#pragma unroll
+                            for (int i = 0; i < 5; i++) t[i] = (double)__ldg(p + j * g.wp + i);
+                            lane_clean = lane_clean && !isnan((t[0] + t[1]) + (t[2] + t[3]) + t[4]);
+#pragma unroll
+                            for (int k = 0; k < PPT; k++)   // x-interpolation of tap row j at pixel column k
+                                r[k][j] = fma(w5[k][4], t[4], fma(w5[k][3], t[3], fma(w5[k][2], t[2],
+                                          fma(w5[k][1], t[1], w5[k][0] * t[0]))));
+                        }
+#pragma unroll
+                        for (int k = 0; k < PPT; k++) {     // cubic B-spline through the 4 tap rows as a polynomial in dy
+                            q[k][b][0] = (r[k][0] + 4.0 * r[k][1] + r[k][2]) * (1.0 / 6.0);
+                            q[k][b][1] = (r[k][2] - r[k][0]) * 0.5;
+                            q[k][b][2] = (r[k][0] - 2.0 * r[k][1] + r[k][2]) * 0.5;
+                            q[k][b][3] = ((r[k][3] - r[k][0]) + 3.0 * (r[k][1] - r[k][2])) * (1.0 / 6.0);
                         }
                     }
                 }
+                q_clean = __all_sync(0xffffffffu, lane_clean);
+                if (!q_clean && lane == 0) list[atomicAdd(list_count, 1)] = make_int2((int)strip, (int)ky);
             }
-        };
-        if (X0 < g.ws) {
-            if (clean) phase_c(std::true_type{}); else phase_c(std::false_type{});
+            if (!q_clean || !lane_in) continue;
+            float s[PPT];
+            bool ok[PPT];
+            if constexpr (APPLY) {
+                Src4<T>::get(ring_b + rr * kRowBytes, nd, s, ok);
+            } else {
+#pragma unroll
+                for (int k = 0; k < PPT; k++) { s[k] = 0.f; ok[k] = true; }
+            }
+            const double dy = ri.x;
+            float res[NOUT][PPT];
+#pragma unroll
+            for (int k = 0; k < PPT; k++) {
+                const double gv = fma(fma(fma(q[k][0][3], dy, q[k][0][2]), dy, q[k][0][1]), dy, q[k][0][0]);
+                double ov = 0.0;
+                if (NB > 1) ov = fma(fma(fma(q[k][NB - 1][3], dy, q[k][NB - 1][2]), dy, q[k][NB - 1][1]), dy,
+                                     q[k][NB - 1][0]);
+                const float gf = ok[k] ? (float)gv : qnan;
+                const float of = ok[k] ? (float)ov : qnan;
+                if (APPLY) {
+                    res[0][k] = __fadd_rn(__fmul_rn(gf, s[k]), of);       // two roundings, as numpy (kernel_model.py:461)
+                } else {
+                    res[0][k] = gf;
+                    if constexpr (NOUT == 2) res[1][k] = of;
+                }
+            }
+            hb_stg_stream16(orow, make_float4(res[0][0], res[0][1], res[0][2], res[0][3]));
+            if constexpr (NOUT == 2)
+                hb_stg_stream16(orow + g.hs * g.ws, make_float4(res[1][0], res[1][1], res[1][2], res[1][3]));
         }
-        __syncwarp();
     }
 }
 
@@ -665,14 +933,16 @@ int launch_upsample(const void *src, NoData nd, const float *coarse, long hs, lo
     UpGeom g;
     g.hs = hs; g.ws = ws; g.hp = hp; g.wp = wp; g.sx = sx; g.ox = ox; g.sy = sy; g.oy = oy;
     g.ncols = (int)ceil((double)kUpWarpW * sx) + 5;
-    // rows per CTA: a couple of coarse rows' worth, so that the register-cached tap rows are re-fetched rarely
+    g.fast = (g.ncols <= 32) ? 1 : 0;                       // ratio >= ~4.8: the per-pixel-column cubics pay off
+    // rows per CTA: a couple of coarse rows' worth, so that the per-cell-row work is amortised
     long rpc = (long)ceil(2.0 / sy);
     rpc = ((rpc + kUpRb - 1) / kUpRb) * kUpRb;
     if (rpc < 16) rpc = 16;
+    if (g.fast) rpc = kUpMaxRows;                           // fewer tap-row changes (cubic rebuilds) per CTA
     if (rpc > kUpMaxRows) rpc = kUpMaxRows;
     g.rows_per_cta = (int)rpc;
     const size_t ring = APPLY ? (size_t)kUpStages * kUpRb * 32 * kUpPpt * sizeof(T) : 0;
-    const size_t per_warp = ((size_t)kUpRb * g.ncols * (2 * sizeof(Pair) + 1) + 15) / 16 * 16 + ring;
+    const size_t per_warp = ((size_t)g.ncols * (2 * sizeof(Pair) + 1) + 15) / 16 * 16 + ring;
     const size_t smem = kUpMaxRows * sizeof(RowInfo) + per_warp * kUpWarps;
     const long cta_w = (long)kUpWarpW * kUpWarps;
     dim3 grid((unsigned)((ws + cta_w - 1) / cta_w), (unsigned)((hs + rpc - 1) / rpc));
@@ -682,16 +952,40 @@ int launch_upsample(const void *src, NoData nd, const float *coarse, long hs, lo
                          (ws % 4 == 0) && (((uintptr_t)out) % 16 == 0);
     NoData ndk = nd;
     if (!ndk.int_ok) ndk.ivalue = -1;                       // integer sources: no pixel can equal it
+    // ---- fast path: aligned rasters, ratio >= ~5, no coverage mask; the general kernel then only fixes up the
+    //      (strip, cell row) segments the fast kernel flagged (nodata / raster edge neighbourhoods)
+    int2 *list = nullptr;
+    int *list_count = nullptr;
+    dim3 ggrid = grid;                                      // grid of the general kernel
+    if (g.fast && aligned && cover == nullptr) {
+        const long strips = (ws + kUpWarpW - 1) / kUpWarpW;
+        // a strip's rows span at most hs * sy + 3 distinct tap rows; (strip, tap row) pairs are appended at most once
+        const long max_seg = strips * ((long)ceil((double)hs * sy) + 4);
+        HB_REQUIRE(max_seg < 2147483000L, "up-sampling work list too large");
+        void *ws_list = nullptr;
+        HB_CUDA_OK(cudaMallocAsync(&ws_list, 16 + (size_t)max_seg * sizeof(int2), stream));
+        list_count = (int *)ws_list;
+        list = (int2 *)((char *)ws_list + 16);
+        HB_CUDA_OK(cudaMemsetAsync(list_count, 0, 16, stream));
+        const size_t fsmem = kUpMaxRows * sizeof(double2) + ring * kUpWarps;
+        auto fkern = upsample_fast_kernel<T, NB, APPLY>;
+        if (fsmem > 48 * 1024)
+            HB_CUDA_OK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        fkern<<<grid, kThreads, fsmem, stream>>>((const T *)src, ndk, coarse, g, out, list, list_count);
+        HB_LAUNCH_OK("upsample_fast_kernel");
+        ggrid = dim3((unsigned)((max_seg + kUpWarps - 1) / kUpWarps), 1, 1);   // one warp per possible segment
+    }
 #define HB_UP_LAUNCH(AL_, MC_)                                                                                        \
     do {                                                                                                              \
         auto kern = upsample_kernel<T, NB, APPLY, AL_, MC_>;                                                          \
         if (smem > 48 * 1024)                                                                                         \
             HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-        kern<<<grid, kThreads, smem, stream>>>((const T *)src, ndk, coarse, g, cover, out);                           \
+        kern<<<ggrid, kThreads, smem, stream>>>((const T *)src, ndk, coarse, g, cover, out, list, list_count);        \
     } while (0)
     if (g.ncols <= 32) { if (aligned) HB_UP_LAUNCH(true, 1); else HB_UP_LAUNCH(false, 1); }
     else if (g.ncols <= 96) { if (aligned) HB_UP_LAUNCH(true, 3); else HB_UP_LAUNCH(false, 3); }
     else { if (aligned) HB_UP_LAUNCH(true, 5); else HB_UP_LAUNCH(false, 5); }
+    if (list_count != nullptr) HB_CUDA_OK(cudaFreeAsync(list_count, stream));
 #undef HB_UP_LAUNCH
     HB_LAUNCH_OK("upsample_kernel");
     return 0;
