@@ -491,6 +491,14 @@ upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ 
     };
     const bool full_vec = (X0 + PPT <= g.ws);
     const bool use_async = APPLY && ALIGNED && full_vec && !list_mode;   // pixels come through the cp.async ring
+    double wxr[PPT][4];                                     // x-weights, first tap column, centre tap column per pixel
+    int clr[PPT], ctr[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {
+        double dxk;
+        px_geom(k, dxk, clr[k], ctr[k]);
+        bspline_weights(dxk, wxr[k]);
+    }
 
     // ---- state of the FAST path: cubic in dy per pixel column and band ----------------------------------------------
     double q[FAST ? PPT : 1][NB][4];
@@ -722,10 +730,8 @@ upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ 
                 load_src(Y, ring_b + rr * kRowBytes, s, ok);
 #pragma unroll
                 for (int k = 0; k < PPT; k++) {
-                    double dxk, wx[4];
-                    int clk, ctk;
-                    px_geom(k, dxk, clk, ctk);
-                    bspline_weights(dxk, wx);
+                    const double (&wx)[4] = wxr[k];
+                    const int clk = clr[k], ctk = ctr[k];
                     const Pair *v = s_val + clk;
                     const Pair a0 = v[0], a1 = v[1], a2 = v[2], a3 = v[3];
                     double gv = fma(wx[3], a3.g, fma(wx[2], a2.g, fma(wx[1], a1.g, wx[0] * a0.g)));
@@ -805,13 +811,20 @@ upsample_fast_kernel(const T *__restrict__ src, NoData nd, const float *__restri
     // cp.async ring of source rows: every lane copies, and later reads, only its own 4 pixels
     const T *src_p = APPLY ? src + Y0 * g.ws + X0 : nullptr;               // next row to prefetch
     long rows_left = Y1 - Y0;                                              // rows not yet prefetched
+    const long row_pitch = g.ws;
     auto prefetch = [&](int stage) {
         if (APPLY && lane_in) {
+            const uint32_t dst = ring_sa + stage * (kUpRb * kRowBytes);
+            if (rows_left >= kUpRb) {                       // (warp-uniform) a whole stage
 #pragma unroll
-            for (int rr = 0; rr < kUpRb; rr++)
-                if (rr < rows_left) cp_async_lane<kLaneBytes>(ring_sa + (stage * kUpRb + rr) * kRowBytes, src_p + rr * g.ws);
+                for (int rr = 0; rr < kUpRb; rr++) cp_async_lane<kLaneBytes>(dst + rr * kRowBytes, src_p + rr * row_pitch);
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < kUpRb; rr++)
+                    if (rr < rows_left) cp_async_lane<kLaneBytes>(dst + rr * kRowBytes, src_p + rr * row_pitch);
+            }
         }
-        src_p += kUpRb * g.ws;
+        src_p += kUpRb * row_pitch;
         rows_left -= kUpRb;
         cp_async_commit();
     };
