@@ -169,8 +169,10 @@ def main():
     fuse = RasterFuse(src_ra, ref_ra, proc_crs=ProcCrs(cfg['proc_crs']))
     fuse.open()
 
-    def step(f=fuse):
-        return f.process(model=Model(cfg['model']), kernel_shape=cfg['kernel_shape'], model_config=model_config)
+    def step(f=fuse, serial=False):
+        # serial=True: one CUDA stream (bands back to back) -- used only for the per-kernel roofline timing pass
+        return f.process(model=Model(cfg['model']), kernel_shape=cfg['kernel_shape'], model_config=model_config,
+                         block_config=dict(threads=1) if serial else None)
 
     def barrier():
         if world > 1:
@@ -187,16 +189,24 @@ def main():
     sampler.start()
     lib.hb_reset_launch_count()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with KernelTimer() as timer:
-        barrier()
-        start.record()
-        for _ in range(args.steps):
-            step()
-        end.record()
-        barrier()
+    barrier()
+    start.record()
+    for _ in range(args.steps):
+        step()
+    end.record()
+    barrier()
     launches = lib.hb_launch_count()
     elapsed_ms = start.elapsed_time(end)
-    kernel_ms = timer.results()
+    # per-launch kernel durations for the roofline: the same K steps again with the bands on ONE stream (concurrent
+    # bands would overlap kernels and inflate each other's event-to-event durations)
+    with KernelTimer() as timer:
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            step(serial=True)
+        s1.record()
+        kernel_ms = timer.results()
+    serial_ms = s0.elapsed_time(s1)
     stop.set()
     sampler.join(timeout=2)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
@@ -268,7 +278,10 @@ def main():
     roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': round(achieved, 1), 'peak': peak_gbs,
                 'peak_source': peak_src, 'unit': 'GB/s', 'frac': round(achieved / peak_gbs, 4), 'traffic': None,
                 'algorithmic_bytes_per_launch': int(alg_bytes[dominant]),
-                'share_of_step': round(sum(kernel_ms[dominant]) / elapsed_ms, 3), 'kernels': per_kernel}
+                'share_of_step': round(sum(kernel_ms[dominant]) / serial_ms, 3),
+                'timing': 'CUDA events around every launch, K steps with the bands serialised on one stream '
+                          f'({round(serial_ms / args.steps, 4)} ms/step); `value` runs the bands on concurrent streams',
+                'kernels': per_kernel}
 
     # ---- CPU baseline: the oracle port on a bounded sample (rank 0, N = 1 only) ---------------------------------------
     cpu_baseline = None

@@ -32,6 +32,22 @@ except ImportError:  # pragma: no cover
     torch = None
 
 
+_STREAM_POOLS: Dict[int, list] = {}
+
+
+def _band_streams(n: int) -> list:
+    """
+    Persistent per-device pool of CUDA streams for band-level concurrency.  Re-using the same streams lets torch's
+    caching allocator re-use each stream's blocks from one ``process`` call to the next (fresh streams would mean
+    fresh cudaMallocs for every band).
+    """
+    dev = torch.cuda.current_device()
+    pool = _STREAM_POOLS.setdefault(dev, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
+
+
 def _validate_threads(threads: int) -> int:
     """ Reference utils.validate_threads (utils.py:156-164). """
     _cpu_count = cpu_count()
@@ -202,11 +218,35 @@ class RasterFuse:
         kernel_model = model_cls(model_type, kernel_shape, find_r2=param_filename is not None, **model_config)
 
         n_bands = len(self._src_bands)
-        corr_planes, param_planes = [], []
-        for band_i in range(n_bands):                  # bands outermost, raster_pair.py:379-381
+        corr_planes, param_planes = [None] * n_bands, [None] * n_bands
+
+        def run_band(band_i):
             corr_ra, param_ra = self._process_band(band_i, kernel_model)
-            corr_planes.append(_convert_dtype(corr_ra, out_profile['dtype'], out_profile['nodata']))
-            param_planes.append(param_ra)
+            corr_planes[band_i] = _convert_dtype(corr_ra, out_profile['dtype'], out_profile['nodata'])
+            param_planes[band_i] = param_ra
+
+        # Bands are independent (the reference runs (band, block) jobs on a thread pool, fuse.py:396-408).  On the
+        # GPU each band is enqueued on its own CUDA stream, so that the small latency-bound kernels of one band (fit
+        # on the proc grid, in-painting) overlap the bandwidth-bound resampling kernels of the others.
+        n_streams = min(n_bands, max(1, int(block_config['threads'])), 4)
+        use_streams = (torch is not None and n_streams > 1 and torch.cuda.is_available()
+                       and is_tensor(self._src.array) and self._src.array.is_cuda)
+        if use_streams:
+            main = torch.cuda.current_stream()
+            streams = _band_streams(n_streams)
+            for st in streams:
+                st.wait_stream(main)
+            for band_i in range(n_bands):              # bands outermost, raster_pair.py:379-381
+                with torch.cuda.stream(streams[band_i % n_streams]):
+                    run_band(band_i)
+            for st in streams:
+                main.wait_stream(st)
+            for t in corr_planes + [p.array for p in param_planes]:
+                if is_tensor(t):
+                    t.record_stream(main)
+        else:
+            for band_i in range(n_bands):
+                run_band(band_i)
 
         stack = torch.stack if is_tensor(corr_planes[0]) else np.stack
         corr = RasterArray(stack(corr_planes), self._src.crs, self._src.transform, nodata=out_profile['nodata'])
