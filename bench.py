@@ -99,7 +99,7 @@ def run_reference(args, cfg, rank):
     from homonim_b200.synthetic import make_pair
     cores = os.cpu_count() or 1
     cv2.setNumThreads(cores)
-    os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+    torch.set_num_threads(cores)
     # bounded sample: one band, and a crop for the source-resolution workload, so that K steps end within minutes
     hp, wp = (cfg['hp'], cfg['wp']) if cfg['proc_crs'] == 'ref' else (min(cfg['hp'], 2048), min(cfg['wp'], 2048))
     src_ra, ref_ra = make_pair(hp, wp, cfg['ratio'], bands=1, dtype=cfg['dtype'], mu=cfg['mu'], seed=2,
@@ -144,8 +144,13 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
 
     if args.impl == 'reference':
+        # all host threads (torchrun exports OMP_NUM_THREADS=1; the OpenMP runtime reads it when the oracle's C
+        # restatement is first loaded, so override it before anything is imported)
+        os.environ['OMP_NUM_THREADS'] = str(os.cpu_count() or 1)
         run_reference(args, cfg, rank)
         return
+    if world == 1:
+        os.environ.setdefault('OMP_NUM_THREADS', str(os.cpu_count() or 1))
 
     import torch
     import torch.distributed as dist

@@ -1,0 +1,77 @@
+"""
+GPU tier: row-band sharding (homonim_b200/dist.py) must reproduce the single-GPU result.  Runs with as many ranks as
+there are GPUs (1 on the single-GPU box: the degenerate group still exercises the code path; 2+ with gpurun --gpus N).
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+import torch.distributed as dist   # noqa: E402
+import torch.multiprocessing as mp   # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, result_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        from homonim_b200 import Affine, KernelModel, Model, RasterArray, RefSpaceModel
+        from homonim_b200.dist import RowBands, fit_same_grid_sharded, fuse_refspace_sharded, \
+            source_band_for_proc_rows
+        from homonim_b200.synthetic import make_pair
+        nan = float('nan')
+        # ---- proc_crs = ref, one raster as row bands (C5a geometry, scaled down) -----------------------------------
+        src_ra, ref_ra = make_pair(90, 64, 20, bands=1, dtype='float32', mu=0.3, seed=21, device=f'cuda:{rank}',
+                                   src_nodata=nan, ref_pad=0)
+        src = RasterArray(src_ra.array[0].contiguous(), src_ra.crs, src_ra.transform, nodata=nan)
+        ref = RasterArray(ref_ra.array[0].contiguous(), ref_ra.crs, ref_ra.transform, nodata=nan)
+        for model_name, kshape, thresh in ((Model.gain_blk_offset, (15, 15), None), (Model.gain_offset, (5, 5), 0.25)):
+            model = RefSpaceModel(model_name, kshape, find_r2=True, r2_inpaint_thresh=thresh)
+            full_params = model.fit(src, ref)
+            full_corr = model.apply(src, full_params).array
+            bands = RowBands.split(ref.height, world)
+            r0, r1 = source_band_for_proc_rows(src.shape, src.transform, ref.transform, bands.band(rank))
+            src_local = RasterArray(src.array[r0:r1].contiguous(), src.crs, src.transform * Affine.translation(0, r0),
+                                    nodata=nan)
+            corr_local, param_ra = fuse_refspace_sharded(model, src_local, ref, bands)
+            assert torch.equal(torch.isnan(param_ra.array), torch.isnan(full_params.array))
+            assert torch.equal(param_ra.array.nan_to_num(0), full_params.array.nan_to_num(0)), 'sharded params differ'
+            assert torch.equal(corr_local.array.nan_to_num(-1), full_corr[r0:r1].nan_to_num(-1)), 'sharded corr differ'
+        # ---- same grid (C5b geometry, scaled down): halo exchange of kh // 2 rows ------------------------------------
+        s_ra, r_ra = make_pair(400, 333, 1, bands=1, dtype='float32', mu=0.3, seed=22, device=f'cuda:{rank}',
+                               src_nodata=nan, ref_pad=0)
+        s_full, r_full = s_ra.array[0].contiguous(), r_ra.array[0].contiguous()
+        km = KernelModel(Model.gain_offset, (15, 15), find_r2=True, r2_inpaint_thresh=None)
+        full = km._fit_planes(s_full, nan, r_full, nan)
+        bands = RowBands.split(s_full.shape[0], world)
+        a, b = bands.band(rank)
+        part = fit_same_grid_sharded(km, s_full[a:b].contiguous(), nan, r_full[a:b].contiguous(), nan, bands)
+        ref_part = full[:, a:b]
+        assert torch.equal(torch.isnan(part), torch.isnan(ref_part))
+        same = ((part == ref_part) | (torch.isnan(part) & torch.isnan(ref_part))).float().mean().item()
+        assert same > 0.999, f'same-grid sharded fit: only {same:.5f} bit-identical'
+        fin = torch.isfinite(ref_part)
+        rel = ((part - ref_part).abs()[fin] / ref_part.abs()[fin].clamp_min(1e-3)).max().item()
+        assert rel <= 1e-4, rel
+        open(os.path.join(result_dir, f'ok{rank}'), 'w').write('ok')
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_equals_unsharded(tmp_path):
+    world = min(torch.cuda.device_count(), 4)
+    assert world >= 1
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f'ok{r}').exists() for r in range(world))
