@@ -32,6 +32,26 @@ struct FitGeom {
     int rows_per_band;
 };
 
+// a / b in double with a quotient that is correctly rounded in all but a vanishing fraction of cases (approximate
+// reciprocal + 2 Newton steps + one residual correction: ~9 instructions instead of the ~35 of the IEEE routine).
+// Its result is immediately rounded to float32 by the callers, so a last-bit difference in double is invisible
+// except on an exact float32 tie.  Zero / non-finite / extreme operands take the IEEE division (x/0 -> +-inf,
+// 0/0 -> nan must come out exactly as numpy produces them).
+__device__ __forceinline__ double hb_ddiv(double a, double b)
+{
+    const double ab = fabs(b);
+    if (!(ab > 1e-280 && ab < 1e280) || !(fabs(a) < 1e280)) return a / b;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    double q = a * r;
+    const double rem = fma(-b, q, a);
+    return fma(rem, r, q);
+}
+
 // contribution of one pixel to the running sums
 template <int NQ, bool NORM>
 __device__ __forceinline__ void pixel_terms(float s, float r, bool valid, double n0, double n1, double (&q)[NQ],
@@ -86,6 +106,13 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
     double n0 = 1.0, n1 = 0.0;
     if (NORM) { n0 = norm[0]; n1 = norm[1]; }
 
+    // validity of a pixel without per-pixel branching on the nodata kind: "equals the nodata value" compares with nan
+    // (never true) when there is no value nodata, and the nan test is switched by a kernel-uniform flag
+    const float ndv_s = (nd_s.has && !nd_s.is_nan) ? nd_s.value : qnan, ndv_r = (nd_r.has && !nd_r.is_nan) ? nd_r.value : qnan;
+    const bool nan_s = nd_s.has && nd_s.is_nan, nan_r = nd_r.has && nd_r.is_nan;
+    auto valid2 = [&](float sv, float rv) {
+        return !(sv == ndv_s) && !(rv == ndv_r) && !(nan_s && (sv != sv)) && !(nan_r && (rv != rv));
+    };
     bool col_in[C];
 #pragma unroll
     for (int i = 0; i < C; i++) col_in[i] = (cx + i >= 0) && (cx + i < g.w);
@@ -124,20 +151,29 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
 
     const bool single_row = (g.kh == 1), single_col = (g.kw == 1);
     const long e_first = y0 - hh, e_last = y1 - 1 + hh;
+    // the rows of step e + 1 are fetched (into registers) before step e is computed: their latency hides behind a
+    // whole row step instead of heading every step's dependency chain
+    float se[C], re[C], sl[C], rl[C], nse[C], nre[C], nsl[C], nrl[C];
+#pragma unroll
+    for (int i = 0; i < C; i++) { se[i] = re[i] = sl[i] = rl[i] = nse[i] = nre[i] = nsl[i] = nrl[i] = 0.f; }
+    auto fetch = [&](long e, float (&a)[C], float (&b)[C], float (&c)[C], float (&d)[C]) {
+        const long l = e - g.kh;
+        if ((e >= 0) && (e < g.h)) load_row(e, a, b);
+        if (!single_row && (l >= e_first) && (l >= 0) && (l < g.h)) load_row(l, c, d);
+    };
+    fetch(e_first, se, re, sl, rl);
     for (long e = e_first; e <= e_last; e++) {
         // ---- vertical running sums: entering row e, leaving row e - kh ---------------------------------------------
         const long l = e - g.kh;
         const bool has_e = (e >= 0) && (e < g.h);
         const bool has_l = !single_row && (l >= e_first) && (l >= 0) && (l < g.h);
-        float se[C], re[C], sl[C], rl[C];
-        if (has_e) load_row(e, se, re);
-        if (has_l) load_row(l, sl, rl);
+        if (e < e_last) fetch(e + 1, nse, nre, nsl, nrl);
 #pragma unroll
         for (int i = 0; i < C; i++) {
             bool ve = false;
             if (has_e) {
                 double q[NQ]; int cnt;
-                ve = col_in[i] && hb_valid(se[i], nd_s) && hb_valid(re[i], nd_r);
+                ve = col_in[i] && valid2(se[i], re[i]);
                 pixel_terms<NQ, NORM>(se[i], re[i], ve, n0, n1, q, cnt);
                 ve = cnt != 0;
                 if (single_row) {                                    // kh == 1: the window IS this row (exact)
@@ -157,13 +193,15 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
             vring[i] = (vring[i] << 1) | (ve ? 1ull : 0ull);
             if (has_l) {
                 double q[NQ]; int cnt;
-                const bool vl = col_in[i] && hb_valid(sl[i], nd_s) && hb_valid(rl[i], nd_r);
+                const bool vl = col_in[i] && valid2(sl[i], rl[i]);
                 pixel_terms<NQ, NORM>(sl[i], rl[i], vl, n0, n1, q, cnt);
 #pragma unroll
                 for (int k = 0; k < NQ; k++) V[i][k] = __dsub_rn(V[i][k], q[k]);
                 VN[i] -= cnt;
             }
         }
+#pragma unroll
+        for (int i = 0; i < C; i++) { se[i] = nse[i]; re[i] = nre[i]; sl[i] = nsl[i]; rl[i] = nrl[i]; }   // rotate
         const long y = e - hh;                                       // output row completed by this step
         if (y < y0) continue;                                        // still filling the first window (uniform)
         const int buf = (int)(y & 1);
@@ -210,8 +248,8 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
 #pragma unroll
         for (int i = 0; i < C; i++) {
 #pragma unroll
-            for (int k = 0; k < NQ; k++) s_q[buf][k][t * C + i] = excl[k] + pre[i][k];
-            if (HAS_N) s_n[buf][t * C + i] = excl_n + pren[i];
+            for (int k = 0; k < NQ; k++) s_q[buf][k][i * kFitThreads + t] = excl[k] + pre[i][k];
+            if (HAS_N) s_n[buf][i * kFitThreads + t] = excl_n + pren[i];
         }
         __syncthreads();        // (double-buffered: the next row writes the other buffer, so one barrier per row)
         }
@@ -222,7 +260,13 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
         for (int i = 0; i < C; i++) {
             const int ci = t * C + i;
             const int a = ci + hw, b = ci - hw - 1;
+            // column c is stored at slot (c % C) * threads + c / C (conflict-free for both the stores and these loads);
+            // the window spans at most two warps (kw <= 129 <= columns per warp + 1): one conditional total
             const int wa = a / WCOLS, wb = (b >= 0) ? b / WCOLS : 0;
+            const int sa = (a % C) * kFitThreads + a / C;
+            const int sb = (b >= 0) ? (b % C) * kFitThreads + b / C : 0;
+            const bool cross = (wa != wb);
+            const bool cross2 = (wa - wb) > 1;                        // only when kw > columns per warp
             double W[NQ];
             int N = 0;
             if (single_col) {
@@ -232,15 +276,17 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
             } else {
 #pragma unroll
                 for (int k = 0; k < NQ; k++) {
-                    double v = s_q[buf][k][a];
-                    for (int ww = wb; ww < wa; ww++) v += s_tot[buf][k][ww];
-                    if (b >= 0) v -= s_q[buf][k][b];
+                    double v = s_q[buf][k][sa];
+                    if (cross) v += s_tot[buf][k][wb];
+                    if (cross2) v += s_tot[buf][k][wb + 1];
+                    if (b >= 0) v -= s_q[buf][k][sb];
                     W[k] = v;
                 }
                 if (HAS_N) {
-                    int v = s_n[buf][a];
-                    for (int ww = wb; ww < wa; ww++) v += s_ntot[buf][ww];
-                    if (b >= 0) v -= s_n[buf][b];
+                    int v = s_n[buf][sa];
+                    if (cross) v += s_ntot[buf][wb];
+                    if (cross2) v += s_ntot[buf][wb + 1];
+                    if (b >= 0) v -= s_n[buf][sb];
                     N = v;
                 }
             }
@@ -256,7 +302,7 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
                 fN = (float)N;
                 const float num = __fsub_rn(__fmul_rn(fN, fP), __fmul_rn(fS, fR));                  // :338, float32
                 const double den = __dsub_rn(__dmul_rn((double)fN, W[Q_S2]), (double)__fmul_rn(fS, fS));   // :342
-                gain = (float)((double)num / den);                                                   // :348
+                gain = (float)hb_ddiv((double)num, den);                                             // :348
                 off = __fdiv_rn(__fsub_rn(fR, __fmul_rn(gain, fS)), fN);                            // :351
                 if (WANT_R2) {
                     const double ss_tot = __dsub_rn(__dmul_rn((double)fN, W[Q_R2]), (double)__fmul_rn(fR, fR));   // :179
@@ -271,12 +317,12 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
                     ss_res = __dadd_rn(ss_res, W[Q_R2]);
                     ss_res = __dadd_rn(ss_res, (double)t6);
                     ss_res = __dmul_rn(ss_res, (double)fN);                                          // :203
-                    r2 = __fsub_rn(1.f, (float)(ss_res / ss_tot));                                   // :212-213
+                    r2 = __fsub_rn(1.f, (float)hb_ddiv(ss_res, ss_tot));                            // :212-213
                 }
             } else {
                 // gain (kernel_model.py:265) -- for gain-blk-offset on the normalised, float64 source sums
                 float g0;
-                if (NORM) g0 = (float)((double)fR / W[Q_S]);
+                if (NORM) g0 = (float)hb_ddiv((double)fR, W[Q_S]);
                 else { fS = (float)W[Q_S]; g0 = __fdiv_rn(fR, fS); }
                 if (WANT_R2) {
                     fN = (float)N;
@@ -286,7 +332,7 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
                     const double t3 = NORM ? __dmul_rn((double)g2, W[Q_P]) : (double)__fmul_rn(g2, (float)W[Q_P]);
                     double ss_res = __dadd_rn(__dsub_rn(t1, t3), W[Q_R2]);                           // :201
                     ss_res = __dmul_rn(ss_res, (double)fN);
-                    r2 = __fsub_rn(1.f, (float)(ss_res / ss_tot));
+                    r2 = __fsub_rn(1.f, (float)hb_ddiv(ss_res, ss_tot));
                 }
                 if (NORM) {
                     off = (float)__dmul_rn((double)g0, n1);                                          // :301
