@@ -232,12 +232,14 @@ def main():
         d2h = out_host.numel() * out_host.element_size()
 
         def e2e_step():
-            s = RasterArray(src_host.to(device, non_blocking=True), src_ra.crs, src_ra.transform, nodata=src_ra.nodata)
-            r = RasterArray(ref_host.to(device, non_blocking=True), ref_ra.crs, ref_ra.transform, nodata=ref_ra.nodata)
+            # the public call with HOST rasters (pinned CPU tensors): per band, host -> device copy of the source,
+            # fit + apply, device -> host copy of the corrected band into `corr_out`; process() returns when the
+            # corrected image is in host memory
+            s = RasterArray(src_host, src_ra.crs, src_ra.transform, nodata=src_ra.nodata)
+            r = RasterArray(ref_host, ref_ra.crs, ref_ra.transform, nodata=ref_ra.nodata)
             with RasterFuse(s, r, proc_crs=ProcCrs(cfg['proc_crs'])) as f:
-                corr, _ = step(f)
-            out_host.copy_(corr.array, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+                f.process(model=Model(cfg['model']), kernel_shape=cfg['kernel_shape'], model_config=model_config,
+                          corr_out=out_host)
 
         for _ in range(2):
             e2e_step()

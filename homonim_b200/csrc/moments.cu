@@ -62,17 +62,22 @@ __device__ __forceinline__ void pixel_terms(float s, float r, bool valid, double
         // src * norm[0] + norm[1] in float64, two roundings (kernel_model.py:295 under numpy >= 2)
         ds = __dadd_rn(__dmul_rn((double)s, n0), n1);
         valid = valid && !isnan(ds);
+        if (!valid) { ds = 0.0; r = 0.f; }       // kernel_model.py:246-247
+        dr = (double)r;
     } else {
+        // zero the invalid pixel once, on the float32 inputs (kernel_model.py:246-247 / 320-321): every term below is
+        // then zero without further selects
+        s = valid ? s : 0.f;
+        r = valid ? r : 0.f;
         ds = (double)s;
+        dr = (double)r;
     }
-    dr = (double)r;
-    if (!valid) { ds = 0.0; dr = 0.0; }          // kernel_model.py:246-247 / 320-321
     q[Q_S] = ds;
     q[Q_R] = dr;
     if (NQ > 2) {
         // src*ref is formed in the arrays' dtype before filtering (kernel_model.py:175, 334): float32 product for
         // float32 planes, float64 when the source was normalised
-        q[Q_P] = NORM ? __dmul_rn(ds, dr) : (double)__fmul_rn(valid ? s : 0.f, valid ? r : 0.f);
+        q[Q_P] = NORM ? __dmul_rn(ds, dr) : (double)__fmul_rn(s, r);
         q[Q_S2] = __dmul_rn(ds, ds);             // cv.sqrBoxFilter squares in double
     }
     if (NQ > 4) q[Q_R2] = __dmul_rn(dr, dr);

@@ -185,27 +185,38 @@ class RasterFuse:
         transform = ref_ra.transform * Affine.translation(col0, row0)
         return RasterArray(array, ref_ra.crs, transform, nodata=ref_ra.nodata)
 
-    def _process_band(self, band_i: int, model: KernelModel) -> Tuple[RasterArray, RasterArray]:
-        """ One band of reference fuse.py:295-319 (``_process_block`` with a single block): read -> fit -> apply. """
+    def _process_band(self, band_i: int, model: KernelModel, out=None, stage: bool = False
+                      ) -> Tuple[RasterArray, RasterArray]:
+        """
+        One band of reference fuse.py:295-319 (``_process_block`` with a single block): read -> fit -> apply.
+        ``stage``: copy a host band to the device once up front (fit and apply both read it) and leave the results
+        on the device; otherwise results live where the inputs live.
+        """
         src_ra = _band(self._src, self._src_bands[band_i])
         ref_ra = self._ref_block(band_i)
+        if stage and not src_ra.is_device:
+            src_ra, ref_ra = src_ra.to_device(), ref_ra.to_device()
         param_ra = model.fit(src_ra, ref_ra)          # fuse.py:306
-        corr_ra = model.apply(src_ra, param_ra)       # fuse.py:307
+        corr_ra = model.apply(src_ra, param_ra, out=out)       # fuse.py:307
         return corr_ra, param_ra
 
     def process(self, corr_filename=None, model: Model = KernelModel.default_model,
                 kernel_shape: Tuple[int, int] = KernelModel.default_kernel_shape, param_filename=None,
                 build_ovw: bool = True, overwrite: bool = False, model_config: Optional[Dict] = None,
-                out_profile: Optional[Dict] = None, block_config: Optional[Dict] = None
+                out_profile: Optional[Dict] = None, block_config: Optional[Dict] = None, corr_out=None
                 ) -> Tuple[RasterArray, Optional[RasterArray]]:
         """
         Correct the source to surface reflectance (reference fuse.py:321-408).  Same arguments as the reference;
         ``corr_filename`` / ``param_filename`` only act as switches here (``param_filename is not None`` turns on the
         R2 band and returns the parameter raster, as ``find_r2=param_filename is not None`` does at fuse.py:377).
 
-        Returns ``(corr_ra, param_ra or None)``: ``corr_ra`` has one band per source band on the source grid;
-        ``param_ra`` interleaves parameters band-major as the reference's parameter file does
-        (index = param_i * n_bands + band_i, fuse.py:315).
+        ``corr_out`` (optional, additive): a pre-allocated ``[bands, H, W]`` tensor of the output dtype to receive the
+        corrected image -- a CUDA tensor, or a (pinned) CPU tensor for host pipelines, where each band's device -> host
+        copy then overlaps the other bands' work.
+
+        Returns ``(corr_ra, param_ra or None)``: ``corr_ra`` has one band per source band on the source grid and lives
+        where the source lives (CUDA tensor / numpy array) or in ``corr_out``; ``param_ra`` interleaves parameters
+        band-major as the reference's parameter file does (index = param_i * n_bands + band_i, fuse.py:315).
         """
         self._assert_open()
         model_type = Model(model)
@@ -217,21 +228,46 @@ class RasterFuse:
         model_cls = SrcSpaceModel if self.proc_crs == ProcCrs.src else RefSpaceModel          # fuse.py:376
         kernel_model = model_cls(model_type, kernel_shape, find_r2=param_filename is not None, **model_config)
 
+        if torch is None or not torch.cuda.is_available():
+            from homonim_b200 import _native
+            _native.require_device()                   # raises: there is no CPU implementation
+
         n_bands = len(self._src_bands)
-        corr_planes, param_planes = [None] * n_bands, [None] * n_bands
+        hs, ws = self._src.shape
+        out_dtype = out_profile['dtype'] or 'float32'
+        out_nodata = out_profile['nodata']
+        plain_f32 = out_dtype == 'float32' and (out_nodata is None or (isinstance(out_nodata, float)
+                                                                       and np.isnan(out_nodata)))
+        src_on_device = self._src.is_device
+        device = self._src.array.device if src_on_device else torch.device('cuda', torch.cuda.current_device())
+        # where the corrected bands go: straight into a [bands, H, W] device tensor (no stacking copy), or band by
+        # band to the host
+        to_host = (corr_out is not None and not corr_out.is_cuda) or (corr_out is None and not src_on_device)
+        if corr_out is not None:
+            if tuple(corr_out.shape) != (n_bands, hs, ws) or str(corr_out.dtype).replace('torch.', '') != out_dtype:
+                raise ValueError(f"'corr_out' must be a [{n_bands}, {hs}, {ws}] {out_dtype} tensor")
+            corr_all = corr_out
+        elif to_host:
+            corr_all = torch.empty((n_bands, hs, ws), dtype=getattr(torch, out_dtype))
+        else:
+            corr_all = torch.empty((n_bands, hs, ws), dtype=getattr(torch, out_dtype), device=device)
+        param_planes = [None] * n_bands
 
         def run_band(band_i):
-            corr_ra, param_ra = self._process_band(band_i, kernel_model)
-            corr_planes[band_i] = _convert_dtype(corr_ra, out_profile['dtype'], out_profile['nodata'])
-            param_planes[band_i] = param_ra
+            direct = (not to_host) and plain_f32       # the apply kernel writes its plane of corr_all itself
+            corr_ra, param_ra = self._process_band(band_i, kernel_model, out=corr_all[band_i] if direct else None,
+                                                   stage=True)
+            if not direct:
+                plane = _convert_dtype(corr_ra, out_dtype, out_nodata)
+                corr_all[band_i].copy_(plane, non_blocking=True)
+            param_planes[band_i] = param_ra if (src_on_device or param_filename is None) else param_ra.to_host()
 
         # Bands are independent (the reference runs (band, block) jobs on a thread pool, fuse.py:396-408).  On the
         # GPU each band is enqueued on its own CUDA stream, so that the small latency-bound kernels of one band (fit
-        # on the proc grid, in-painting) overlap the bandwidth-bound resampling kernels of the others.
+        # on the proc grid, in-painting) overlap the bandwidth-bound resampling kernels of the others -- and, for host
+        # rasters, one band's host <-> device copies overlap the other bands' kernels.
         n_streams = min(n_bands, max(1, int(block_config['threads'])), 4)
-        use_streams = (torch is not None and n_streams > 1 and torch.cuda.is_available()
-                       and is_tensor(self._src.array) and self._src.array.is_cuda)
-        if use_streams:
+        if n_streams > 1:
             main = torch.cuda.current_stream()
             streams = _band_streams(n_streams)
             for st in streams:
@@ -241,19 +277,23 @@ class RasterFuse:
                     run_band(band_i)
             for st in streams:
                 main.wait_stream(st)
-            for t in corr_planes + [p.array for p in param_planes]:
-                if is_tensor(t):
+            for t in [corr_all] + [p.array for p in param_planes]:
+                if is_tensor(t) and t.is_cuda:
                     t.record_stream(main)
         else:
             for band_i in range(n_bands):
                 run_band(band_i)
+        if to_host:
+            torch.cuda.current_stream().synchronize()  # the host copies have landed
 
-        stack = torch.stack if is_tensor(corr_planes[0]) else np.stack
-        corr = RasterArray(stack(corr_planes), self._src.crs, self._src.transform, nodata=out_profile['nodata'])
+        corr_array = corr_all if (src_on_device or corr_out is not None or is_tensor(self._src.array)) \
+            else corr_all.numpy()
+        corr = RasterArray(corr_array, self._src.crs, self._src.transform, nodata=out_nodata)
         params = None
         if param_filename is not None:
             n_params = param_planes[0].count
             planes = [param_planes[b].array[p] for p in range(n_params) for b in range(n_bands)]
+            stack = torch.stack if is_tensor(planes[0]) else np.stack
             params = RasterArray(stack(planes), param_planes[0].crs, param_planes[0].transform, nodata=float('nan'))
         return corr, params
 

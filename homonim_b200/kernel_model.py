@@ -279,22 +279,35 @@ class KernelModel:
         params = self._fit_planes(src_t, src_ra.nodata, ref_t, ref_ra.nodata)
         return RasterArray(_result(params, on_device), src_ra.crs, src_ra.transform, nodata=NAN)
 
-    def apply(self, src_ra: RasterArray, param_ra: RasterArray) -> RasterArray:
+    def apply(self, src_ra: RasterArray, param_ra: RasterArray, out=None) -> RasterArray:
+        """
+        Reference kernel_model.py:442-463.  ``out`` (optional, additive): a float32 CUDA tensor ``[H, W]`` to write the
+        corrected band into (device-resident callers avoid a copy); the returned RasterArray then wraps it.
+        """
         if (param_ra.transform != src_ra.transform) or (param_ra.shape != src_ra.shape):
             raise ValueError("'param_ra' and 'src_ra' must have the same CRS, transform and shape")
         _require_torch()
-        on_device = src_ra.is_device and param_ra.is_device
+        on_device = (src_ra.is_device and param_ra.is_device) or out is not None
         src_t, par_t = _to_device(src_ra.array), _to_device(param_ra.array)
-        corr = self._apply_planes(src_t, src_ra.nodata, par_t, mask_src=False)
+        corr = self._apply_planes(src_t, src_ra.nodata, par_t, mask_src=False, out=out)
         return RasterArray(_result(corr, on_device), param_ra.crs, param_ra.transform, nodata=param_ra.nodata)
 
     @staticmethod
-    def _apply_planes(src_t, src_nodata, par_t, mask_src: bool):
+    def _check_out(out, h, w, device):
+        if out is None:
+            return torch.empty((h, w), dtype=torch.float32, device=device)
+        if (not is_tensor(out)) or (not out.is_cuda) or out.dtype != torch.float32 or tuple(out.shape) != (h, w) \
+                or not out.is_contiguous():
+            raise ValueError("'out' must be a contiguous float32 CUDA tensor with the shape of 'src_ra'")
+        return out
+
+    @staticmethod
+    def _apply_planes(src_t, src_nodata, par_t, mask_src: bool, out=None):
         lib = _native.lib()
         if par_t.ndim != 3 or par_t.shape[0] < 2 or par_t.dtype != torch.float32:
             raise ValueError("'param_ra' must hold at least 2 float32 bands (gain, offset)")
         h, w = int(src_t.shape[-2]), int(src_t.shape[-1])
-        corr = torch.empty((h, w), dtype=torch.float32, device=src_t.device)
+        corr = KernelModel._check_out(out, h, w, src_t.device)
         has, nd = _nodata_args(src_nodata)
         _call('hb_apply_same_grid', src_t.data_ptr(), _plane_code(src_t), has, nd, int(mask_src),
                                              par_t.data_ptr(), h, w, corr.data_ptr(), _stream())
@@ -390,10 +403,10 @@ class RefSpaceModel(KernelModel):
         params = self._fit_planes(src_ds, NAN, ref_t, ref_ra.nodata)                         # :482
         return RasterArray(_result(params, on_device), ref_ra.crs, ref_ra.transform, nodata=NAN)
 
-    def apply(self, src_ra: RasterArray, param_ra: RasterArray) -> RasterArray:
+    def apply(self, src_ra: RasterArray, param_ra: RasterArray, out=None) -> RasterArray:
         _require_torch()
         lib = _native.lib()
-        on_device = src_ra.is_device and param_ra.is_device
+        on_device = (src_ra.is_device and param_ra.is_device) or out is not None
         src_t, par_t = _to_device(src_ra.array), _to_device(param_ra.array)
         if par_t.ndim != 3 or par_t.shape[0] < 2 or par_t.dtype != torch.float32:
             raise ValueError("'param_ra' must hold at least 2 float32 bands (gain, offset)")
@@ -408,7 +421,7 @@ class RefSpaceModel(KernelModel):
             # fused up-sample + apply (:491, :497-503): the up-sampled parameters never reach memory
             gm = grid_map(param_ra.transform, src_ra.transform)       # source grid -> param grid
             hp, wp = int(par2.shape[-2]), int(par2.shape[-1])
-            corr = torch.empty((hs, ws), dtype=torch.float32, device=src_t.device)
+            corr = self._check_out(out, hs, ws, src_t.device)
             has, nd = _nodata_args(src_ra.nodata)
             _call('hb_upsample_apply', src_t.data_ptr(), _plane_code(src_t), hs, ws, has, nd,
                                                 par2.data_ptr(), hp, wp, gm.sx, gm.ox, gm.sy, gm.oy,
@@ -422,9 +435,9 @@ class RefSpaceModel(KernelModel):
                 cover_us = _resample_up(cover.to(torch.float32), param_ra.transform, None, (hs, ws),
                                         src_ra.transform, _native.HB_UP_NEAREST)
                 par_us[:, ~(cover_us > 0)] = NAN                                             # :497-498
-                corr = self._apply_planes(src_t, src_ra.nodata, par_us, mask_src=False)
+                corr = self._apply_planes(src_t, src_ra.nodata, par_us, mask_src=False, out=out)
             else:
-                corr = self._apply_planes(src_t, src_ra.nodata, par_us, mask_src=True)       # :500
+                corr = self._apply_planes(src_t, src_ra.nodata, par_us, mask_src=True, out=out)       # :500
         return RasterArray(_result(corr, on_device), src_ra.crs, src_ra.transform, nodata=NAN)
 
 

@@ -206,7 +206,8 @@ class RasterArray:
         if torch is None:
             raise RuntimeError('torch is required for device rasters')
         array = self._array if is_tensor(self._array) else torch.from_numpy(np.ascontiguousarray(self._array))
-        return RasterArray(array.to(device).contiguous(), self._crs, self._transform, nodata=self._nodata)
+        return RasterArray(array.to(device, non_blocking=True).contiguous(), self._crs, self._transform,
+                           nodata=self._nodata)
 
     def to_host(self) -> 'RasterArray':
         """ Copy of this raster whose array is a numpy array. """
