@@ -11,6 +11,7 @@
 #include <type_traits>
 
 #include "hb_common.cuh"
+#include "upsample_poly.cuh"
 
 namespace {
 
@@ -54,6 +55,7 @@ template <> struct Raw8<float> {
     }
 };
 
+template <typename T> constexpr int hb_dtype_code() { return sizeof(T) == 1 ? HB_U8 : (sizeof(T) == 2 ? HB_U16 : HB_F32); }
 template <typename T> struct IsInt { static constexpr bool value = true; };
 template <> struct IsInt<float> { static constexpr bool value = false; };
 
@@ -297,14 +299,9 @@ int launch_downsample(const void *src, long hs, long ws, NoData nd, float *dst, 
 // CTA barrier): it owns a 128-pixel-wide column strip (4 pixels per lane, vector stores) and walks down it row by row.
 // Source pixels arrive through a 4-deep cp.async ring (each lane copies, and later reads, only its own bytes).
 //
-//   FAST rows (ratio >= 4, every tap of the warp's window valid and in range -- the overwhelming majority).
-//     Inside one coarse cell the interpolated surface is a bicubic polynomial.  When the tap rows change (once per
-//     `ratio` destination rows) every lane interpolates its 4 pixel COLUMNS through the 4 tap rows (x-weights) and
-//     converts the 4 results into the cubic in dy of that pixel column: 4 coefficients per pixel and band, in
-//     registers.  A destination row then costs one Horner evaluation per pixel and band (3 FMAs) -- no shared memory,
-//     no per-row weights -- fused with corr = gain*src + offset.  Mathematically identical to GDAL's sum of 16
-//     weighted taps (sum of weights == 1, so GDAL does not renormalise); evaluated in double like GDAL.
-//   GENERAL rows (windows touching nodata or the raster edge, and all rows when ratio < 4).
+//   (Destinations >= ~3.4x finer than the coarse grid take the polynomial fast path of upsample_poly.cu instead; this
+//   kernel handles small ratios, unaligned rasters and the coverage mask of mask_partial.)
+//   Per destination row:
 //     A. lane <-> coarse column: combine the column's 4 tap rows (register cache, invalid taps zeroed + validity mask)
 //        with the row's y-weights into warp-private shared memory (values, weight sums, flags);
 //     C. lane <-> 4 pixels: sum the 4 column combinations with the pixel's x-weights, apply GDAL's centre-pixel and
@@ -392,20 +389,15 @@ struct UpGeom {
     double sx, ox, sy, oy;
     int ncols;            // coarse columns staged per warp (cells + 3)
     int rows_per_cta;
-    int fast;             // the column-polynomial path is worth it (ratio >= 4)
 };
 
 // T: storage type of the source plane (APPLY); NB: coarse bands (1 or 2); APPLY: fuse gain*src+offset;
 // MC: coarse columns per lane (ncols <= 32 * MC).
-// list != nullptr: fix-up mode after upsample_fast_kernel -- every warp takes one (strip, cell row) segment from the
-// list the fast kernel appended to and re-does its rows (source pixels are read directly, not through the ring).
 template <typename T, int NB, bool APPLY, bool ALIGNED, int MC>
 __global__ void __launch_bounds__(kThreads, HB_UP_MIN_CTAS)
 upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ coarse, UpGeom g,
-                const uint8_t *__restrict__ cover, float *__restrict__ out, const int2 *__restrict__ list,
-                const int *__restrict__ list_count)
+                const uint8_t *__restrict__ cover, float *__restrict__ out)
 {
-    constexpr bool FAST = false;
     constexpr int PPT = kUpPpt;
     constexpr int NOUT = (NB == 2 && !APPLY) ? 2 : 1;
     constexpr int kLaneBytes = APPLY ? Src4<T>::kBytes : 0;
@@ -416,7 +408,6 @@ upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ 
     const int ncols = g.ncols;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float qnan = __int_as_float(0x7fc00000);
-    const bool list_mode = (list != nullptr);
 
     auto row_info = [&](long Y) {
         const double srcy = g.sy * ((double)Y + 0.5) + g.oy;
@@ -433,28 +424,13 @@ upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ 
         return ri;
     };
 
-    long Y0, Y1, strip;
+    // ---- per-CTA row table: y-geometry of the CTA's destination rows ---------------------------------------------------
     RowInfo *s_rows = reinterpret_cast<RowInfo *>(smem_raw);
-    if (!list_mode) {
-        // ---- per-CTA row table: y-geometry of the CTA's destination rows -------------------------------------------
-        Y0 = (long)blockIdx.y * g.rows_per_cta;
-        Y1 = min(Y0 + (long)g.rows_per_cta, g.hs);
-        strip = (long)blockIdx.x * kUpWarps + warp;
-        if ((long)threadIdx.x < Y1 - Y0) s_rows[threadIdx.x] = row_info(Y0 + threadIdx.x);
-        __syncthreads();                                    // the only CTA barrier
-    } else {
-        // ---- fix-up mode: this warp's (strip, tap row) segment; its rows are those whose first tap row is ky - 1 ----
-        const long e = (long)blockIdx.x * kUpWarps + warp;
-        if (e >= *list_count) return;
-        const int2 seg = list[e];
-        strip = seg.x;
-        long ya = (long)floor(((double)seg.y + 0.5 - g.oy) / g.sy - 0.5) - 1;
-        if (ya < 0) ya = 0;
-        while (ya < g.hs && row_info(ya).ky < seg.y) ya++;
-        long yb = ya;
-        while (yb < g.hs && row_info(yb).ky == seg.y) yb++;
-        Y0 = ya; Y1 = yb;
-    }
+    const long Y0 = (long)blockIdx.y * g.rows_per_cta;
+    const long Y1 = min(Y0 + (long)g.rows_per_cta, g.hs);
+    const long strip = (long)blockIdx.x * kUpWarps + warp;
+    if ((long)threadIdx.x < Y1 - Y0) s_rows[threadIdx.x] = row_info(Y0 + threadIdx.x);
+    __syncthreads();                                        // the only CTA barrier
 
     // warp-private shared memory: values [ncols], weights [ncols], column flags [ncols] of ONE row, source ring
     const int comb_bytes = ((ncols * (2 * (int)sizeof(Pair) + 1)) + 15) / 16 * 16;
@@ -490,7 +466,7 @@ upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ 
         ctk = (ct >= 0 && ct < 4) ? ct : -1;
     };
     const bool full_vec = (X0 + PPT <= g.ws);
-    const bool use_async = APPLY && ALIGNED && full_vec && !list_mode;   // pixels come through the cp.async ring
+    const bool use_async = APPLY && ALIGNED && full_vec;   // pixels come through the cp.async ring
     double wxr[PPT][4];                                     // x-weights, first tap column, centre tap column per pixel
     int clr[PPT], ctr[PPT];
 #pragma unroll
@@ -500,11 +476,7 @@ upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ 
         bspline_weights(dxk, wxr[k]);
     }
 
-    // ---- state of the FAST path: cubic in dy per pixel column and band ----------------------------------------------
-    double q[FAST ? PPT : 1][NB][4];
-    int q_ky = INT_MIN;
-    bool q_clean = false;
-    // ---- state of the GENERAL path when it is the main path (!FAST): tap rows cached per lane column ---------------------
+    // ---- tap rows cached per lane column ---------------------------------------------------------------------------
     float tv[MC][NB][4];
     unsigned tmask[MC];
 #pragma unroll
@@ -520,7 +492,7 @@ upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ 
         }
         cp_async_commit();
     };
-    if (APPLY && !list_mode) {
+    if (APPLY) {
 #pragma unroll
         for (int st = 0; st < kUpStages - 1; st++) prefetch(Y0 + (long)st * kUpRb, st);
     }
@@ -562,7 +534,7 @@ upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ 
     int batch = 0;
     for (long Yb = Y0; Yb < Y1; Yb += kUpRb, batch++) {
         const int nrows = (int)min((long)kUpRb, Y1 - Yb);
-        if (APPLY && !list_mode) {
+        if (APPLY) {
             prefetch(Yb + (long)(kUpStages - 1) * kUpRb, (batch + kUpStages - 1) % kUpStages);
             cp_async_wait<kUpStages - 1>();                 // this stage's source rows have landed
         }
@@ -571,105 +543,17 @@ upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ 
         for (int rr = 0; rr < nrows; rr++) {
             float *orow = out + (Yb + rr) * g.ws + X0;
             const long Y = Yb + rr;
-            const RowInfo ri = list_mode ? row_info(Y) : s_rows[Y - Y0];
-
-            // ---- new cell row: rebuild the per-pixel-column cubics (FAST path) ---------------------------------------
-            if (FAST && ri.ky != q_ky) {                    // warp-uniform
-                double dxk[PPT];
-                int clk[PPT], ctk[PPT];
-                bool lane_clean = (cover == nullptr) && (ri.ky - 1 >= 0) && (ri.ky + 2 < g.hp);
-#pragma unroll
-                for (int k = 0; k < PPT; k++) {
-                    px_geom(k, dxk[k], clk[k], ctk[k]);
-                    lane_clean = lane_clean && (ctk[k] == 1 || ctk[k] == 2) && (clk[k] - clk[0] >= 0) &&
-                                 (clk[k] - clk[0] <= 1);
-                }
-                // the lane's 4 pixels use tap columns clk[0] .. clk[0] + 4 (their windows start 0 or 1 column in)
-                const long col0 = col_base + clk[0];
-                lane_clean = lane_clean && (col0 >= 0) && (col0 + 4 < g.wp);
-                if (lane_clean) {
-                    // x-weights of every pixel over the 5-column window (zero where the pixel's window does not reach)
-                    double w5[PPT][5];
-#pragma unroll
-                    for (int k = 0; k < PPT; k++) {
-                        double wx[4];
-                        bspline_weights(dxk[k], wx);
-                        const bool sh = (clk[k] != clk[0]);
-                        w5[k][0] = sh ? 0.0 : wx[0];
-                        w5[k][1] = sh ? wx[0] : wx[1];
-                        w5[k][2] = sh ? wx[1] : wx[2];
-                        w5[k][3] = sh ? wx[2] : wx[3];
-                        w5[k][4] = sh ? wx[3] : 0.0;
-                    }
-#pragma unroll
-                    for (int b = 0; b < NB; b++) {
-                        const float *p = coarse + b * plane + (long)(ri.ky - 1) * g.wp + col0;
-                        double r[PPT][4];
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            double t[5];
-#pragma unroll
-                            for (int i = 0; i < 5; i++) t[i] = (double)__ldg(p + j * g.wp + i);
-                            lane_clean = lane_clean && !isnan((t[0] + t[1]) + (t[2] + t[3]) + t[4]);
-#pragma unroll
-                            for (int k = 0; k < PPT; k++)   // x-interpolation of tap row j at pixel column k
-                                r[k][j] = fma(w5[k][4], t[4], fma(w5[k][3], t[3], fma(w5[k][2], t[2],
-                                          fma(w5[k][1], t[1], w5[k][0] * t[0]))));
-                        }
-#pragma unroll
-                        for (int k = 0; k < PPT; k++) {     // cubic B-spline through the 4 tap rows, as a polynomial in dy
-                            q[k][b][0] = (r[k][0] + 4.0 * r[k][1] + r[k][2]) * (1.0 / 6.0);
-                            q[k][b][1] = (r[k][2] - r[k][0]) * 0.5;
-                            q[k][b][2] = (r[k][0] - 2.0 * r[k][1] + r[k][2]) * 0.5;
-                            q[k][b][3] = ((r[k][3] - r[k][0]) + 3.0 * (r[k][1] - r[k][2])) * (1.0 / 6.0);
-                        }
-                    }
-                }
-                q_clean = __all_sync(0xffffffffu, lane_clean);
-                q_ky = ri.ky;
-            }
+            const RowInfo ri = s_rows[Y - Y0];
 
             float s[PPT];
             bool ok[PPT];
             float res[NOUT][PPT];
-#ifdef HB_UP_SKELETON
-            if (true) {                                     // experiment: memory skeleton only (no interpolation)
-                load_src(Y, ring_b + rr * kRowBytes, s, ok);
-#pragma unroll
-                for (int k = 0; k < PPT; k++) res[0][k] = ok[k] ? s[k] * 2.0f : qnan;
-                store_row(orow, res);
-                continue;
-            }
-#endif
-            if (FAST && q_clean) {
-                // ---- FAST row: Horner in dy, fused apply --------------------------------------------------------------
-                load_src(Y, ring_b + rr * kRowBytes, s, ok);
-                const double dy = ri.dy;
-#pragma unroll
-                for (int k = 0; k < PPT; k++) {
-                    const double gv = fma(fma(fma(q[FAST ? k : 0][0][3], dy, q[FAST ? k : 0][0][2]), dy, q[FAST ? k : 0][0][1]), dy,
-                                          q[FAST ? k : 0][0][0]);
-                    double ov = 0.0;
-                    if (NB > 1) ov = fma(fma(fma(q[FAST ? k : 0][NB - 1][3], dy, q[FAST ? k : 0][NB - 1][2]), dy,
-                                             q[FAST ? k : 0][NB - 1][1]), dy, q[FAST ? k : 0][NB - 1][0]);
-                    const float gf = ok[k] ? (float)gv : qnan;
-                    const float of = ok[k] ? (float)ov : qnan;
-                    if (APPLY) {
-                        res[0][k] = __fadd_rn(__fmul_rn(gf, s[k]), of);   // two roundings, as numpy (kernel_model.py:461)
-                    } else {
-                        res[0][k] = gf;
-                        if constexpr (NOUT == 2) res[1][k] = of;
-                    }
-                }
-                store_row(orow, res);
-                continue;
-            }
 
             // ---- GENERAL row, phase A: column combinations ------------------------------------------------------------
             double wy[4];
             bspline_weights(ri.dy, wy);
-            if (FAST || ri.ky != a_ky) {                    // (warp-uniform) fetch / shift the tap rows
-                const bool shift1 = !FAST && (ri.ky - a_ky) == 1;
+            if (ri.ky != a_ky) {                            // (warp-uniform) fetch / shift the tap rows
+                const bool shift1 = (ri.ky - a_ky) == 1;
 #pragma unroll
                 for (int m = 0; m < MC; m++) {
                     const long col = col_base + lane + 32 * m;
@@ -769,172 +653,6 @@ upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ 
     }
 }
 
-// ---- FAST kernel (ratio >= ~5): per-pixel-column cubics in registers, nothing else ------------------------------------
-// One warp = 128-pixel strip x rows_per_cta rows, 4 pixels per lane.  At every change of tap rows the lane rebuilds,
-// for each of its 4 pixel columns and each band, the cubic in dy (4 double coefficients).  If any tap of the warp's
-// window is missing / out of range the whole (strip, tap row) segment is appended to `list` and skipped:
-// upsample_kernel re-does exactly those segments, one warp each, with GDAL's general rules.
-template <typename T, int NB, bool APPLY>
-__global__ void __launch_bounds__(kThreads, 2)
-upsample_fast_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ coarse, UpGeom g,
-                     float *__restrict__ out, int2 *__restrict__ list, int *__restrict__ list_count)
-{
-    constexpr int PPT = kUpPpt;
-    constexpr int NOUT = (NB == 2 && !APPLY) ? 2 : 1;
-    constexpr int kLaneBytes = APPLY ? Src4<T>::kBytes : 0;
-    constexpr int kRowBytes = 32 * kLaneBytes;
-    constexpr int kRingBytes = kUpStages * kUpRb * kRowBytes;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long Y0 = (long)blockIdx.y * g.rows_per_cta;
-    const long Y1 = min(Y0 + (long)g.rows_per_cta, g.hs);
-    const float qnan = __int_as_float(0x7fc00000);
-
-    // per-CTA row table: (dy, ky) of the CTA's destination rows
-    double2 *s_rows = reinterpret_cast<double2 *>(smem_raw);              // .x = dy, .y = (double)ky
-    if ((long)threadIdx.x < Y1 - Y0) {
-        const double srcy = g.sy * ((double)(Y0 + threadIdx.x) + 0.5) + g.oy;
-        const double ky = floor(srcy - 0.5);
-        s_rows[threadIdx.x] = make_double2(srcy - 0.5 - ky, ky);
-    }
-    __syncthreads();                                        // the only CTA barrier
-
-    const long strip = (long)blockIdx.x * kUpWarps + warp;
-    const long Xw0 = strip * kUpWarpW;
-    if (Xw0 >= g.ws) return;
-    const long X0 = Xw0 + (long)lane * PPT;                 // (ws % 4 == 0: a lane is wholly inside or outside)
-    const bool lane_in = X0 < g.ws;
-    const long plane = g.hp * g.wp;
-    const unsigned char *s_ring = smem_raw + kUpMaxRows * sizeof(double2) + warp * kRingBytes + lane * kLaneBytes;
-    const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(s_ring);
-
-    // cp.async ring of source rows: every lane copies, and later reads, only its own 4 pixels
-    const T *src_p = APPLY ? src + Y0 * g.ws + X0 : nullptr;               // next row to prefetch
-    long rows_left = Y1 - Y0;                                              // rows not yet prefetched
-    const long row_pitch = g.ws;
-    auto prefetch = [&](int stage) {
-        if (APPLY && lane_in) {
-            const uint32_t dst = ring_sa + stage * (kUpRb * kRowBytes);
-            if (rows_left >= kUpRb) {                       // (warp-uniform) a whole stage
-#pragma unroll
-                for (int rr = 0; rr < kUpRb; rr++) cp_async_lane<kLaneBytes>(dst + rr * kRowBytes, src_p + rr * row_pitch);
-            } else {
-#pragma unroll
-                for (int rr = 0; rr < kUpRb; rr++)
-                    if (rr < rows_left) cp_async_lane<kLaneBytes>(dst + rr * kRowBytes, src_p + rr * row_pitch);
-            }
-        }
-        src_p += kUpRb * row_pitch;
-        rows_left -= kUpRb;
-        cp_async_commit();
-    };
-    if (APPLY) {
-#pragma unroll
-        for (int st = 0; st < kUpStages - 1; st++) prefetch(st);
-    }
-
-    double q[PPT][NB][4];                                   // cubic in dy per pixel column and band
-    double q_ky = -1e300;
-    bool q_clean = false;
-    float *orow = out + Y0 * g.ws + X0;
-    int stage = 0;
-    for (long Yb = Y0; Yb < Y1; Yb += kUpRb) {
-        const int nrows = (int)min((long)kUpRb, Y1 - Yb);
-        if (APPLY) {
-            prefetch((stage + kUpStages - 1) % kUpStages);
-            cp_async_wait<kUpStages - 1>();
-        }
-        const unsigned char *ring_b = s_ring + stage * kUpRb * kRowBytes;
-        stage = (stage + 1) % kUpStages;
-#pragma unroll 1
-        for (int rr = 0; rr < nrows; rr++, orow += g.ws) {
-            const double2 ri = s_rows[Yb - Y0 + rr];
-            if (ri.y != q_ky) {                             // (warp-uniform) new tap rows: rebuild the cubics
-                q_ky = ri.y;
-                const long ky = (long)ri.y;
-                bool lane_clean = (ky - 1 >= 0) && (ky + 2 < g.hp);
-                double w5[PPT][5];
-                long col0 = 0;
-#pragma unroll
-                for (int k = 0; k < PPT; k++) {
-                    const double srcx = g.sx * ((double)(X0 + k) + 0.5) + g.ox;
-                    const double kxd = floor(srcx - 0.5);
-                    const long kx = (long)kxd;
-                    if (k == 0) col0 = kx - 1;
-                    const long sh = (kx - 1) - col0;        // this pixel's window starts 0 or 1 column into the lane's
-                    long cx = (long)floor(srcx + 1e-10);
-                    const long ct = cx - (kx - 1);          // tap column hosting the centre: 1 or 2 away from the edges
-                    lane_clean = lane_clean && (sh == 0 || sh == 1) && (ct == 1 || ct == 2) && (srcx >= 0.0);
-                    double wx[4];
-                    bspline_weights(srcx - 0.5 - kxd, wx);
-                    w5[k][0] = sh ? 0.0 : wx[0];
-                    w5[k][1] = sh ? wx[0] : wx[1];
-                    w5[k][2] = sh ? wx[1] : wx[2];
-                    w5[k][3] = sh ? wx[2] : wx[3];
-                    w5[k][4] = sh ? wx[3] : 0.0;
-                }
-                lane_clean = (lane_clean && (col0 >= 0) && (col0 + 4 < g.wp)) || !lane_in;
-                if (lane_clean && lane_in) {
-#pragma unroll
-                    for (int b = 0; b < NB; b++) {
-                        const float *p = coarse + b * plane + (ky - 1) * g.wp + col0;
-                        double r[PPT][4];
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            double t[5];
-#pragma unroll
-                            for (int i = 0; i < 5; i++) t[i] = (double)__ldg(p + j * g.wp + i);
-                            lane_clean = lane_clean && !isnan((t[0] + t[1]) + (t[2] + t[3]) + t[4]);
-#pragma unroll
-                            for (int k = 0; k < PPT; k++)   // x-interpolation of tap row j at pixel column k
-                                r[k][j] = fma(w5[k][4], t[4], fma(w5[k][3], t[3], fma(w5[k][2], t[2],
-                                          fma(w5[k][1], t[1], w5[k][0] * t[0]))));
-                        }
-#pragma unroll
-                        for (int k = 0; k < PPT; k++) {     // cubic B-spline through the 4 tap rows as a polynomial in dy
-                            q[k][b][0] = (r[k][0] + 4.0 * r[k][1] + r[k][2]) * (1.0 / 6.0);
-                            q[k][b][1] = (r[k][2] - r[k][0]) * 0.5;
-                            q[k][b][2] = (r[k][0] - 2.0 * r[k][1] + r[k][2]) * 0.5;
-                            q[k][b][3] = ((r[k][3] - r[k][0]) + 3.0 * (r[k][1] - r[k][2])) * (1.0 / 6.0);
-                        }
-                    }
-                }
-                q_clean = __all_sync(0xffffffffu, lane_clean);
-                if (!q_clean && lane == 0) list[atomicAdd(list_count, 1)] = make_int2((int)strip, (int)ky);
-            }
-            if (!q_clean || !lane_in) continue;
-            float s[PPT];
-            bool ok[PPT];
-            if constexpr (APPLY) {
-                Src4<T>::get(ring_b + rr * kRowBytes, nd, s, ok);
-            } else {
-#pragma unroll
-                for (int k = 0; k < PPT; k++) { s[k] = 0.f; ok[k] = true; }
-            }
-            const double dy = ri.x;
-            float res[NOUT][PPT];
-#pragma unroll
-            for (int k = 0; k < PPT; k++) {
-                const double gv = fma(fma(fma(q[k][0][3], dy, q[k][0][2]), dy, q[k][0][1]), dy, q[k][0][0]);
-                double ov = 0.0;
-                if (NB > 1) ov = fma(fma(fma(q[k][NB - 1][3], dy, q[k][NB - 1][2]), dy, q[k][NB - 1][1]), dy,
-                                     q[k][NB - 1][0]);
-                const float gf = ok[k] ? (float)gv : qnan;
-                const float of = ok[k] ? (float)ov : qnan;
-                if (APPLY) {
-                    res[0][k] = __fadd_rn(__fmul_rn(gf, s[k]), of);       // two roundings, as numpy (kernel_model.py:461)
-                } else {
-                    res[0][k] = gf;
-                    if constexpr (NOUT == 2) res[1][k] = of;
-                }
-            }
-            hb_stg_stream16(orow, make_float4(res[0][0], res[0][1], res[0][2], res[0][3]));
-            if constexpr (NOUT == 2)
-                hb_stg_stream16(orow + g.hs * g.ws, make_float4(res[1][0], res[1][1], res[1][2], res[1][3]));
-        }
-    }
-}
-
 template <typename T, int NB, bool APPLY>
 int launch_upsample(const void *src, NoData nd, const float *coarse, long hs, long ws, long hp, long wp, double sx,
                     double ox, double sy, double oy, const uint8_t *cover, float *out, cudaStream_t stream)
@@ -946,12 +664,10 @@ int launch_upsample(const void *src, NoData nd, const float *coarse, long hs, lo
     UpGeom g;
     g.hs = hs; g.ws = ws; g.hp = hp; g.wp = wp; g.sx = sx; g.ox = ox; g.sy = sy; g.oy = oy;
     g.ncols = (int)ceil((double)kUpWarpW * sx) + 5;
-    g.fast = (g.ncols <= 32) ? 1 : 0;                       // ratio >= ~4.8: the per-pixel-column cubics pay off
     // rows per CTA: a couple of coarse rows' worth, so that the per-cell-row work is amortised
     long rpc = (long)ceil(2.0 / sy);
     rpc = ((rpc + kUpRb - 1) / kUpRb) * kUpRb;
     if (rpc < 16) rpc = 16;
-    if (g.fast) rpc = kUpMaxRows;                           // fewer tap-row changes (cubic rebuilds) per CTA
     if (rpc > kUpMaxRows) rpc = kUpMaxRows;
     g.rows_per_cta = (int)rpc;
     const size_t ring = APPLY ? (size_t)kUpStages * kUpRb * 32 * kUpPpt * sizeof(T) : 0;
@@ -965,40 +681,25 @@ int launch_upsample(const void *src, NoData nd, const float *coarse, long hs, lo
                          (ws % 4 == 0) && (((uintptr_t)out) % 16 == 0);
     NoData ndk = nd;
     if (!ndk.int_ok) ndk.ivalue = -1;                       // integer sources: no pixel can equal it
-    // ---- fast path: aligned rasters, ratio >= ~5, no coverage mask; the general kernel then only fixes up the
-    //      (strip, cell row) segments the fast kernel flagged (nodata / raster edge neighbourhoods)
-    int2 *list = nullptr;
-    int *list_count = nullptr;
-    dim3 ggrid = grid;                                      // grid of the general kernel
-    if (g.fast && aligned && cover == nullptr) {
-        const long strips = (ws + kUpWarpW - 1) / kUpWarpW;
-        // a strip's rows span at most hs * sy + 3 distinct tap rows; (strip, tap row) pairs are appended at most once
-        const long max_seg = strips * ((long)ceil((double)hs * sy) + 4);
-        HB_REQUIRE(max_seg < 2147483000L, "up-sampling work list too large");
-        void *ws_list = nullptr;
-        HB_CUDA_OK(cudaMallocAsync(&ws_list, 16 + (size_t)max_seg * sizeof(int2), stream));
-        list_count = (int *)ws_list;
-        list = (int2 *)((char *)ws_list + 16);
-        HB_CUDA_OK(cudaMemsetAsync(list_count, 0, 16, stream));
-        const size_t fsmem = kUpMaxRows * sizeof(double2) + ring * kUpWarps;
-        auto fkern = upsample_fast_kernel<T, NB, APPLY>;
-        if (fsmem > 48 * 1024)
-            HB_CUDA_OK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-        fkern<<<grid, kThreads, fsmem, stream>>>((const T *)src, ndk, coarse, g, out, list, list_count);
-        HB_LAUNCH_OK("upsample_fast_kernel");
-        ggrid = dim3((unsigned)((max_seg + kUpWarps - 1) / kUpWarps), 1, 1);   // one warp per possible segment
+    // ---- fast path (upsample_poly.cu): aligned rasters, >= ~3.4 destination pixels per coarse pixel, no coverage mask
+    if (aligned && cover == nullptr) {
+        UpPolyGeom pg;
+        pg.hs = hs; pg.ws = ws; pg.hp = hp; pg.wp = wp; pg.sx = sx; pg.ox = ox; pg.sy = sy; pg.oy = oy;
+        if (hb_up_poly_eligible(pg)) {
+            if (APPLY) return hb_up_poly_apply(src, hb_dtype_code<T>(), ndk, coarse, pg, out, stream);
+            return hb_up_poly_resample(coarse, NB, pg, out, stream);
+        }
     }
 #define HB_UP_LAUNCH(AL_, MC_)                                                                                        \
     do {                                                                                                              \
         auto kern = upsample_kernel<T, NB, APPLY, AL_, MC_>;                                                          \
         if (smem > 48 * 1024)                                                                                         \
             HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-        kern<<<ggrid, kThreads, smem, stream>>>((const T *)src, ndk, coarse, g, cover, out, list, list_count);        \
+        kern<<<grid, kThreads, smem, stream>>>((const T *)src, ndk, coarse, g, cover, out);                          \
     } while (0)
     if (g.ncols <= 32) { if (aligned) HB_UP_LAUNCH(true, 1); else HB_UP_LAUNCH(false, 1); }
     else if (g.ncols <= 96) { if (aligned) HB_UP_LAUNCH(true, 3); else HB_UP_LAUNCH(false, 3); }
     else { if (aligned) HB_UP_LAUNCH(true, 5); else HB_UP_LAUNCH(false, 5); }
-    if (list_count != nullptr) HB_CUDA_OK(cudaFreeAsync(list_count, stream));
 #undef HB_UP_LAUNCH
     HB_LAUNCH_OK("upsample_kernel");
     return 0;

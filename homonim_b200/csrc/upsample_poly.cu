@@ -1,0 +1,631 @@
+// upsample_poly.cu -- the fast path of the cubic-spline up-sampler (sm_100a), used by hb_upsample_apply /
+// hb_resample_up when the destination is >= ~3.4x finer than the coarse (parameter) grid.
+//
+// Replaces, for RefSpaceModel.apply (reference kernel_model.py:484-503): the GDAL GRA_CubicSpline warp of the gain and
+// offset planes onto the source grid, the two float32 planes it writes, and numpy's gain*src + offset pass (:461).
+// GDAL's algorithm is restated in oracle/gdal_restate.c (gr_cubic_spline_up); this file evaluates the same
+// interpolant with a different arithmetic organisation:
+//
+//   * Inside one coarse cell the interpolated surface is a bicubic polynomial.  A lane owns 4 adjacent destination
+//     columns; whenever the tap rows change (once per `ratio` destination rows) it interpolates its 4 pixel COLUMNS
+//     through the 4 tap rows with the columns' x-weights and keeps the 4 results per pixel column and band in
+//     registers.  A destination row then costs 4 multiply-adds per pixel and band with the row's 4 y-weights (which
+//     are per-row scalars from a small per-CTA table).  This is GDAL's sum of 16 weighted taps, re-associated; all
+//     weights are positive, so there is no cancellation (a monomial-basis cubic in dy would save one operation but
+//     cancels catastrophically next to parameter spikes).
+//   * All of that is float32 arithmetic on PACKED pairs (FFMA2 / FADD2 / FMUL2: two adjacent pixels per
+//     instruction), because the kernel is instruction-issue bound, not memory bound, when evaluated in double
+//     (profiles/README.md, round 1).  B-spline weights are a convex combination, so float32 evaluation stays within a
+//     few 1e-7 relative of GDAL's double accumulation -- inside the 1e-4 contract of BASELINE.json (tests:
+//     test_upsample_apply, test_refspace_fuse_vs_oracle).  The geometry (tap indices, fractional offsets, weights)
+//     is computed in double.
+//   * A tiny pre-pass on the coarse grid classifies every cell: CLEAN (all 4x4 taps in range and valid in every
+//     band: the polynomial form is exact, GDAL does not renormalise), DEAD (no destination pixel of the cell can
+//     have a valid centre pixel: output is nodata) or DIRTY (anything else: taps dropped, weights renormalised).
+//     Lanes touching a DIRTY cell store nothing; the DIRTY cells are appended to a list and a small fix-up kernel
+//     re-does their destination pixels with GDAL's general rules in double, tap by tap.
+//   * Source pixels arrive through a per-warp cp.async ring (each lane copies, and later reads, only its own bytes:
+//     no barriers); one CTA barrier in total.
+#include <limits.h>
+
+#include "hb_common.cuh"
+#include "upsample_poly.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kPpt = 4;                    // destination pixels per lane
+constexpr int kWarpW = 32 * kPpt;          // destination columns per warp
+constexpr int kRb = 4;                     // rows per cp.async stage
+constexpr int kStages = 4;                 // stages in flight per warp
+constexpr int kMaxRows = 64;               // destination rows per CTA
+constexpr int kRowTableBytes = kMaxRows * (16 + 4);   // per-CTA row table: 4 float y-weights + tap row per row
+
+// ---- packed float32 pairs -------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long ua = *reinterpret_cast<unsigned long long *>(&a), ub = *reinterpret_cast<unsigned long long *>(&b),
+                       uc = *reinterpret_cast<unsigned long long *>(&c), ud;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ud) : "l"(ua), "l"(ub), "l"(uc));
+    return *reinterpret_cast<float2 *>(&ud);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b)
+{
+    unsigned long long ua = *reinterpret_cast<unsigned long long *>(&a), ub = *reinterpret_cast<unsigned long long *>(&b), ud;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
+    return *reinterpret_cast<float2 *>(&ud);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b)
+{
+    unsigned long long ua = *reinterpret_cast<unsigned long long *>(&a), ub = *reinterpret_cast<unsigned long long *>(&b), ud;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
+    return *reinterpret_cast<float2 *>(&ud);
+}
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+
+// ---- geometry shared by the fast kernel and the fix-up kernel (identical expressions => identical cell indices) -----
+__device__ __forceinline__ double up_src_coord(double scale, double off, long i) { return scale * ((double)i + 0.5) + off; }
+__device__ __forceinline__ long up_cell(double scale, double off, long i)
+{
+    return (long)floor(up_src_coord(scale, off, i) - 0.5);
+}
+
+// first destination index i in [0, n] with up_cell(i) >= k (up_cell is monotone in i)
+__device__ __forceinline__ long up_first_index(double scale, double off, long k, long n)
+{
+    long i = (long)floor(((double)k + 0.5 - off) / scale - 0.5) - 1;
+    i = min(max(i, 0L), n);
+    while (i < n && up_cell(scale, off, i) < k) i++;
+    return i;
+}
+
+__device__ __forceinline__ void bspline_weights(double d, double (&w)[4])   // taps -1, 0, 1, 2: B(tap - d)
+{
+    const double u = 1.0 - d, d2 = d * d, u2 = u * u;
+    w[0] = u2 * u * (1.0 / 6.0);
+    w[1] = (4.0 + d2 * (3.0 * d - 6.0)) * (1.0 / 6.0);
+    w[2] = (4.0 + u2 * (3.0 * u - 6.0)) * (1.0 / 6.0);
+    w[3] = d2 * d * (1.0 / 6.0);
+}
+
+// ---- cp.async (LDGSTS) ---------------------------------------------------------------------------------------------
+template <int BYTES> __device__ __forceinline__ void cp_async_lane(uint32_t smem_dst, const void *gmem_src)
+{
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_dst), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- 4 source pixels of storage type T -> two float32 pairs + validity ---------------------------------------------
+// Key: the nodata test, prepared once per thread (integer storage: the bit pattern of 2^23 + nodata, or a pattern no
+// pixel can produce when the nodata value is not representable in the storage type).
+template <typename T> struct SrcQuad;
+template <> struct SrcQuad<uint16_t> {
+    static constexpr int kBytes = 8;
+    typedef uint32_t Key;
+    static __device__ __forceinline__ Key key(const NoData &nd)
+    {
+        return (nd.ivalue >= 0 && nd.ivalue <= 65535) ? (0x4B000000u | (uint32_t)nd.ivalue) : 0xFFFFFFFFu;
+    }
+    static __device__ __forceinline__ void get(const void *p, const Key magic, float2 (&s)[2], bool (&ok)[4])
+    {
+        const uint2 w = *reinterpret_cast<const uint2 *>(p);
+        // 2^23 + v has v in its mantissa: one byte-permute per pixel and one packed subtract per pair (exact)
+        const float2 m0 = make_float2(__uint_as_float(__byte_perm(w.x, 0x4B000000u, 0x7410)),
+                                      __uint_as_float(__byte_perm(w.x, 0x4B000000u, 0x7432)));
+        const float2 m1 = make_float2(__uint_as_float(__byte_perm(w.y, 0x4B000000u, 0x7410)),
+                                      __uint_as_float(__byte_perm(w.y, 0x4B000000u, 0x7432)));
+        s[0] = fadd2(m0, splat(-8388608.0f));
+        s[1] = fadd2(m1, splat(-8388608.0f));
+        ok[0] = __float_as_uint(m0.x) != magic;
+        ok[1] = __float_as_uint(m0.y) != magic;
+        ok[2] = __float_as_uint(m1.x) != magic;
+        ok[3] = __float_as_uint(m1.y) != magic;
+    }
+};
+template <> struct SrcQuad<uint8_t> {
+    static constexpr int kBytes = 4;
+    typedef uint32_t Key;
+    static __device__ __forceinline__ Key key(const NoData &nd)
+    {
+        return (nd.ivalue >= 0 && nd.ivalue <= 255) ? (0x4B000000u | (uint32_t)nd.ivalue) : 0xFFFFFFFFu;
+    }
+    static __device__ __forceinline__ void get(const void *p, const Key magic, float2 (&s)[2], bool (&ok)[4])
+    {
+        const uint32_t w = *reinterpret_cast<const uint32_t *>(p);
+        const float2 m0 = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440)),
+                                      __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441)));
+        const float2 m1 = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7442)),
+                                      __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7443)));
+        s[0] = fadd2(m0, splat(-8388608.0f));
+        s[1] = fadd2(m1, splat(-8388608.0f));
+        ok[0] = __float_as_uint(m0.x) != magic;
+        ok[1] = __float_as_uint(m0.y) != magic;
+        ok[2] = __float_as_uint(m1.x) != magic;
+        ok[3] = __float_as_uint(m1.y) != magic;
+    }
+};
+template <> struct SrcQuad<float> {
+    static constexpr int kBytes = 16;
+    typedef NoData Key;
+    static __device__ __forceinline__ Key key(const NoData &nd) { return nd; }
+    static __device__ __forceinline__ void get(const void *p, const Key &nd, float2 (&s)[2], bool (&ok)[4])
+    {
+        const float4 w = *reinterpret_cast<const float4 *>(p);
+        s[0] = make_float2(w.x, w.y);
+        s[1] = make_float2(w.z, w.w);
+        ok[0] = hb_valid(w.x, nd); ok[1] = hb_valid(w.y, nd); ok[2] = hb_valid(w.z, nd); ok[3] = hb_valid(w.w, nd);
+    }
+};
+
+// =====================================================================================================================
+// pre-pass: classify the coarse cells, interleave the two bands, list the DIRTY cells
+// =====================================================================================================================
+// Cell (ky, kx), ky in [-1, hp], kx in [-1, wp]: the destination pixels whose first tap is (ky - 1, kx - 1).
+// flags[(ky + 1) * (wp + 2) + (kx + 1)]: bit0 CLEAN, bit1 DEAD.
+// GUARD (apply mode): a cell is only CLEAN if the gain band's taps are within a factor 16 of each other.  Next to a
+// parameter spike (an ill-conditioned solve of the reference) corr = gain*src + offset cancels heavily
+// and float32 interpolation errors would be amplified past 1e-4; such cells take the double-precision fix-up instead.
+template <int NB, bool GUARD>
+__global__ void upsample_prep_kernel(const float *__restrict__ coarse, long hp, long wp, float2 *__restrict__ coarse2,
+                                     uint8_t *__restrict__ flags, int *__restrict__ list, int *__restrict__ count)
+{
+    const long fw = wp + 2, n = (hp + 2) * fw, plane = hp * wp;
+    const long n_round = (n + 31) / 32 * 32;                // whole warps stay in the loop (for the ballot below)
+    for (long idx0 = (long)blockIdx.x * blockDim.x + threadIdx.x; idx0 < n_round; idx0 += (long)gridDim.x * blockDim.x) {
+        const bool live = idx0 < n;
+        const long idx = live ? idx0 : n - 1;
+        const long ky = idx / fw - 1, kx = idx % fw - 1;
+        // validity bits of the 4x4 tap window: bit (j*4+i) of `all` = valid in every band, of `any` = valid in some band
+        unsigned all = 0, any = 0;
+        float gmin = 3.0e38f, gmax = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const long y = ky - 1 + j, x = kx - 1 + i;
+                if (y >= 0 && y < hp && x >= 0 && x < wp) {
+                    const float g0 = __ldg(coarse + y * wp + x);
+                    const bool v0 = !isnan(g0);
+                    const bool v1 = (NB > 1) ? !isnan(__ldg(coarse + plane + y * wp + x)) : v0;
+                    if (v0 && v1) all |= 1u << (j * 4 + i);
+                    if (v0 || v1) any |= 1u << (j * 4 + i);
+                    if (GUARD && v0) { gmin = fminf(gmin, fabsf(g0)); gmax = fmaxf(gmax, fabsf(g0)); }
+                }
+            }
+        }
+        const bool clean = (all == 0xFFFFu) && (!GUARD || gmax <= 16.0f * gmin);
+        // centre-pixel candidates of the cell's destination pixels: rows {ky, ky+1} (+ ky-1 when ky == hp, GDAL's
+        // "cy == hs -> cy--" rule), same for the columns; window bit (j, i) is row ky-1+j, column kx-1+i
+        unsigned rows_m = 0x6u, cols_m = 0x6u;                  // j (i) in {1, 2}
+        if (ky == hp) rows_m |= 0x1u;
+        if (kx == wp) cols_m |= 0x1u;
+        unsigned cand = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if ((rows_m >> j) & 1u) cand |= (cols_m & 0xFu) << (j * 4);
+        const bool dead = (any & cand) == 0;
+        if (live) flags[idx] = (uint8_t)((clean ? 1 : 0) | (dead ? 2 : 0));
+        // append the DIRTY cells: one atomic per warp
+        const bool dirty = live && !clean && !dead;
+        const unsigned vote = __ballot_sync(0xffffffffu, dirty);
+        if (vote) {
+            const int lane = threadIdx.x & 31, leader = __ffs(vote) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(count, __popc(vote));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (dirty) list[base + __popc(vote & ((1u << lane) - 1u))] = (int)idx;
+        }
+        if (NB == 2 && live && ky >= 0 && ky < hp && kx >= 0 && kx < wp)
+            coarse2[ky * wp + kx] = make_float2(__ldg(coarse + ky * wp + kx), __ldg(coarse + plane + ky * wp + kx));
+    }
+}
+
+// =====================================================================================================================
+// fast kernel
+// =====================================================================================================================
+struct __align__(16) RowEntry { float wy[4]; };            // the row's B-spline y-weights (taps ky-1 .. ky+2)
+
+// T: storage type of the source plane (APPLY); NB: coarse bands; APPLY: fuse corr = gain*src + offset.
+// coarse: NB == 2: interleaved (gain, offset) float2 [hp][wp]; NB == 1: the float plane.
+template <typename T, int NB, bool APPLY>
+__global__ void __launch_bounds__(kThreads, 3)
+upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restrict__ coarse_v,
+                     const uint8_t *__restrict__ flags, UpPolyGeom g, float *__restrict__ out)
+{
+    constexpr int NOUT = (NB == 2 && !APPLY) ? 2 : 1;
+    constexpr int kLaneBytes = APPLY ? SrcQuad<T>::kBytes : 0;
+    constexpr int kRowBytes = 32 * kLaneBytes;
+    constexpr int kRingBytes = kStages * kRb * kRowBytes;
+    constexpr int kWBytes = 5 * 32 * (int)sizeof(float4);                  // x-weights of one warp
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long Y0 = (long)blockIdx.y * kMaxRows;
+    const long Y1 = min(Y0 + (long)kMaxRows, g.hs);
+    const float qnan = __int_as_float(0x7fc00000);
+
+    // per-CTA row table: y-weights and first tap row (+1) of the CTA's destination rows
+    RowEntry *s_rows = reinterpret_cast<RowEntry *>(smem_raw);
+    int *s_ky = reinterpret_cast<int *>(smem_raw + kMaxRows * sizeof(RowEntry));
+    if ((long)threadIdx.x < Y1 - Y0) {
+        const double srcy = up_src_coord(g.sy, g.oy, Y0 + threadIdx.x);
+        const double ky = floor(srcy - 0.5);
+        double wy[4];
+        bspline_weights(srcy - 0.5 - ky, wy);
+        RowEntry e;
+#pragma unroll
+        for (int j = 0; j < 4; j++) e.wy[j] = (float)wy[j];
+        s_rows[threadIdx.x] = e;
+        s_ky[threadIdx.x] = (int)ky;
+    }
+    __syncthreads();                                        // the only CTA barrier
+
+    const long strip = (long)blockIdx.x * kWarps + warp;
+    const long Xw0 = strip * kWarpW;
+    if (Xw0 >= g.ws) return;
+    const long X0 = Xw0 + (long)lane * kPpt;                // (ws % 4 == 0: a lane is wholly inside or outside)
+    const bool lane_in = X0 < g.ws;
+    unsigned char *warp_base = smem_raw + kRowTableBytes + warp * (kWBytes + kRingBytes);
+    float4 *s_w = reinterpret_cast<float4 *>(warp_base) + lane;            // s_w[i * 32]: tap i of the lane's 4 pixels
+    const unsigned char *s_ring = warp_base + kWBytes + lane * kLaneBytes;
+    const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(s_ring);
+
+    // ---- cp.async ring of source rows ---------------------------------------------------------------------------------
+    const T *src_p = APPLY ? src + Y0 * g.ws + X0 : nullptr;               // next row to prefetch
+    long rows_left = Y1 - Y0;
+    const long row_pitch = g.ws;
+    auto prefetch = [&](int stage) {
+        if (APPLY && lane_in) {
+            const uint32_t dst = ring_sa + stage * (kRb * kRowBytes);
+            if (rows_left >= kRb) {
+#pragma unroll
+                for (int rr = 0; rr < kRb; rr++) cp_async_lane<kLaneBytes>(dst + rr * kRowBytes, src_p + rr * row_pitch);
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < kRb; rr++)
+                    if (rr < rows_left) cp_async_lane<kLaneBytes>(dst + rr * kRowBytes, src_p + rr * row_pitch);
+            }
+        }
+        src_p += kRb * row_pitch;
+        rows_left -= kRb;
+        cp_async_commit();
+    };
+    if (APPLY) {
+#pragma unroll
+        for (int st = 0; st < kStages - 1; st++) prefetch(st);
+    }
+
+    // ---- row-invariant lane geometry (double), x-weights over the lane's 5-column tap window -> shared memory ----------
+    long col0 = 0;                                          // first tap column of the lane's window
+    int cellA = 0, cellB = 0;                               // flag columns (kx + 1) of the lane's first / last pixel
+    bool geom_ok = lane_in;
+    {
+        float w5[kPpt][5];
+        long kx0 = 0;
+#pragma unroll
+        for (int k = 0; k < kPpt; k++) {
+            const double srcx = up_src_coord(g.sx, g.ox, X0 + k);
+            const double kxd = floor(srcx - 0.5);
+            const long kx = (long)kxd;
+            if (k == 0) kx0 = kx;
+            const long sh = kx - kx0;                       // the pixel's window starts 0 or 1 column into the lane's
+            geom_ok = geom_ok && (sh == 0 || sh == 1);
+            if (k == kPpt - 1) cellB = (int)min(max(kx + 1, -1L), g.wp + 2);
+            double wx[4];
+            bspline_weights(srcx - 0.5 - kxd, wx);
+            w5[k][0] = sh ? 0.f : (float)wx[0];
+            w5[k][1] = (float)(sh ? wx[0] : wx[1]);
+            w5[k][2] = (float)(sh ? wx[1] : wx[2]);
+            w5[k][3] = (float)(sh ? wx[2] : wx[3]);
+            w5[k][4] = sh ? (float)wx[3] : 0.f;
+        }
+        col0 = kx0 - 1;
+        cellA = (int)min(max(kx0 + 1, -1L), g.wp + 2);
+#pragma unroll
+        for (int i = 0; i < 5; i++) s_w[i * 32] = make_float4(w5[0][i], w5[1][i], w5[2][i], w5[3][i]);
+    }
+    const int fw = (int)g.wp + 2;
+    // cells outside the flag table hold no pixel with an in-range centre: DEAD
+    auto cell_flags = [&](int ky, int cell) -> unsigned {
+        if (ky < -1 || ky > g.hp || cell < 0 || cell >= fw) return 2u;
+        return flags[(long)(ky + 1) * fw + cell];
+    };
+
+    const typename SrcQuad<T>::Key nd_key = SrcQuad<T>::key(nd);
+    float2 q[2][NB][4];                                     // x-interpolated tap rows per pixel PAIR and band
+    int q_ky = INT_MIN;
+    // 0: CLEAN (polynomial), 1: SKIP (DIRTY: left to the fix-up kernel; or a lane beyond the raster), 2: DEAD (nodata)
+    int state = 1;
+    float *orow = out + Y0 * g.ws + X0;
+    int stage = 0;
+    for (long Yb = Y0; Yb < Y1; Yb += kRb) {
+        const int nrows = (int)min((long)kRb, Y1 - Yb);
+        if (APPLY) {
+            prefetch((stage + kStages - 1) % kStages);
+            cp_async_wait<kStages - 1>();
+        }
+        const unsigned char *ring_b = s_ring + stage * kRb * kRowBytes;
+        stage = (stage + 1) % kStages;
+#pragma unroll 1
+        for (int rr = 0; rr < nrows; rr++, orow += g.ws) {
+            const int ky = s_ky[Yb - Y0 + rr];
+            if (ky != q_ky) {                               // (warp-uniform) new tap rows: re-classify, re-interpolate
+                q_ky = ky;
+                const unsigned fa = cell_flags(ky, cellA), fb = cell_flags(ky, cellB);
+                state = !lane_in ? 1 : (((fa & fb & 1u) && geom_ok) ? 0 : (((fa & fb & 2u) || !geom_ok) ? 2 : 1));
+                if (state == 0) {
+                    const bool five = (cellB != cellA);     // some pixel's window starts one column in: 5th column is used
+                    float2 wp01[5], wp23[5];
+#pragma unroll
+                    for (int i = 0; i < 5; i++) {
+                        const float4 w = s_w[i * 32];
+                        wp01[i] = make_float2(w.x, w.y);
+                        wp23[i] = make_float2(w.z, w.w);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        float t[NB][5];
+                        if (NB == 2) {
+                            const float2 *p = reinterpret_cast<const float2 *>(coarse_v) + (long)(ky - 1 + j) * g.wp + col0;
+#pragma unroll
+                            for (int i = 0; i < 5; i++) {
+                                // (the 5th column has weight 0 when unused, but may be out of range or NaN: skip it)
+                                const float2 v = (i < 4 || five) ? __ldg(p + i) : make_float2(0.f, 0.f);
+                                t[0][i] = v.x;
+                                t[NB - 1][i] = v.y;
+                            }
+                        } else {
+                            const float *p = reinterpret_cast<const float *>(coarse_v) + (long)(ky - 1 + j) * g.wp + col0;
+#pragma unroll
+                            for (int i = 0; i < 5; i++) t[0][i] = (i < 4 || five) ? __ldg(p + i) : 0.f;
+                        }
+#pragma unroll
+                        for (int b = 0; b < NB; b++) {      // x-interpolation of tap row j at the lane's 4 pixel columns
+                            float2 r0 = fmul2(wp01[0], splat(t[b][0])), r1 = fmul2(wp23[0], splat(t[b][0]));
+#pragma unroll
+                            for (int i = 1; i < 5; i++) {
+                                r0 = ffma2(wp01[i], splat(t[b][i]), r0);
+                                r1 = ffma2(wp23[i], splat(t[b][i]), r1);
+                            }
+                            q[0][b][j] = r0;
+                            q[1][b][j] = r1;
+                        }
+                    }
+                }
+            }
+            if (state == 1) continue;                       // DIRTY lanes are written by the fix-up kernel
+            float4 res[NOUT];
+            if (state == 0) {
+                const RowEntry ri = s_rows[Yb - Y0 + rr];
+                const float2 w0 = splat(ri.wy[0]), w1 = splat(ri.wy[1]), w2 = splat(ri.wy[2]), w3 = splat(ri.wy[3]);
+                float2 gv[2], ov[2];
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    gv[p] = ffma2(q[p][0][3], w3, ffma2(q[p][0][2], w2, ffma2(q[p][0][1], w1, fmul2(q[p][0][0], w0))));
+                    if (NB > 1)
+                        ov[p] = ffma2(q[p][NB - 1][3], w3, ffma2(q[p][NB - 1][2], w2, ffma2(q[p][NB - 1][1], w1,
+                                      fmul2(q[p][NB - 1][0], w0))));
+                    else
+                        ov[p] = splat(0.f);
+                }
+                if constexpr (APPLY) {
+                    float2 s[2];
+                    bool ok[4];
+                    SrcQuad<T>::get(ring_b + rr * kRowBytes, nd_key, s, ok);
+                    const float2 c0 = ffma2(gv[0], s[0], ov[0]), c1 = ffma2(gv[1], s[1], ov[1]);   // corr = gain*src + offset
+                    res[0] = make_float4(ok[0] ? c0.x : qnan, ok[1] ? c0.y : qnan, ok[2] ? c1.x : qnan,
+                                         ok[3] ? c1.y : qnan);
+                } else {
+                    res[0] = make_float4(gv[0].x, gv[0].y, gv[1].x, gv[1].y);
+                    if constexpr (NOUT == 2) res[1] = make_float4(ov[0].x, ov[0].y, ov[1].x, ov[1].y);
+                }
+            } else {
+                res[0] = make_float4(qnan, qnan, qnan, qnan);
+                if constexpr (NOUT == 2) res[1] = res[0];
+            }
+            hb_stg_stream16(orow, res[0]);
+            if constexpr (NOUT == 2) hb_stg_stream16(orow + g.hs * g.ws, res[1]);
+        }
+    }
+}
+
+// =====================================================================================================================
+// fix-up kernel: the destination pixels of the DIRTY cells, GDAL's general rules, double arithmetic, tap by tap
+// =====================================================================================================================
+// (gr_cubic_spline_up in oracle/gdal_restate.c: centre pixel in range and valid in some band; out-of-range / invalid
+// taps dropped; pixel dropped if sum(w) < 1e-6; renormalised unless sum(w) is within 1e-5 of 1.)
+constexpr int kFixThreads = 128;
+
+// One warp per DIRTY cell (grid-stride over the list), one lane per destination pixel COLUMN of the 4-pixel groups that
+// touch the cell.  A lane first combines its column's 4x4 taps along x -- values A[j] = sum_i wx[i] v[j][i] over the
+// usable taps, and their weights M[j] = sum_i wx[i] -- and then walks down the cell's rows: acc = sum_j wy[j] A[j],
+// acc_w = sum_j wy[j] M[j], which is GDAL's double sum over the usable taps, re-associated.
+template <typename T, int NB, bool APPLY>
+__global__ void __launch_bounds__(kFixThreads, 4)
+upsample_fixup_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ coarse, UpPolyGeom g,
+                      float *__restrict__ out, const int *__restrict__ list, const int *__restrict__ count)
+{
+    constexpr int NOUT = (NB == 2 && !APPLY) ? 2 : 1;
+    constexpr int kFixWarps = kFixThreads / 32;
+    const int lane = threadIdx.x & 31;
+    const long warp_id = (long)blockIdx.x * kFixWarps + (threadIdx.x >> 5);
+    const long n_warps = (long)gridDim.x * kFixWarps;
+    const long fw = g.wp + 2, plane = g.hp * g.wp;
+    const float qnan = __int_as_float(0x7fc00000);
+    const int n = *count;
+    for (long e = warp_id; e < n; e += n_warps) {
+        const long idx = list[e];
+        const long ky = idx / fw - 1, kx = idx % fw - 1;
+        // destination rows / columns of the cell: the i with up_cell(i) == k (monotone in i)
+        const long ya = up_first_index(g.sy, g.oy, ky, g.hs), yb = up_first_index(g.sy, g.oy, ky + 1, g.hs);
+        const long xa = up_first_index(g.sx, g.ox, kx, g.ws), xb = up_first_index(g.sx, g.ox, kx + 1, g.ws);
+        if (yb <= ya || xb <= xa) continue;
+        // every 4-pixel group (= lane of the fast kernel) that touches the cell was skipped there: do whole groups
+        const long ga = (xa / kPpt) * kPpt, gb = min(((xb - 1) / kPpt + 1) * kPpt, g.ws);
+        for (long X = ga + lane; X < gb; X += 32) {
+            const double srcx = up_src_coord(g.sx, g.ox, X);
+            long cx = (long)floor(srcx + 1e-10);
+            if (cx == g.wp) cx--;
+            const bool cx_ok = (srcx >= 0.0) && cx >= 0 && cx < g.wp;
+            const long kxx = (long)floor(srcx - 0.5);
+            double wx[4];
+            bspline_weights(srcx - 0.5 - (double)kxx, wx);
+            // x-combination of the 4 tap rows ky-1 .. ky+2 (every row of the cell has the same tap rows)
+            double A[NB][4], M[NB][4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const long y = ky - 1 + j;
+                float v[NB][4];
+                bool in[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const long x = kxx - 1 + i;
+                    in[i] = y >= 0 && y < g.hp && x >= 0 && x < g.wp;
+                    const long a = min(max(y, 0L), g.hp - 1) * g.wp + min(max(x, 0L), g.wp - 1);
+#pragma unroll
+                    for (int b = 0; b < NB; b++) v[b][i] = __ldg(coarse + b * plane + a);
+                }
+#pragma unroll
+                for (int b = 0; b < NB; b++) {
+                    double a = 0.0, m = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const bool ok = in[i] && !isnan(v[b][i]);
+                        a = fma(ok ? (double)v[b][i] : 0.0, ok ? wx[i] : 0.0, a);   // dropped taps add exact zeros
+                        m += ok ? wx[i] : 0.0;
+                    }
+                    A[b][j] = a;
+                    M[b][j] = m;
+                }
+            }
+            // validity (in some band) of the centre-pixel candidates: coarse rows ky-1, ky, ky+1 at column cx
+            bool cen[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const long y = ky - 1 + j;
+                bool any = false;
+                if (cx_ok && y >= 0 && y < g.hp) {
+                    any = !isnan(__ldg(coarse + y * g.wp + cx));
+                    if (NB > 1) any = any || !isnan(__ldg(coarse + plane + y * g.wp + cx));
+                }
+                cen[j] = any;
+            }
+            constexpr int kBatch = 8;                        // source pixels of 8 rows in flight per lane
+            for (long Yc = ya; Yc < yb; Yc += kBatch) {
+                float sv[kBatch];
+#pragma unroll
+                for (int u = 0; u < kBatch; u++)
+                    sv[u] = (APPLY && Yc + u < yb) ? hb_to_f32<T>(src[(Yc + u) * g.ws + X]) : 0.f;
+#pragma unroll
+                for (int u = 0; u < kBatch; u++) {
+                    const long Y = Yc + u;
+                    if (Y >= yb) break;
+                    const double srcy = up_src_coord(g.sy, g.oy, Y);
+                    long cy = (long)floor(srcy + 1e-10);
+                    if (cy == g.hp) cy--;
+                    const long jc = cy - (ky - 1);           // 0 .. 2
+                    bool c_ok = (srcy >= 0.0) && (jc == 0 ? cen[0] : (jc == 1 ? cen[1] : (jc == 2 ? cen[2] : false)));
+                    const float s = sv[u];
+                    if (APPLY) c_ok = c_ok && hb_valid(s, nd);
+                    float r[2] = {qnan, qnan};
+                    if (c_ok) {
+                        double wy[4];
+                        bspline_weights(srcy - 0.5 - (double)ky, wy);
+#pragma unroll
+                        for (int b = 0; b < NB; b++) {
+                            double acc = 0.0, acc_w = 0.0;
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                acc = fma(wy[j], A[b][j], acc);
+                                acc_w = fma(wy[j], M[b][j], acc_w);
+                            }
+                            if (acc_w < 0.000001) continue;
+                            if (acc_w < 0.99999 || acc_w > 1.00001) acc /= acc_w;
+                            r[b] = (float)acc;
+                        }
+                    }
+                    if (APPLY) {
+                        out[Y * g.ws + X] = fmaf(r[0], s, r[NB - 1]);
+                    } else {
+                        out[Y * g.ws + X] = r[0];
+                        if constexpr (NOUT == 2) out[g.hs * g.ws + Y * g.ws + X] = r[1];
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <typename T, int NB, bool APPLY>
+int launch_poly(const void *src, NoData nd, const float *coarse, const UpPolyGeom &g, float *out, cudaStream_t stream)
+{
+    const long fw = g.wp + 2, ncell = (g.hp + 2) * fw;
+    HB_REQUIRE(ncell < 2147483000L, "up-sampling: coarse raster too large");
+    // workspace: [count (16 B)] [list: ncell ints] [flags: ncell bytes] [interleaved bands: hp*wp float2 (NB == 2)]
+    const size_t off_list = 16, off_flags = off_list + (((size_t)ncell * 4 + 15) / 16) * 16;
+    const size_t off_c2 = off_flags + (((size_t)ncell + 15) / 16) * 16;
+    const size_t total = off_c2 + (NB == 2 ? (size_t)g.hp * g.wp * sizeof(float2) : 0);
+    char *wsb = nullptr;
+    HB_CUDA_OK(cudaMallocAsync((void **)&wsb, total, stream));
+    int *count = (int *)wsb, *list = (int *)(wsb + off_list);
+    uint8_t *flags = (uint8_t *)(wsb + off_flags);
+    float2 *coarse2 = (float2 *)(wsb + off_c2);
+    HB_CUDA_OK(cudaMemsetAsync(count, 0, 16, stream));
+    {
+        long blocks = (ncell + 255) / 256;
+        const long cap = (long)hb_sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        upsample_prep_kernel<NB, APPLY><<<(unsigned)blocks, 256, 0, stream>>>(coarse, g.hp, g.wp, coarse2, flags, list,
+                                                                             count);
+        HB_LAUNCH_OK("upsample_prep_kernel");
+    }
+    {
+        const size_t ring = APPLY ? (size_t)kStages * kRb * 32 * kPpt * sizeof(T) : 0;
+        const size_t smem = kRowTableBytes + (5 * 32 * sizeof(float4) + ring) * kWarps;
+        const long cta_w = (long)kWarpW * kWarps;
+        dim3 grid((unsigned)((g.ws + cta_w - 1) / cta_w), (unsigned)((g.hs + kMaxRows - 1) / kMaxRows));
+        HB_REQUIRE(grid.y <= 65535u, "up-sampling destination has too many rows (%ld)", g.hs);
+        auto kern = upsample_poly_kernel<T, NB, APPLY>;
+        if (smem > 48 * 1024)
+            HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kThreads, smem, stream>>>((const T *)src, nd, NB == 2 ? (const void *)coarse2 : (const void *)coarse,
+                                               flags, g, out);
+        HB_LAUNCH_OK("upsample_poly_kernel");
+    }
+    {
+        const unsigned blocks = (unsigned)hb_sm_count() * 16;
+        upsample_fixup_kernel<T, NB, APPLY><<<blocks, kFixThreads, 0, stream>>>((const T *)src, nd, coarse, g, out, list,
+                                                                               count);
+        HB_LAUNCH_OK("upsample_fixup_kernel");
+    }
+    HB_CUDA_OK(cudaFreeAsync(wsb, stream));
+    return 0;
+}
+
+}  // namespace
+
+bool hb_up_poly_eligible(const UpPolyGeom &g)
+{
+    // a lane's 4 pixels must span at most 2 coarse cells: 3 * sx < 1 (with margin); the row direction only needs sy <= 1
+    return g.sx <= 0.3 && g.sy <= 1.0 + 1e-9 && (g.ws % kPpt == 0);
+}
+
+int hb_up_poly_apply(const void *src, int src_dtype, NoData nd, const float *params, const UpPolyGeom &g, float *out,
+                     cudaStream_t stream)
+{
+    switch (src_dtype) {
+        case HB_U8: return launch_poly<uint8_t, 2, true>(src, nd, params, g, out, stream);
+        case HB_U16: return launch_poly<uint16_t, 2, true>(src, nd, params, g, out, stream);
+        case HB_F32: return launch_poly<float, 2, true>(src, nd, params, g, out, stream);
+    }
+    HB_REQUIRE(false, "hb_up_poly_apply: unknown dtype %d", src_dtype);
+}
+
+int hb_up_poly_resample(const float *coarse, int nb, const UpPolyGeom &g, float *out, cudaStream_t stream)
+{
+    NoData none = hb_make_nodata(0, 0.0);
+    if (nb == 1) return launch_poly<float, 1, false>(nullptr, none, coarse, g, out, stream);
+    return launch_poly<float, 2, false>(nullptr, none, coarse, g, out, stream);
+}

@@ -243,12 +243,14 @@ def test_full_size_refspace_properties():
     assert bool((gain[cnt > 0] == 2).all()) and bool((param_ra.array[1][cnt > 0] == 0).all())
     corr = km.apply(src_ra, param_ra).array
     assert torch.equal(torch.isnan(corr), src == 0)
-    # away from the nodata block and from the raster edge every spline tap is present and equal: exactly 2 * src
-    # (within 2 coarse pixels of an edge GDAL drops the out-of-range taps and, when their weight is < 1e-5, does not
-    # renormalise -- the corrected value is then 2 * src * (1 - O(1e-6)), which the oracle tests cover)
+    # away from the nodata block and from the raster edge every spline tap is present and equal: 2 * src up to the
+    # float32 rounding of the spline weights (their sum is 1 to a few 1e-7; GDAL's double sum is then rounded to
+    # float32 as well) -- two orders of magnitude inside the 1e-4 contract.  (Within 2 coarse pixels of an edge GDAL
+    # drops the out-of-range taps and, when their weight is < 1e-5, does not renormalise: 2 * src * (1 - O(1e-6)).)
     interior = torch.zeros_like(src, dtype=torch.bool)
     interior[900:-60, 1400:-60] = src[900:-60, 1400:-60] != 0
-    assert torch.equal(corr[interior], 2 * src.to(torch.int32)[interior].to(torch.float32))
+    expect = 2 * src.to(torch.int32)[interior].to(torch.float32)
+    assert float(((corr[interior] - expect).abs() / expect).max()) <= 1e-6
 
 
 def test_full_size_same_grid_properties():
