@@ -38,7 +38,11 @@ struct DevBuf {
     void *p = nullptr;
     cudaStream_t st;
     explicit DevBuf(cudaStream_t s) : st(s) {}
-    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 16, st); }
+    cudaError_t alloc(size_t bytes)
+    {
+        const cudaError_t err = hb_pool_keep_memory();
+        return err != cudaSuccess ? err : cudaMallocAsync(&p, bytes ? bytes : 16, st);
+    }
     ~DevBuf() { if (p) cudaFreeAsync(p, st); }
 };
 }  // namespace

@@ -112,6 +112,23 @@ __device__ __forceinline__ void hb_stg_stream16(void *p, float4 v)
                  : "memory");
 }
 
+// Stream-ordered scratch (cudaMallocAsync) comes from the device's default memory pool.  By default the pool hands
+// freed memory back to the OS at every synchronisation, so that each call would pay for a fresh allocation; keep it.
+static inline cudaError_t hb_pool_keep_memory()
+{
+    static thread_local int done_for = -1;
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess || dev == done_for) return err;
+    cudaMemPool_t pool;
+    err = cudaDeviceGetDefaultMemPool(&pool, dev);
+    if (err != cudaSuccess) return err;
+    unsigned long long keep = ~0ull;
+    err = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (err == cudaSuccess) done_for = dev;
+    return err;
+}
+
 static inline int hb_sm_count()
 {
     static int sms = 0;

@@ -166,8 +166,46 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
         if ((e >= 0) && (e < g.h)) load_row(e, a, b);
         if (!single_row && (l >= e_first) && (l >= 0) && (l < g.h)) load_row(l, c, d);
     };
-    fetch(e_first, se, re, sl, rl);
-    for (long e = e_first; e <= e_last; e++) {
+    // ---- warm-up: the rows above the first output row's centre only ENTER the window (nothing leaves, no output row is
+    //      completed).  Fetch them 4 at a time -- all loads in flight together -- and accumulate in row order (the same
+    //      additions, in the same order, as the row-by-row steps below would perform).
+    long e_begin = e_first;
+    if (!single_row) {
+        const long e_warm_end = y0 + hh;                             // first step that completes an output row
+        for (; e_begin < e_warm_end; e_begin += 4) {
+            float ws[4][C], wr[4][C];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const long e = e_begin + u;
+#pragma unroll
+                for (int i = 0; i < C; i++) { ws[u][i] = 0.f; wr[u][i] = 0.f; }
+                if (e < e_warm_end && e >= 0 && e < g.h) load_row(e, ws[u], wr[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const long e = e_begin + u;
+                if (e >= e_warm_end) break;
+                const bool has_e = (e >= 0) && (e < g.h);
+#pragma unroll
+                for (int i = 0; i < C; i++) {
+                    bool ve = false;
+                    if (has_e) {
+                        double q[NQ]; int cnt;
+                        ve = col_in[i] && valid2(ws[u][i], wr[u][i]);
+                        pixel_terms<NQ, NORM>(ws[u][i], wr[u][i], ve, n0, n1, q, cnt);
+                        ve = cnt != 0;
+#pragma unroll
+                        for (int k = 0; k < NQ; k++) V[i][k] = __dadd_rn(V[i][k], q[k]);
+                        VN[i] += cnt;
+                    }
+                    vring[i] = (vring[i] << 1) | (ve ? 1ull : 0ull);
+                }
+            }
+        }
+        e_begin = e_warm_end;
+    }
+    fetch(e_begin, se, re, sl, rl);
+    for (long e = e_begin; e <= e_last; e++) {
         // ---- vertical running sums: entering row e, leaving row e - kh ---------------------------------------------
         const long l = e - g.kh;
         const bool has_e = (e >= 0) && (e < g.h);
@@ -406,7 +444,8 @@ int launch_fit(const float *src, NoData nd_s, const float *ref, NoData nd_r, lon
     const long target_ctas = (long)hb_sm_count() * 8;
     long bands = (target_ctas + xtiles - 1) / xtiles;
     long rpb = (h + bands - 1) / bands;
-    const long min_rpb = (C == 1) ? 2L * kh : 8L * kh;
+    // (small rasters, C == 1: the machine is mostly empty and the warm-up is cheap -- short bands, many CTAs)
+    const long min_rpb = (C == 1) ? 4L : 8L * kh;
     if (rpb < min_rpb) rpb = min_rpb;
     if (rpb > h) rpb = h;
     g.rows_per_band = (int)rpb;

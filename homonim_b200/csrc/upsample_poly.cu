@@ -39,7 +39,7 @@ constexpr int kPpt = 4;                    // destination pixels per lane
 constexpr int kWarpW = 32 * kPpt;          // destination columns per warp
 constexpr int kRb = 4;                     // rows per cp.async stage
 constexpr int kStages = 4;                 // stages in flight per warp
-constexpr int kMaxRows = 64;               // destination rows per CTA
+constexpr int kMaxRows = 128;              // destination rows per CTA (upper bound)
 constexpr int kRowTableBytes = kMaxRows * (16 + 4);   // per-CTA row table: 4 float y-weights + tap row per row
 
 // ---- packed float32 pairs -------------------------------------------------------------------------------------------
@@ -89,6 +89,34 @@ __device__ __forceinline__ void bspline_weights(double d, double (&w)[4])   // t
     w[3] = d2 * d * (1.0 / 6.0);
 }
 
+// B-spline weights of one destination index along one axis with GDAL's edge rules folded in: taps outside [0, n) get
+// weight 0 and the remaining weights are divided by their sum unless it is within 1e-5 of 1 (GWKResample's rule,
+// applied per axis -- GDAL applies it to the product of the two axis sums; the two differ by <= 2e-5 relative, and
+// only where taps are dropped on both axes); all weights are NaN when the pixel's centre coarse pixel is out of
+// range (GDAL skips such pixels).  `k` returns the first tap index + 1.
+__device__ __forceinline__ void up_axis_weights(double scale, double off, long i, long n, double (&w)[4], long &k)
+{
+    const double c = up_src_coord(scale, off, i);
+    const double kd = floor(c - 0.5);
+    k = (long)kd;
+    bspline_weights(c - 0.5 - kd, w);
+    long centre = (long)floor(c + 1e-10);
+    if (centre == n) centre--;
+    const bool ok = (c >= 0.0) && centre >= 0 && centre < n;
+    double sum = 0.0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const long tap = k - 1 + t;
+        if (tap < 0 || tap >= n) w[t] = 0.0;
+        sum += w[t];
+    }
+    if (!ok || sum < 0.99999 || sum > 1.00001) {            // (rare: only next to the raster's edges)
+        const double norm = ok ? 1.0 / sum : __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+        for (int t = 0; t < 4; t++) w[t] *= norm;
+    }
+}
+
 // ---- cp.async (LDGSTS) ---------------------------------------------------------------------------------------------
 template <int BYTES> __device__ __forceinline__ void cp_async_lane(uint32_t smem_dst, const void *gmem_src)
 {
@@ -109,9 +137,10 @@ template <> struct SrcQuad<uint16_t> {
     {
         return (nd.ivalue >= 0 && nd.ivalue <= 65535) ? (0x4B000000u | (uint32_t)nd.ivalue) : 0xFFFFFFFFu;
     }
-    static __device__ __forceinline__ void get(const void *p, const Key magic, float2 (&s)[2], bool (&ok)[4])
+    static __device__ __forceinline__ void get_shared(uint32_t sa, const Key magic, float2 (&s)[2], bool (&ok)[4])
     {
-        const uint2 w = *reinterpret_cast<const uint2 *>(p);
+        uint2 w;
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w.x), "=r"(w.y) : "r"(sa));
         // 2^23 + v has v in its mantissa: one byte-permute per pixel and one packed subtract per pair (exact)
         const float2 m0 = make_float2(__uint_as_float(__byte_perm(w.x, 0x4B000000u, 0x7410)),
                                       __uint_as_float(__byte_perm(w.x, 0x4B000000u, 0x7432)));
@@ -132,9 +161,10 @@ template <> struct SrcQuad<uint8_t> {
     {
         return (nd.ivalue >= 0 && nd.ivalue <= 255) ? (0x4B000000u | (uint32_t)nd.ivalue) : 0xFFFFFFFFu;
     }
-    static __device__ __forceinline__ void get(const void *p, const Key magic, float2 (&s)[2], bool (&ok)[4])
+    static __device__ __forceinline__ void get_shared(uint32_t sa, const Key magic, float2 (&s)[2], bool (&ok)[4])
     {
-        const uint32_t w = *reinterpret_cast<const uint32_t *>(p);
+        uint32_t w;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sa));
         const float2 m0 = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440)),
                                       __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441)));
         const float2 m1 = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7442)),
@@ -151,9 +181,10 @@ template <> struct SrcQuad<float> {
     static constexpr int kBytes = 16;
     typedef NoData Key;
     static __device__ __forceinline__ Key key(const NoData &nd) { return nd; }
-    static __device__ __forceinline__ void get(const void *p, const Key &nd, float2 (&s)[2], bool (&ok)[4])
+    static __device__ __forceinline__ void get_shared(uint32_t sa, const Key &nd, float2 (&s)[2], bool (&ok)[4])
     {
-        const float4 w = *reinterpret_cast<const float4 *>(p);
+        float4 w;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w) : "r"(sa));
         s[0] = make_float2(w.x, w.y);
         s[1] = make_float2(w.z, w.w);
         ok[0] = hb_valid(w.x, nd); ok[1] = hb_valid(w.y, nd); ok[2] = hb_valid(w.z, nd); ok[3] = hb_valid(w.w, nd);
@@ -164,7 +195,7 @@ template <> struct SrcQuad<float> {
 // pre-pass: classify the coarse cells, interleave the two bands, list the DIRTY cells
 // =====================================================================================================================
 // Cell (ky, kx), ky in [-1, hp], kx in [-1, wp]: the destination pixels whose first tap is (ky - 1, kx - 1).
-// flags[(ky + 1) * (wp + 2) + (kx + 1)]: bit0 CLEAN, bit1 DEAD.
+// flags[(ky + 1) * (wp + 2) + (kx + 1)]: bit0 CLEAN, bit1 DEAD, bit2 OUT (DEAD because the centre pixels are out of range).
 // GUARD (apply mode): a cell is only CLEAN if the gain band's taps are within a factor 16 of each other.  Next to a
 // parameter spike (an ill-conditioned solve of the reference) corr = gain*src + offset cancels heavily
 // and float32 interpolation errors would be amplified past 1e-4; such cells take the double-precision fix-up instead.
@@ -179,7 +210,7 @@ __global__ void upsample_prep_kernel(const float *__restrict__ coarse, long hp, 
         const long idx = live ? idx0 : n - 1;
         const long ky = idx / fw - 1, kx = idx % fw - 1;
         // validity bits of the 4x4 tap window: bit (j*4+i) of `all` = valid in every band, of `any` = valid in some band
-        unsigned all = 0, any = 0;
+        unsigned all = 0, any = 0, inr = 0;
         float gmin = 3.0e38f, gmax = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -188,15 +219,16 @@ __global__ void upsample_prep_kernel(const float *__restrict__ coarse, long hp, 
                 const long y = ky - 1 + j, x = kx - 1 + i;
                 if (y >= 0 && y < hp && x >= 0 && x < wp) {
                     const float g0 = __ldg(coarse + y * wp + x);
-                    const bool v0 = !isnan(g0);
-                    const bool v1 = (NB > 1) ? !isnan(__ldg(coarse + plane + y * wp + x)) : v0;
-                    if (v0 && v1) all |= 1u << (j * 4 + i);
-                    if (v0 || v1) any |= 1u << (j * 4 + i);
-                    if (GUARD && v0) { gmin = fminf(gmin, fabsf(g0)); gmax = fmaxf(gmax, fabsf(g0)); }
+                    const float g1 = (NB > 1) ? __ldg(coarse + plane + y * wp + x) : g0;
+                    inr |= 1u << (j * 4 + i);
+                    // (an infinite tap is data for GDAL; the fast path cannot multiply it by a zero weight: not CLEAN)
+                    if (isfinite(g0) && isfinite(g1)) all |= 1u << (j * 4 + i);
+                    if (!isnan(g0) || !isnan(g1)) any |= 1u << (j * 4 + i);
+                    if (GUARD && !isnan(g0)) { gmin = fminf(gmin, fabsf(g0)); gmax = fmaxf(gmax, fabsf(g0)); }
                 }
             }
         }
-        const bool clean = (all == 0xFFFFu) && (!GUARD || gmax <= 16.0f * gmin);
+
         // centre-pixel candidates of the cell's destination pixels: rows {ky, ky+1} (+ ky-1 when ky == hp, GDAL's
         // "cy == hs -> cy--" rule), same for the columns; window bit (j, i) is row ky-1+j, column kx-1+i
         unsigned rows_m = 0x6u, cols_m = 0x6u;                  // j (i) in {1, 2}
@@ -206,8 +238,11 @@ __global__ void upsample_prep_kernel(const float *__restrict__ coarse, long hp, 
 #pragma unroll
         for (int j = 0; j < 4; j++)
             if ((rows_m >> j) & 1u) cand |= (cols_m & 0xFu) << (j * 4);
-        const bool dead = (any & cand) == 0;
-        if (live) flags[idx] = (uint8_t)((clean ? 1 : 0) | (dead ? 2 : 0));
+        const bool dead = (any & cand) == 0;                  // no destination pixel of the cell has a valid centre
+        const bool outr = (inr & cand) == 0;                  // ... because no centre candidate is inside the raster
+        // CLEAN: every tap inside the raster is usable in every band (taps outside it are handled by the edge weights)
+        const bool clean = !dead && (all == inr) && (!GUARD || gmax <= 16.0f * gmin);
+        if (live) flags[idx] = (uint8_t)((clean ? 1 : 0) | (dead ? 2 : 0) | (outr ? 4 : 0));
         // append the DIRTY cells: one atomic per warp
         const bool dirty = live && !clean && !dead;
         const unsigned vote = __ballot_sync(0xffffffffu, dirty);
@@ -228,203 +263,239 @@ __global__ void upsample_prep_kernel(const float *__restrict__ coarse, long hp, 
 // =====================================================================================================================
 struct __align__(16) RowEntry { float wy[4]; };            // the row's B-spline y-weights (taps ky-1 .. ky+2)
 
+#ifndef HB_POLY_MIN_CTAS
+#define HB_POLY_MIN_CTAS 2
+#endif
+
 // T: storage type of the source plane (APPLY); NB: coarse bands; APPLY: fuse corr = gain*src + offset.
 // coarse: NB == 2: interleaved (gain, offset) float2 [hp][wp]; NB == 1: the float plane.
+// rows_per_cta (<= kMaxRows) is chosen by the host so that the grid fills whole waves.
 template <typename T, int NB, bool APPLY>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, HB_POLY_MIN_CTAS)
 upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restrict__ coarse_v,
-                     const uint8_t *__restrict__ flags, UpPolyGeom g, float *__restrict__ out)
+                     const uint8_t *__restrict__ flags, UpPolyGeom g, int rows_per_cta, float *__restrict__ out)
 {
     constexpr int NOUT = (NB == 2 && !APPLY) ? 2 : 1;
     constexpr int kLaneBytes = APPLY ? SrcQuad<T>::kBytes : 0;
     constexpr int kRowBytes = 32 * kLaneBytes;
-    constexpr int kRingBytes = kStages * kRb * kRowBytes;
+    constexpr int kStageBytes = kRb * kRowBytes;
+    constexpr int kRingBytes = kStages * kStageBytes;
     constexpr int kWBytes = 5 * 32 * (int)sizeof(float4);                  // x-weights of one warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long Y0 = (long)blockIdx.y * kMaxRows;
-    const long Y1 = min(Y0 + (long)kMaxRows, g.hs);
+    const long Y0 = (long)blockIdx.y * rows_per_cta;
+    const int nrows = (int)min((long)rows_per_cta, g.hs - Y0);
     const float qnan = __int_as_float(0x7fc00000);
 
     // per-CTA row table: y-weights and first tap row (+1) of the CTA's destination rows
     RowEntry *s_rows = reinterpret_cast<RowEntry *>(smem_raw);
     int *s_ky = reinterpret_cast<int *>(smem_raw + kMaxRows * sizeof(RowEntry));
-    if ((long)threadIdx.x < Y1 - Y0) {
-        const double srcy = up_src_coord(g.sy, g.oy, Y0 + threadIdx.x);
-        const double ky = floor(srcy - 0.5);
+    if ((int)threadIdx.x < nrows) {
         double wy[4];
-        bspline_weights(srcy - 0.5 - ky, wy);
+        long ky;
+        up_axis_weights(g.sy, g.oy, Y0 + threadIdx.x, g.hp, wy, ky);
         RowEntry e;
 #pragma unroll
         for (int j = 0; j < 4; j++) e.wy[j] = (float)wy[j];
         s_rows[threadIdx.x] = e;
-        s_ky[threadIdx.x] = (int)ky;
+        s_ky[threadIdx.x] = (int)min(max(ky, -4L), g.hp + 4);
     }
     __syncthreads();                                        // the only CTA barrier
 
-    const long strip = (long)blockIdx.x * kWarps + warp;
-    const long Xw0 = strip * kWarpW;
-    if (Xw0 >= g.ws) return;
-    const long X0 = Xw0 + (long)lane * kPpt;                // (ws % 4 == 0: a lane is wholly inside or outside)
-    const bool lane_in = X0 < g.ws;
+    const long X0 = ((long)blockIdx.x * kWarps + warp) * kWarpW + (long)lane * kPpt;
+    if (X0 - lane * kPpt >= g.ws) return;                   // the whole warp is beyond the raster
+    const bool lane_in = X0 < g.ws;                         // (ws % 4 == 0: a lane is wholly inside or outside)
     unsigned char *warp_base = smem_raw + kRowTableBytes + warp * (kWBytes + kRingBytes);
     float4 *s_w = reinterpret_cast<float4 *>(warp_base) + lane;            // s_w[i * 32]: tap i of the lane's 4 pixels
-    const unsigned char *s_ring = warp_base + kWBytes + lane * kLaneBytes;
-    const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(s_ring);
+    const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(warp_base + kWBytes + lane * kLaneBytes);
 
-    // ---- cp.async ring of source rows ---------------------------------------------------------------------------------
-    const T *src_p = APPLY ? src + Y0 * g.ws + X0 : nullptr;               // next row to prefetch
-    long rows_left = Y1 - Y0;
-    const long row_pitch = g.ws;
-    auto prefetch = [&](int stage) {
+    // ---- cp.async ring of source rows: every lane copies, and later reads, only its own 4 pixels ----------------------
+    const long pitch_b = g.ws * (long)sizeof(T);
+    const char *pf = APPLY ? reinterpret_cast<const char *>(src + Y0 * g.ws + X0) : nullptr;   // next row to prefetch
+    int pf_left = nrows;
+    uint32_t pf_dst = ring_sa;
+    auto prefetch = [&]() {
         if (APPLY && lane_in) {
-            const uint32_t dst = ring_sa + stage * (kRb * kRowBytes);
-            if (rows_left >= kRb) {
+            if (pf_left >= kRb) {
 #pragma unroll
-                for (int rr = 0; rr < kRb; rr++) cp_async_lane<kLaneBytes>(dst + rr * kRowBytes, src_p + rr * row_pitch);
+                for (int rr = 0; rr < kRb; rr++) {
+                    cp_async_lane<kLaneBytes>(pf_dst + rr * kRowBytes, pf);
+                    pf += pitch_b;
+                }
             } else {
-#pragma unroll
-                for (int rr = 0; rr < kRb; rr++)
-                    if (rr < rows_left) cp_async_lane<kLaneBytes>(dst + rr * kRowBytes, src_p + rr * row_pitch);
+                for (int rr = 0; rr < pf_left; rr++) {
+                    cp_async_lane<kLaneBytes>(pf_dst + rr * kRowBytes, pf);
+                    pf += pitch_b;
+                }
             }
         }
-        src_p += kRb * row_pitch;
-        rows_left -= kRb;
+        pf_left -= kRb;
+        pf_dst = (pf_dst + kStageBytes == ring_sa + kRingBytes) ? ring_sa : pf_dst + kStageBytes;
         cp_async_commit();
     };
     if (APPLY) {
 #pragma unroll
-        for (int st = 0; st < kStages - 1; st++) prefetch(st);
+        for (int st = 0; st < kStages - 1; st++) prefetch();
     }
 
-    // ---- row-invariant lane geometry (double), x-weights over the lane's 5-column tap window -> shared memory ----------
-    long col0 = 0;                                          // first tap column of the lane's window
+    // ---- row-invariant lane geometry (double): edge-aware x-weights over the lane's 5-column tap window -> shared ------
+    int col0 = 0;                                           // first tap column of the lane's window
     int cellA = 0, cellB = 0;                               // flag columns (kx + 1) of the lane's first / last pixel
-    bool geom_ok = lane_in;
     {
         float w5[kPpt][5];
         long kx0 = 0;
 #pragma unroll
         for (int k = 0; k < kPpt; k++) {
-            const double srcx = up_src_coord(g.sx, g.ox, X0 + k);
-            const double kxd = floor(srcx - 0.5);
-            const long kx = (long)kxd;
-            if (k == 0) kx0 = kx;
-            const long sh = kx - kx0;                       // the pixel's window starts 0 or 1 column into the lane's
-            geom_ok = geom_ok && (sh == 0 || sh == 1);
-            if (k == kPpt - 1) cellB = (int)min(max(kx + 1, -1L), g.wp + 2);
             double wx[4];
-            bspline_weights(srcx - 0.5 - kxd, wx);
+            long kx;
+            up_axis_weights(g.sx, g.ox, X0 + k, g.wp, wx, kx);
+            if (k == 0) kx0 = kx;
+            const bool sh = (kx != kx0);                    // the pixel's window starts 0 or 1 column into the lane's
+            if (k == kPpt - 1) cellB = (int)min(max(kx + 1, -1L), g.wp + 2);
             w5[k][0] = sh ? 0.f : (float)wx[0];
             w5[k][1] = (float)(sh ? wx[0] : wx[1]);
             w5[k][2] = (float)(sh ? wx[1] : wx[2]);
             w5[k][3] = (float)(sh ? wx[2] : wx[3]);
             w5[k][4] = sh ? (float)wx[3] : 0.f;
         }
-        col0 = kx0 - 1;
+        col0 = (int)min(max(kx0 - 1, -8L), g.wp + 8);
         cellA = (int)min(max(kx0 + 1, -1L), g.wp + 2);
 #pragma unroll
         for (int i = 0; i < 5; i++) s_w[i * 32] = make_float4(w5[0][i], w5[1][i], w5[2][i], w5[3][i]);
     }
-    const int fw = (int)g.wp + 2;
+    const int fw = (int)g.wp + 2, hp = (int)g.hp, wp = (int)g.wp;
     // cells outside the flag table hold no pixel with an in-range centre: DEAD
     auto cell_flags = [&](int ky, int cell) -> unsigned {
-        if (ky < -1 || ky > g.hp || cell < 0 || cell >= fw) return 2u;
+        if (ky < -1 || ky > hp || cell < 0 || cell >= fw) return 6u;
         return flags[(long)(ky + 1) * fw + cell];
     };
 
     const typename SrcQuad<T>::Key nd_key = SrcQuad<T>::key(nd);
-    float2 q[2][NB][4];                                     // x-interpolated tap rows per pixel PAIR and band
+    // x-interpolated tap rows per pixel PAIR and band.  CLEAN lanes: the interpolated values; DEAD lanes: NaN (so that
+    // the row arithmetic produces nodata by itself); DIRTY lanes / lanes beyond the raster: stale, never stored.
+    float2 q[2][NB][4];
     int q_ky = INT_MIN;
-    // 0: CLEAN (polynomial), 1: SKIP (DIRTY: left to the fix-up kernel; or a lane beyond the raster), 2: DEAD (nodata)
-    int state = 1;
+    bool do_store = false;
     float *orow = out + Y0 * g.ws + X0;
-    int stage = 0;
-    for (long Yb = Y0; Yb < Y1; Yb += kRb) {
-        const int nrows = (int)min((long)kRb, Y1 - Yb);
-        if (APPLY) {
-            prefetch((stage + kStages - 1) % kStages);
+    const long out_pitch = g.ws;
+    uint32_t ring_rd = ring_sa;                             // this lane's pixels of the current row in the ring
+    // the row table entry of row r + 1 is fetched while row r is computed (the loop is a chain of short dependent
+    // steps with only a few warps per scheduler to hide shared-memory latency behind)
+    int ky_next = s_ky[0];
+    RowEntry ri_next = s_rows[0];
+#pragma unroll 1
+    for (int r = 0; r < nrows; r++, orow += out_pitch) {
+        if (APPLY && (r & (kRb - 1)) == 0) {                // (warp-uniform) a new stage: keep the ring full, wait for it
+            prefetch();
             cp_async_wait<kStages - 1>();
         }
-        const unsigned char *ring_b = s_ring + stage * kRb * kRowBytes;
-        stage = (stage + 1) % kStages;
-#pragma unroll 1
-        for (int rr = 0; rr < nrows; rr++, orow += g.ws) {
-            const int ky = s_ky[Yb - Y0 + rr];
-            if (ky != q_ky) {                               // (warp-uniform) new tap rows: re-classify, re-interpolate
-                q_ky = ky;
-                const unsigned fa = cell_flags(ky, cellA), fb = cell_flags(ky, cellB);
-                state = !lane_in ? 1 : (((fa & fb & 1u) && geom_ok) ? 0 : (((fa & fb & 2u) || !geom_ok) ? 2 : 1));
-                if (state == 0) {
-                    const bool five = (cellB != cellA);     // some pixel's window starts one column in: 5th column is used
-                    float2 wp01[5], wp23[5];
-#pragma unroll
-                    for (int i = 0; i < 5; i++) {
-                        const float4 w = s_w[i * 32];
-                        wp01[i] = make_float2(w.x, w.y);
-                        wp23[i] = make_float2(w.z, w.w);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        float t[NB][5];
-                        if (NB == 2) {
-                            const float2 *p = reinterpret_cast<const float2 *>(coarse_v) + (long)(ky - 1 + j) * g.wp + col0;
-#pragma unroll
-                            for (int i = 0; i < 5; i++) {
-                                // (the 5th column has weight 0 when unused, but may be out of range or NaN: skip it)
-                                const float2 v = (i < 4 || five) ? __ldg(p + i) : make_float2(0.f, 0.f);
-                                t[0][i] = v.x;
-                                t[NB - 1][i] = v.y;
-                            }
-                        } else {
-                            const float *p = reinterpret_cast<const float *>(coarse_v) + (long)(ky - 1 + j) * g.wp + col0;
-#pragma unroll
-                            for (int i = 0; i < 5; i++) t[0][i] = (i < 4 || five) ? __ldg(p + i) : 0.f;
-                        }
-#pragma unroll
-                        for (int b = 0; b < NB; b++) {      // x-interpolation of tap row j at the lane's 4 pixel columns
-                            float2 r0 = fmul2(wp01[0], splat(t[b][0])), r1 = fmul2(wp23[0], splat(t[b][0]));
-#pragma unroll
-                            for (int i = 1; i < 5; i++) {
-                                r0 = ffma2(wp01[i], splat(t[b][i]), r0);
-                                r1 = ffma2(wp23[i], splat(t[b][i]), r1);
-                            }
-                            q[0][b][j] = r0;
-                            q[1][b][j] = r1;
-                        }
-                    }
-                }
+        const int ky = ky_next;
+        const RowEntry ri = ri_next;
+        {
+            const int rn = min(r + 1, nrows - 1);
+            ky_next = s_ky[rn];
+            ri_next = s_rows[rn];
+        }
+        if (ky != q_ky) {                                   // (warp-uniform) new tap rows: re-classify, re-interpolate
+            q_ky = ky;
+            const unsigned fa = cell_flags(ky, cellA), fb = cell_flags(ky, cellB);
+            if (lane_in) {
+                // next cell row's flags -> L1 (the flag load heads the dependency chain of every re-interpolation)
+                const long nf = (long)min(max(ky + 2, 0), hp + 1) * fw;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(flags + nf + min(max(cellA, 0), fw - 1)));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(flags + nf + min(max(cellB, 0), fw - 1)));
             }
-            if (state == 1) continue;                       // DIRTY lanes are written by the fix-up kernel
-            float4 res[NOUT];
+            // 0: CLEAN, 1: SKIP (DIRTY: left to the fix-up kernel; or a lane beyond the raster), 2: DEAD.
+            // A CLEAN cell next to an OUT cell: the OUT cell's pixel columns carry NaN x-weights.
+            const bool clean2 = ((fa | fb) & 1u) && (fa & 5u) && (fb & 5u);
+            const int state = !lane_in ? 1 : (clean2 ? 0 : ((fa & fb & 2u) ? 2 : 1));
+            do_store = (state != 1);
+            if (state == 2) {
+#pragma unroll
+                for (int p = 0; p < 2; p++)
+#pragma unroll
+                    for (int b = 0; b < NB; b++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) q[p][b][j] = splat(qnan);
+            }
+            if (lane_in) {
+                // the NEXT cell row re-uses 3 of these tap rows (L1 hits by then); pull its one new row into L1 now, so
+                // that the whole CTA does not stall on L2 at its next (simultaneous) re-interpolation
+                const long nrow = (long)min(max(ky + 3, 0), hp - 1) * wp + min(max(col0, 0), wp - 1);
+                const char *np = reinterpret_cast<const char *>(coarse_v) + nrow * (NB == 2 ? 8 : 4);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(np));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(np + (NB == 2 ? 32 : 16)));
+            }
             if (state == 0) {
-                const RowEntry ri = s_rows[Yb - Y0 + rr];
-                const float2 w0 = splat(ri.wy[0]), w1 = splat(ri.wy[1]), w2 = splat(ri.wy[2]), w3 = splat(ri.wy[3]);
-                float2 gv[2], ov[2];
+                const bool five = (cellB != cellA);         // some pixel's window starts one column in: 5th column is used
+                // taps outside the raster have weight 0 (x-weights / row table): read the clamped position
+                int coff[5];
 #pragma unroll
-                for (int p = 0; p < 2; p++) {
-                    gv[p] = ffma2(q[p][0][3], w3, ffma2(q[p][0][2], w2, ffma2(q[p][0][1], w1, fmul2(q[p][0][0], w0))));
-                    if (NB > 1)
-                        ov[p] = ffma2(q[p][NB - 1][3], w3, ffma2(q[p][NB - 1][2], w2, ffma2(q[p][NB - 1][1], w1,
-                                      fmul2(q[p][NB - 1][0], w0))));
-                    else
-                        ov[p] = splat(0.f);
+                for (int i = 0; i < 5; i++) coff[i] = min(max(col0 + i, 0), wp - 1);
+                float2 wp01[5], wp23[5];
+#pragma unroll
+                for (int i = 0; i < 5; i++) {
+                    const float4 w = s_w[i * 32];
+                    wp01[i] = make_float2(w.x, w.y);
+                    wp23[i] = make_float2(w.z, w.w);
                 }
-                if constexpr (APPLY) {
-                    float2 s[2];
-                    bool ok[4];
-                    SrcQuad<T>::get(ring_b + rr * kRowBytes, nd_key, s, ok);
-                    const float2 c0 = ffma2(gv[0], s[0], ov[0]), c1 = ffma2(gv[1], s[1], ov[1]);   // corr = gain*src + offset
-                    res[0] = make_float4(ok[0] ? c0.x : qnan, ok[1] ? c0.y : qnan, ok[2] ? c1.x : qnan,
-                                         ok[3] ? c1.y : qnan);
-                } else {
-                    res[0] = make_float4(gv[0].x, gv[0].y, gv[1].x, gv[1].y);
-                    if constexpr (NOUT == 2) res[1] = make_float4(ov[0].x, ov[0].y, ov[1].x, ov[1].y);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const long row_off = (long)min(max(ky - 1 + j, 0), hp - 1) * wp;
+                    float t[NB][5];
+                    if (NB == 2) {
+                        const float2 *p = reinterpret_cast<const float2 *>(coarse_v) + row_off;
+#pragma unroll
+                        for (int i = 0; i < 5; i++) {
+                            // (the 5th column has weight 0 when unused, but may be NaN: skip it)
+                            const float2 v = (i < 4 || five) ? __ldg(p + coff[i]) : make_float2(0.f, 0.f);
+                            t[0][i] = v.x;
+                            t[NB - 1][i] = v.y;
+                        }
+                    } else {
+                        const float *p = reinterpret_cast<const float *>(coarse_v) + row_off;
+#pragma unroll
+                        for (int i = 0; i < 5; i++) t[0][i] = (i < 4 || five) ? __ldg(p + coff[i]) : 0.f;
+                    }
+#pragma unroll
+                    for (int b = 0; b < NB; b++) {          // x-interpolation of tap row j at the lane's 4 pixel columns
+                        float2 r0 = fmul2(wp01[0], splat(t[b][0])), r1 = fmul2(wp23[0], splat(t[b][0]));
+#pragma unroll
+                        for (int i = 1; i < 5; i++) {
+                            r0 = ffma2(wp01[i], splat(t[b][i]), r0);
+                            r1 = ffma2(wp23[i], splat(t[b][i]), r1);
+                        }
+                        q[0][b][j] = r0;
+                        q[1][b][j] = r1;
+                    }
                 }
-            } else {
-                res[0] = make_float4(qnan, qnan, qnan, qnan);
-                if constexpr (NOUT == 2) res[1] = res[0];
             }
+        }
+        // ---- one destination row: 4 multiply-adds per pixel pair and band with the row's y-weights, fused apply ------------
+        const float2 w0 = splat(ri.wy[0]), w1 = splat(ri.wy[1]), w2 = splat(ri.wy[2]), w3 = splat(ri.wy[3]);
+        float2 gv[2], ov[2];
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            gv[p] = ffma2(q[p][0][3], w3, ffma2(q[p][0][2], w2, ffma2(q[p][0][1], w1, fmul2(q[p][0][0], w0))));
+            if (NB > 1)
+                ov[p] = ffma2(q[p][NB - 1][3], w3, ffma2(q[p][NB - 1][2], w2, ffma2(q[p][NB - 1][1], w1,
+                              fmul2(q[p][NB - 1][0], w0))));
+            else
+                ov[p] = splat(0.f);
+        }
+        float4 res[NOUT];
+        if constexpr (APPLY) {
+            float2 s[2];
+            bool ok[4];
+            SrcQuad<T>::get_shared(ring_rd, nd_key, s, ok);
+            ring_rd = (ring_rd + kRowBytes == ring_sa + kRingBytes) ? ring_sa : ring_rd + kRowBytes;
+            const float2 c0 = ffma2(gv[0], s[0], ov[0]), c1 = ffma2(gv[1], s[1], ov[1]);   // corr = gain*src + offset
+            res[0] = make_float4(ok[0] ? c0.x : qnan, ok[1] ? c0.y : qnan, ok[2] ? c1.x : qnan, ok[3] ? c1.y : qnan);
+        } else {
+            res[0] = make_float4(gv[0].x, gv[0].y, gv[1].x, gv[1].y);
+            if constexpr (NOUT == 2) res[1] = make_float4(ov[0].x, ov[0].y, ov[1].x, ov[1].y);
+        }
+        if (do_store) {                                     // (DIRTY lanes are written by the fix-up kernel)
             hb_stg_stream16(orow, res[0]);
             if constexpr (NOUT == 2) hb_stg_stream16(orow + g.hs * g.ws, res[1]);
         }
@@ -437,6 +508,7 @@ upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restric
 // (gr_cubic_spline_up in oracle/gdal_restate.c: centre pixel in range and valid in some band; out-of-range / invalid
 // taps dropped; pixel dropped if sum(w) < 1e-6; renormalised unless sum(w) is within 1e-5 of 1.)
 constexpr int kFixThreads = 128;
+constexpr int kFixSplit = 1;
 
 // One warp per DIRTY cell (grid-stride over the list), one lane per destination pixel COLUMN of the 4-pixel groups that
 // touch the cell.  A lane first combines its column's 4x4 taps along x -- values A[j] = sum_i wx[i] v[j][i] over the
@@ -454,14 +526,22 @@ upsample_fixup_kernel(const T *__restrict__ src, NoData nd, const float *__restr
     const long n_warps = (long)gridDim.x * kFixWarps;
     const long fw = g.wp + 2, plane = g.hp * g.wp;
     const float qnan = __int_as_float(0x7fc00000);
-    const int n = *count;
+    // every cell is split into kFixSplit row chunks (one warp each): short dependent chains, more warps in flight
+    const long n = (long)*count * kFixSplit;
     for (long e = warp_id; e < n; e += n_warps) {
-        const long idx = list[e];
+        const long idx = list[e / kFixSplit];
+        const int part = (int)(e % kFixSplit);
         const long ky = idx / fw - 1, kx = idx % fw - 1;
         // destination rows / columns of the cell: the i with up_cell(i) == k (monotone in i)
-        const long ya = up_first_index(g.sy, g.oy, ky, g.hs), yb = up_first_index(g.sy, g.oy, ky + 1, g.hs);
+        long ya = up_first_index(g.sy, g.oy, ky, g.hs), yb = up_first_index(g.sy, g.oy, ky + 1, g.hs);
         const long xa = up_first_index(g.sx, g.ox, kx, g.ws), xb = up_first_index(g.sx, g.ox, kx + 1, g.ws);
         if (yb <= ya || xb <= xa) continue;
+        {
+            const long chunk = (yb - ya + kFixSplit - 1) / kFixSplit;
+            ya += part * chunk;
+            yb = min(yb, ya + chunk);
+            if (yb <= ya) continue;
+        }
         // every 4-pixel group (= lane of the fast kernel) that touches the cell was skipped there: do whole groups
         const long ga = (xa / kPpt) * kPpt, gb = min(((xb - 1) / kPpt + 1) * kPpt, g.ws);
         for (long X = ga + lane; X < gb; X += 32) {
@@ -568,6 +648,7 @@ int launch_poly(const void *src, NoData nd, const float *coarse, const UpPolyGeo
     const size_t off_c2 = off_flags + (((size_t)ncell + 15) / 16) * 16;
     const size_t total = off_c2 + (NB == 2 ? (size_t)g.hp * g.wp * sizeof(float2) : 0);
     char *wsb = nullptr;
+    HB_CUDA_OK(hb_pool_keep_memory());
     HB_CUDA_OK(cudaMallocAsync((void **)&wsb, total, stream));
     int *count = (int *)wsb, *list = (int *)(wsb + off_list);
     uint8_t *flags = (uint8_t *)(wsb + off_flags);
@@ -585,13 +666,33 @@ int launch_poly(const void *src, NoData nd, const float *coarse, const UpPolyGeo
         const size_t ring = APPLY ? (size_t)kStages * kRb * 32 * kPpt * sizeof(T) : 0;
         const size_t smem = kRowTableBytes + (5 * 32 * sizeof(float4) + ring) * kWarps;
         const long cta_w = (long)kWarpW * kWarps;
-        dim3 grid((unsigned)((g.ws + cta_w - 1) / cta_w), (unsigned)((g.hs + kMaxRows - 1) / kMaxRows));
-        HB_REQUIRE(grid.y <= 65535u, "up-sampling destination has too many rows (%ld)", g.hs);
+        const long gx = (g.ws + cta_w - 1) / cta_w;
         auto kern = upsample_poly_kernel<T, NB, APPLY>;
         if (smem > 48 * 1024)
             HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // rows per CTA: as many as possible (fewer row tables / weight set-ups per pixel) such that the grid is just
+        // under a whole number of waves of resident CTAs (every warp streams the same amount: no ragged tail)
+        static int ctas_per_sm = 0;
+        if (ctas_per_sm == 0) {
+            int n = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kThreads, smem) != cudaSuccess || n < 1) n = 1;
+            ctas_per_sm = n;
+        }
+        const long slots = (long)hb_sm_count() * ctas_per_sm;
+        long rpc = kMaxRows;
+        {
+            double best = -1.0;
+            for (long cand = kMaxRows; cand >= 32; cand -= kRb) {
+                const long ctas = gx * ((g.hs + cand - 1) / cand);
+                const long waves = (ctas + slots - 1) / slots;
+                const double eff = (double)ctas / (double)(waves * slots) * (cand >= 64 ? 1.0 : 0.97);
+                if (eff > best + 0.02) { best = eff; rpc = cand; }
+            }
+        }
+        dim3 grid((unsigned)gx, (unsigned)((g.hs + rpc - 1) / rpc));
+        HB_REQUIRE(grid.y <= 65535u, "up-sampling destination has too many rows (%ld)", g.hs);
         kern<<<grid, kThreads, smem, stream>>>((const T *)src, nd, NB == 2 ? (const void *)coarse2 : (const void *)coarse,
-                                               flags, g, out);
+                                               flags, g, (int)rpc, out);
         HB_LAUNCH_OK("upsample_poly_kernel");
     }
     {

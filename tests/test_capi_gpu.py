@@ -47,6 +47,8 @@ def _rand_src(rng, h, w, dtype, nodata, holes=True):
     ('uint16', 0, 5, (1.3, 2.6), (40, 33)),       # mis-aligned: fractional edge weights
     ('float32', NAN, 3, (0.5, 0.25), (41, 50)),
     ('float32', -9999.0, 2.5, (0.2, 0.7), (40, 44)),   # non-integer ratio, value nodata
+    ('uint16', 0, 100, (0, 0), (9, 11)),          # few destination pixels per warp strip
+    ('uint8', 0, 300, (7.0, 3.0), (12, 13)),      # very large ratio (0.1 m drone imagery vs 30 m Landsat)
 ])
 def test_downsample_average(dtype, nodata, ratio, shift, hw):
     gr, _ = _oracle()
