@@ -2,13 +2,15 @@
 """
 bench.py -- fit + apply throughput of the kernel-model hot path (BASELINE.json metric) on N B200 GPUs of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c2-gain|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c2-gain|c3|c4|c5a]
 
 One "step" is one pass of the hot path over one synthetic source image: RasterFuse.process() = per band
 RefSpaceModel/SrcSpaceModel .fit() + .apply().  Default workload (N = 1): BASELINE.json configs[1] --
 a 4-band uint16 10 000 x 10 000 aerial image against a 10 m reference (20x coarser), gain-offset 15x15 with
 r2_inpaint_thresh = 0.25, proc_crs = ref.  With N > 1 every rank corrects its own source image (the batch-mosaic
-regime, no data-path collective): weak scaling, value = pixels of all ranks / max-over-ranks time.
+regime, no data-path collective): weak scaling, value = pixels of all ranks / max-over-ranks time.  `--workload c5a` is
+the one-raster regime instead: ONE 60 000 x 60 000 4-band float32 raster split into row bands over the ranks (strong
+scaling; the down-sampled proc-grid planes are all-gathered over NCCL, homonim_b200/dist.py).
 
 The JSON line carries: `value` (device-resident inputs, CUDA-event timed), `e2e` (the same call with HOST buffers:
 pinned host -> device copies of the inputs and device -> host copy of the corrected image inside the timed region),
@@ -50,6 +52,14 @@ WORKLOADS = {
                kernel_shape=(31, 31), r2_inpaint_thresh=None, proc_crs='src',
                desc='C3: synthetic 4-band float32 20000x20000, proc_crs=src (fit at source resolution), gain-offset '
                     '31x31, no in-painting'),
+    'c4': dict(hp=400, wp=400, ratio=20, bands=4, dtype='uint16', mu=3000.0, src_nodata=0.0, model='gain-blk-offset',
+               kernel_shape=(5, 5), r2_inpaint_thresh=0.25, proc_crs='ref',
+               desc='C4: batch mosaic, synthetic 4-band uint16 8000x8000 sources vs a 10 m reference, one source per '
+                    'GPU and step, gain-blk-offset 5x5, proc_crs=ref'),
+    'c5a': dict(hp=3000, wp=3000, ratio=20, bands=4, dtype='float32', mu=0.3, src_nodata=NAN,
+                model='gain-blk-offset', kernel_shape=(15, 15), r2_inpaint_thresh=0.25, proc_crs='ref', sharded=True,
+                desc='C5a: ONE synthetic 4-band float32 60000x60000 raster sharded as row bands over the GPUs, '
+                     'gain-blk-offset 15x15, proc_crs=ref (proc-grid planes all-gathered over NCCL)'),
 }
 
 
@@ -128,6 +138,149 @@ def run_reference(args, cfg, rank):
     print(json.dumps(line), flush=True)
 
 
+def _peak():
+    peaks_path = REPO / 'MEASURED_PEAKS.json'
+    if peaks_path.exists():
+        return float(json.loads(peaks_path.read_text())['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def _ncu_traffic(workload, entry_point):
+    """
+    DRAM bytes (read + write) per launch of `entry_point` from the committed `ncu --set full` capture of this workload
+    (profiles/ncu_traffic.json: {workload: {entry point: bytes}}); None when no capture is on record.
+    """
+    path = REPO / 'profiles' / 'ncu_traffic.json'
+    if not path.exists():
+        return None
+    try:
+        return json.loads(path.read_text()).get(workload, {}).get(entry_point)
+    except Exception:
+        return None
+
+
+def run_sharded(args, cfg, rank, world, local_rank):
+    """
+    One raster split into row bands over the ranks (configuration C5a): strong scaling.  Every rank
+    generates its own rows (seeded per rank; the reference rows are all-gathered into the replicated proc-grid
+    reference), then per band: down-sample own rows -> all-gather the proc-grid plane -> fit (redundantly, < 1 % of the
+    work) -> up-sample + apply own rows.
+    """
+    import torch
+    import torch.distributed as dist
+    from homonim_b200 import Affine, Model, RasterArray, RefSpaceModel, _native
+    from homonim_b200.dist import RowBands, all_gather_rows, fuse_refspace_sharded
+    from homonim_b200.kernel_model import KernelTimer
+    from homonim_b200.synthetic import make_pair
+
+    args.warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    os.environ.setdefault('MASTER_PORT', '29511')
+    dist.init_process_group('nccl', device_id=device, rank=rank, world_size=world)
+    lib = _native.lib()
+    bands = RowBands.split(cfg['hp'], world)
+    a, b = bands.band(rank)
+    ratio, n_bands = cfg['ratio'], cfg['bands']
+    # this rank's rows of the source, one band at a time (the float32 intermediates of a 60k-wide band are large)
+    # (generated in chunks of 500 proc rows: a whole 60 000 x 60 000 float32 plane exceeds torch's 2^31-element limit
+    # for bilinear interpolation, and its float32 intermediates would not fit beside the raster itself)
+    src_planes, ref_rows = [], []
+    chunk = 500
+    tdtype = getattr(torch, cfg['dtype'])
+    for band in range(n_bands):
+        plane = torch.empty(((b - a) * ratio, cfg['wp'] * ratio), dtype=tdtype, device=device)
+        rrows = torch.empty((b - a, cfg['wp']), dtype=torch.float32, device=device)
+        for c0 in range(0, b - a, chunk):
+            c1 = min(c0 + chunk, b - a)
+            s_ra, r_ra = make_pair(c1 - c0, cfg['wp'], ratio, bands=1, dtype=cfg['dtype'],
+                                   mu=cfg['mu'] * (1 + 0.15 * band), seed=50 + 1009 * rank + 31 * band + c0,
+                                   device=device, src_nodata=cfg['src_nodata'], ref_pad=0)
+            plane[c0 * ratio:c1 * ratio] = s_ra.array[0]
+            rrows[c0:c1] = r_ra.array[0]
+            crs, src_tf0 = s_ra.crs, s_ra.transform
+            del s_ra, r_ra
+        src_planes.append(plane)
+        ref_rows.append(rrows)
+        torch.cuda.empty_cache()
+    # global grids: rank's source rows start at proc row a
+    res = src_tf0.a
+    x0, y0 = src_tf0.c, src_tf0.f
+    ref_global_tf = Affine(res * ratio, 0.0, x0, 0.0, -res * ratio, y0)
+    src_local_tf = Affine(res, 0.0, x0, 0.0, -res, y0 - a * ratio * res)
+    ref_planes = [all_gather_rows(r, bands) for r in ref_rows]
+    del ref_rows
+    model = RefSpaceModel(Model(cfg['model']), cfg['kernel_shape'], r2_inpaint_thresh=cfg['r2_inpaint_thresh'])
+    out = torch.empty_like(src_planes[0], dtype=torch.float32)          # one band of corrected rows, re-used
+    npix_total = cfg['hp'] * cfg['wp'] * ratio * ratio * n_bands        # source band-pixels of the WHOLE raster
+
+    def step():
+        for band in range(n_bands):
+            src_local = RasterArray(src_planes[band], crs, src_local_tf, nodata=cfg['src_nodata'])
+            ref_ra = RasterArray(ref_planes[band], crs, ref_global_tf, nodata=NAN)
+            fuse_refspace_sharded(model, src_local, ref_ra, bands, out=out)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    stop, samples = threading.Event(), []
+    sampler = threading.Thread(target=_clock_sampler, args=(stop, samples, local_rank), daemon=True)
+    sampler.start()
+    lib.hb_reset_launch_count()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for _ in range(args.steps):
+        step()
+    end.record()
+    barrier()
+    launches = lib.hb_launch_count()
+    elapsed_ms = start.elapsed_time(end)
+    with KernelTimer() as timer:
+        step()
+        kernel_ms = timer.results()
+    stop.set()
+    sampler.join(timeout=2)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = npix_total * args.steps / (elapsed_ms * 1e-3) / 1e6
+    peak_gbs, peak_src = _peak()
+    b_in = src_planes[0].element_size()
+    local_px = src_planes[0].numel()
+    alg = {'hb_upsample_apply': local_px * (b_in + 4), 'hb_downsample_average': local_px * b_in}
+    per_kernel = {k: {'launches': len(v), 'ms_avg': round(sum(v) / len(v), 4)} for k, v in kernel_ms.items()}
+    for k, d in per_kernel.items():
+        if k in alg:
+            d['gbs'] = round(alg[k] / (d['ms_avg'] * 1e-3) / 1e9, 1)
+    dominant = max((k for k in kernel_ms if k in alg), key=lambda k: sum(kernel_ms[k]))
+    achieved = alg[dominant] / (sum(kernel_ms[dominant]) / len(kernel_ms[dominant]) * 1e-3) / 1e9
+    if rank == 0:
+        line = {
+            'metric': 'fit+apply Mpix/s', 'value': round(value, 1), 'unit': 'Mpix/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(elapsed_ms / args.steps, 4),
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': cfg['desc'], 'kernel_model': cfg['model'], 'kernel_shape': list(cfg['kernel_shape']),
+                       'proc_crs': cfg['proc_crs'], 'bands': n_bands, 'src_dtype': cfg['dtype'],
+                       'pixels_per_step': int(npix_total),
+                       'sharding': f'row bands of {cfg["hp"]} proc rows over {world} rank(s); per band one all-gather '
+                                   f'of the {cfg["hp"]}x{cfg["wp"]} float32 proc-grid plane',
+                       'l2': 'inputs larger than L2 (no flush needed)'},
+            'clocks': _clocks_summary(samples), 'e2e': None, 'gpu_launches': int(launches),
+            'roofline': {'bound': 'hbm', 'kernel': dominant, 'achieved': round(achieved, 1), 'peak': peak_gbs,
+                         'peak_source': peak_src, 'unit': 'GB/s', 'frac': round(achieved / peak_gbs, 4),
+                         'traffic': None, 'algorithmic_bytes_per_launch': int(alg[dominant]), 'kernels': per_kernel},
+            'cpu_baseline': None,
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -151,6 +304,9 @@ def main():
         return
     if world == 1:
         os.environ.setdefault('OMP_NUM_THREADS', str(os.cpu_count() or 1))
+    if cfg.get('sharded'):
+        run_sharded(args, cfg, rank, world, local_rank)
+        return
 
     import torch
     import torch.distributed as dist
@@ -258,11 +414,7 @@ def main():
         del src_host, ref_host, out_host
 
     # ---- roofline of the dominant kernel (per-launch CUDA-event durations from the timed region) ---------------------
-    peaks_path = REPO / 'MEASURED_PEAKS.json'
-    if peaks_path.exists():
-        peak_gbs, peak_src = float(json.loads(peaks_path.read_text())['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
-    else:
-        peak_gbs, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    peak_gbs, peak_src = _peak()
     b_in = src_ra.array.element_size()
     band_px = npix // cfg['bands']
     proc_px = (cfg['hp'] * cfg['wp']) if cfg['proc_crs'] == 'ref' else band_px
@@ -283,7 +435,8 @@ def main():
         if k in alg_bytes:
             d['gbs'] = round(alg_bytes[k] / (d['ms_avg'] * 1e-3) / 1e9, 1)
     roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': round(achieved, 1), 'peak': peak_gbs,
-                'peak_source': peak_src, 'unit': 'GB/s', 'frac': round(achieved / peak_gbs, 4), 'traffic': None,
+                'peak_source': peak_src, 'unit': 'GB/s', 'frac': round(achieved / peak_gbs, 4),
+                'traffic': _ncu_traffic(args.workload, dominant),
                 'algorithmic_bytes_per_launch': int(alg_bytes[dominant]),
                 'share_of_step': round(sum(kernel_ms[dominant]) / serial_ms, 3),
                 'timing': 'CUDA events around every launch, K steps with the bands serialised on one stream '
@@ -316,7 +469,7 @@ def main():
             'metric': 'fit+apply Mpix/s', 'value': round(value, 1), 'unit': 'Mpix/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(elapsed_ms / args.steps, 4),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': cfg['desc'], 'model': cfg['model'], 'kernel_shape': list(cfg['kernel_shape']),
+            'config': {'workload': cfg['desc'], 'kernel_model': cfg['model'], 'kernel_shape': list(cfg['kernel_shape']),
                        'proc_crs': cfg['proc_crs'], 'bands': cfg['bands'], 'src_dtype': cfg['dtype'],
                        'pixels_per_step_per_gpu': int(npix), 'sharding': 'one source image per GPU, no collective',
                        'l2': 'inputs larger than L2 (no flush needed)'},

@@ -148,16 +148,29 @@ downsample_average_kernel(const T *__restrict__ src, long hs, long ws, NoData nd
 #pragma unroll
             for (int k = 0; k < 8; k++) ndc[k] = 0;
             const T *p = src + ya * ws + c;
-#pragma unroll 10
-            for (long y = ya; y < yb; y++, p += ws) {
-                uint32_t w[4];
+            // rows are fetched kDsBatch at a time, ALL loads of a batch issued before the first is used (the rare
+            // nodata branch below would otherwise keep the compiler from hoisting loads: 1-3 in flight per thread)
+            constexpr int kDsBatch = 10;
+            for (long yb0 = ya; yb0 < yb; yb0 += kDsBatch) {
+            uint32_t wb[kDsBatch][NW];
+#pragma unroll
+            for (int u = 0; u < kDsBatch; u++) {
+                const T *pu = p + (yb0 + u < yb ? (long)u : yb - 1 - yb0) * ws;      // (clamped: re-reads the last row)
                 if (sizeof(T) == 2) {
-                    const uint4 v = hb_ldg_stream16(p);
-                    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+                    const uint4 v = hb_ldg_stream16(pu);
+                    wb[u][0] = v.x; wb[u][1] = v.y; wb[u][NW > 2 ? 2 : 0] = v.z; wb[u][NW > 3 ? 3 : 0] = v.w;
                 } else {
-                    const uint2 v = hb_ldg_stream8(p);
-                    w[0] = v.x; w[1] = v.y; w[2] = 0; w[3] = 0;
+                    const uint2 v = hb_ldg_stream8(pu);
+                    wb[u][0] = v.x; wb[u][1] = v.y;
                 }
+            }
+            p += (long)kDsBatch * ws;
+#pragma unroll
+            for (int u = 0; u < kDsBatch; u++) {
+                if (yb0 + u >= yb) break;
+                uint32_t w[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) w[i] = (i < NW) ? wb[u][i] : 0u;
                 uint32_t anyz = 0;
 #pragma unroll
                 for (int i = 0; i < NW; i++) {
@@ -182,6 +195,7 @@ downsample_average_kernel(const T *__restrict__ src, long hs, long ws, NoData nd
                         ndc[k] += (v == (uint32_t)ndk.ivalue) ? 1u : 0u;
                     }
                 }
+            }
             }
             const uint32_t nrows = (uint32_t)(yb > ya ? yb - ya : 0);
 #pragma unroll

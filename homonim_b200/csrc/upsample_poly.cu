@@ -196,65 +196,83 @@ template <> struct SrcQuad<float> {
 // =====================================================================================================================
 // Cell (ky, kx), ky in [-1, hp], kx in [-1, wp]: the destination pixels whose first tap is (ky - 1, kx - 1).
 // flags[(ky + 1) * (wp + 2) + (kx + 1)]: bit0 CLEAN, bit1 DEAD, bit2 OUT (DEAD because the centre pixels are out of range).
-// GUARD (apply mode): a cell is only CLEAN if the gain band's taps are within a factor 16 of each other.  Next to a
+// GUARD (apply mode): a cell is only CLEAN if the gain band's taps are within a factor ~16 of each other.  Next to a
 // parameter spike (an ill-conditioned solve of the reference) corr = gain*src + offset cancels heavily
 // and float32 interpolation errors would be amplified past 1e-4; such cells take the double-precision fix-up instead.
-template <int NB, bool GUARD>
-__global__ void upsample_prep_kernel(const float *__restrict__ coarse, long hp, long wp, float2 *__restrict__ coarse2,
-                                     uint8_t *__restrict__ flags, int *__restrict__ list, int *__restrict__ count)
-{
-    const long fw = wp + 2, n = (hp + 2) * fw, plane = hp * wp;
-    const long n_round = (n + 31) / 32 * 32;                // whole warps stay in the loop (for the ballot below)
-    for (long idx0 = (long)blockIdx.x * blockDim.x + threadIdx.x; idx0 < n_round; idx0 += (long)gridDim.x * blockDim.x) {
-        const bool live = idx0 < n;
-        const long idx = live ? idx0 : n - 1;
-        const long ky = idx / fw - 1, kx = idx % fw - 1;
-        // validity bits of the 4x4 tap window: bit (j*4+i) of `all` = valid in every band, of `any` = valid in some band
-        unsigned all = 0, any = 0, inr = 0;
-        float gmin = 3.0e38f, gmax = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const long y = ky - 1 + j, x = kx - 1 + i;
-                if (y >= 0 && y < hp && x >= 0 && x < wp) {
-                    const float g0 = __ldg(coarse + y * wp + x);
-                    const float g1 = (NB > 1) ? __ldg(coarse + plane + y * wp + x) : g0;
-                    inr |= 1u << (j * 4 + i);
-                    // (an infinite tap is data for GDAL; the fast path cannot multiply it by a zero weight: not CLEAN)
-                    if (isfinite(g0) && isfinite(g1)) all |= 1u << (j * 4 + i);
-                    if (!isnan(g0) || !isnan(g1)) any |= 1u << (j * 4 + i);
-                    if (GUARD && !isnan(g0)) { gmin = fminf(gmin, fabsf(g0)); gmax = fmaxf(gmax, fabsf(g0)); }
-                }
-            }
-        }
+// One CTA = 32 x 8 cells.  The per-pixel facts (in range, usable in every band, valid in some band, binary exponent of
+// |gain|) of the 35 x 11 coarse pixels under the tile's tap windows are packed into 16-bit words in shared memory once;
+// every cell then combines its 4 x 4 window from there.
+constexpr int kPrepW = 32, kPrepH = 8;
 
-        // centre-pixel candidates of the cell's destination pixels: rows {ky, ky+1} (+ ky-1 when ky == hp, GDAL's
-        // "cy == hs -> cy--" rule), same for the columns; window bit (j, i) is row ky-1+j, column kx-1+i
-        unsigned rows_m = 0x6u, cols_m = 0x6u;                  // j (i) in {1, 2}
-        if (ky == hp) rows_m |= 0x1u;
-        if (kx == wp) cols_m |= 0x1u;
-        unsigned cand = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if ((rows_m >> j) & 1u) cand |= (cols_m & 0xFu) << (j * 4);
-        const bool dead = (any & cand) == 0;                  // no destination pixel of the cell has a valid centre
-        const bool outr = (inr & cand) == 0;                  // ... because no centre candidate is inside the raster
-        // CLEAN: every tap inside the raster is usable in every band (taps outside it are handled by the edge weights)
-        const bool clean = !dead && (all == inr) && (!GUARD || gmax <= 16.0f * gmin);
-        if (live) flags[idx] = (uint8_t)((clean ? 1 : 0) | (dead ? 2 : 0) | (outr ? 4 : 0));
-        // append the DIRTY cells: one atomic per warp
-        const bool dirty = live && !clean && !dead;
-        const unsigned vote = __ballot_sync(0xffffffffu, dirty);
-        if (vote) {
-            const int lane = threadIdx.x & 31, leader = __ffs(vote) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(count, __popc(vote));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (dirty) list[base + __popc(vote & ((1u << lane) - 1u))] = (int)idx;
+template <int NB, bool GUARD>
+__global__ void __launch_bounds__(kPrepW * kPrepH)
+upsample_prep_kernel(const float *__restrict__ coarse, long hp, long wp, float2 *__restrict__ coarse2,
+                     uint8_t *__restrict__ flags, int *__restrict__ list, int *__restrict__ count)
+{
+    constexpr int TW = kPrepW + 3, TH = kPrepH + 3;
+    __shared__ unsigned short s_px[TH][TW + 1];
+    const long fw = wp + 2, plane = hp * wp;
+    const long ky0 = (long)blockIdx.y * kPrepH - 1, kx0 = (long)blockIdx.x * kPrepW - 1;   // first cell of the tile
+    // pixel tile: rows ky0 - 1 .. ky0 + kPrepH + 1, columns kx0 - 1 .. kx0 + kPrepW + 1
+    for (int i = threadIdx.x; i < TW * TH; i += kPrepW * kPrepH) {
+        const int ty = i / TW, tx = i % TW;
+        const long y = ky0 - 1 + ty, x = kx0 - 1 + tx;
+        unsigned v = 0;
+        if (y >= 0 && y < hp && x >= 0 && x < wp) {
+            const float g0 = __ldg(coarse + y * wp + x);
+            const float g1 = (NB > 1) ? __ldg(coarse + plane + y * wp + x) : g0;
+            // (an infinite tap is data for GDAL; the fast path cannot multiply it by a zero weight: not usable)
+            v = 4u | ((isfinite(g0) && isfinite(g1)) ? 1u : 0u) | ((!isnan(g0) || !isnan(g1)) ? 2u : 0u);
+            if (!isnan(g0)) v |= 8u | (((__float_as_uint(g0) >> 23) & 0xFFu) << 8);
+            // the interleaved copy is written by the tile that owns the pixel as a cell
+            if (NB == 2 && ty >= 1 && ty <= kPrepH && tx >= 1 && tx <= kPrepW) coarse2[y * wp + x] = make_float2(g0, g1);
         }
-        if (NB == 2 && live && ky >= 0 && ky < hp && kx >= 0 && kx < wp)
-            coarse2[ky * wp + kx] = make_float2(__ldg(coarse + ky * wp + kx), __ldg(coarse + plane + ky * wp + kx));
+        s_px[ty][tx] = (unsigned short)v;
+    }
+    __syncthreads();
+    const int cx = threadIdx.x % kPrepW, cy = threadIdx.x / kPrepW;
+    const long ky = ky0 + cy, kx = kx0 + cx;
+    const bool live = (ky <= hp) && (kx <= wp);
+    // bit (j*4+i) of `all` = usable in every band, of `any` = valid in some band, of `inr` = inside the raster
+    unsigned all = 0, any = 0, inr = 0;
+    int emin = 255, emax = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const unsigned v = s_px[cy + j][cx + i];
+            const unsigned bit = 1u << (j * 4 + i);
+            if (v & 1u) all |= bit;
+            if (v & 2u) any |= bit;
+            if (v & 4u) inr |= bit;
+            if (GUARD && (v & 8u)) { emin = min(emin, (int)(v >> 8)); emax = max(emax, (int)(v >> 8)); }
+        }
+    }
+    // centre-pixel candidates of the cell's destination pixels: rows {ky, ky+1} (+ ky-1 when ky == hp, GDAL's
+    // "cy == hs -> cy--" rule), same for the columns; window bit (j, i) is row ky-1+j, column kx-1+i
+    unsigned rows_m = 0x6u, cols_m = 0x6u;                      // j (i) in {1, 2}
+    if (ky == hp) rows_m |= 0x1u;
+    if (kx == wp) cols_m |= 0x1u;
+    unsigned cand = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if ((rows_m >> j) & 1u) cand |= (cols_m & 0xFu) << (j * 4);
+    const bool dead = (any & cand) == 0;                      // no destination pixel of the cell has a valid centre
+    const bool outr = (inr & cand) == 0;                      // ... because no centre candidate is inside the raster
+    // CLEAN: every tap inside the raster is usable in every band (taps outside it are handled by the edge weights);
+    // GUARD: the gains' binary exponents differ by <= 3, i.e. their magnitudes by less than a factor 16
+    const bool clean = !dead && (all == inr) && (!GUARD || emax - emin <= 3);
+    const long idx = (ky + 1) * fw + (kx + 1);
+    if (live) flags[idx] = (uint8_t)((clean ? 1 : 0) | (dead ? 2 : 0) | (outr ? 4 : 0));
+    // append the DIRTY cells: one atomic per warp
+    const bool dirty = live && !clean && !dead;
+    const unsigned vote = __ballot_sync(0xffffffffu, dirty);
+    if (vote) {
+        const int lane = threadIdx.x & 31, leader = __ffs(vote) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(count, __popc(vote));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (dirty) list[base + __popc(vote & ((1u << lane) - 1u))] = (int)idx;
     }
 }
 
@@ -655,11 +673,10 @@ int launch_poly(const void *src, NoData nd, const float *coarse, const UpPolyGeo
     float2 *coarse2 = (float2 *)(wsb + off_c2);
     HB_CUDA_OK(cudaMemsetAsync(count, 0, 16, stream));
     {
-        long blocks = (ncell + 255) / 256;
-        const long cap = (long)hb_sm_count() * 8;
-        if (blocks > cap) blocks = cap;
-        upsample_prep_kernel<NB, APPLY><<<(unsigned)blocks, 256, 0, stream>>>(coarse, g.hp, g.wp, coarse2, flags, list,
-                                                                             count);
+        dim3 pgrid((unsigned)((fw + kPrepW - 1) / kPrepW), (unsigned)((g.hp + 2 + kPrepH - 1) / kPrepH));
+        HB_REQUIRE(pgrid.y <= 65535u, "up-sampling: coarse raster has too many rows (%ld)", g.hp);
+        upsample_prep_kernel<NB, APPLY><<<pgrid, kPrepW * kPrepH, 0, stream>>>(coarse, g.hp, g.wp, coarse2, flags, list,
+                                                                              count);
         HB_LAUNCH_OK("upsample_prep_kernel");
     }
     {

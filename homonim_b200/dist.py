@@ -141,7 +141,7 @@ def source_band_for_proc_rows(src_ra_shape: Tuple[int, int], src_transform: Affi
     return r0, max(r1, r0)
 
 
-def fuse_refspace_sharded(model, src_local: RasterArray, ref_ra: RasterArray, bands: RowBands, group=None
+def fuse_refspace_sharded(model, src_local: RasterArray, ref_ra: RasterArray, bands: RowBands, group=None, out=None
                           ) -> Tuple[RasterArray, RasterArray]:
     """
     proc_crs = ref fit + apply of ONE band of a raster that is sharded by rows (configuration C5a).
@@ -149,6 +149,7 @@ def fuse_refspace_sharded(model, src_local: RasterArray, ref_ra: RasterArray, ba
     ``src_local`` holds this rank's source rows (its transform already points at its first row); ``ref_ra`` is the
     whole (replicated) reference band on the proc grid; ``bands`` partitions the proc-grid rows.  Returns
     ``(corr_local, param_ra)``: the corrected rows of this rank and the (global, identical on every rank) parameters.
+    ``out`` (optional): float32 CUDA tensor to receive the corrected rows.
     """
     from homonim_b200 import kernel_model as km
     rank = dist.get_rank(group)
@@ -164,7 +165,8 @@ def fuse_refspace_sharded(model, src_local: RasterArray, ref_ra: RasterArray, ba
     params = model._fit_planes(src_ds, float('nan'), ref_t, ref_ra.nodata)
     param_ra = RasterArray(params, ref_ra.crs, ref_ra.transform, nodata=float('nan'))
     # 4. apply to my source rows
-    corr_local = model.apply(RasterArray(src_t, src_local.crs, src_local.transform, nodata=src_local.nodata), param_ra)
+    corr_local = model.apply(RasterArray(src_t, src_local.crs, src_local.transform, nodata=src_local.nodata), param_ra,
+                             out=out)
     return corr_local, param_ra
 
 
