@@ -47,6 +47,57 @@ struct DevBuf {
 };
 }  // namespace
 
+// One (band, block) of RasterFuse._process_block (homonim/fuse.py:304-307) for proc_crs = ref on DEVICE buffers:
+// down-sample -> [block normalisation] -> fit -> [in-paint + refit] -> up-sample + apply, all enqueued on `stream`.
+extern "C" int hb_fuse_refspace(const void *src_dev, int src_dtype, long hs, long ws, int src_has_nodata,
+                                double src_nodata, const float *ref_dev, long hr, long wr, int ref_has_nodata,
+                                double ref_nodata, double sx, double ox, double sy, double oy, int model, int kh, int kw,
+                                int want_r2, int do_inpaint, double r2_thresh, float *corr_dev, float *params_dev,
+                                void *stream)
+{
+    HB_REQUIRE(src_dev && ref_dev && corr_dev && hs > 0 && ws > 0 && hr > 0 && wr > 0, "hb_fuse_refspace: bad arguments");
+    HB_REQUIRE(src_dtype == HB_U8 || src_dtype == HB_U16 || src_dtype == HB_F32, "hb_fuse_refspace: bad dtype");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool inpaint = (model == HB_MODEL_GAIN_OFFSET) && do_inpaint;
+    const int r2 = (want_r2 || inpaint) ? 1 : 0;
+    const size_t nr = (size_t)hr * wr;
+    const double nan = __builtin_nan("");
+
+    DevBuf d_ds(st), d_params(st), d_sums(st), d_norm(st), d_work(st), d_work2(st);
+    HB_CUDA_OK(d_ds.alloc(nr * sizeof(float)));
+    float *params = params_dev;
+    if (params == nullptr) {
+        HB_CUDA_OK(d_params.alloc(nr * sizeof(float) * 3));
+        params = (float *)d_params.p;
+    }
+    int rc = hb_downsample_average(src_dev, src_dtype, hs, ws, src_has_nodata, src_nodata, (float *)d_ds.p, hr, wr, sx,
+                                   ox, sy, oy, stream);
+    if (rc) return rc;
+    const double *norm = nullptr;
+    if (model == HB_MODEL_GAIN_BLK_OFFSET) {
+        const size_t wb = hb_block_norm_workspace_bytes((long)nr);
+        HB_CUDA_OK(d_norm.alloc(2 * sizeof(double)));
+        HB_CUDA_OK(d_work.alloc(wb));
+        rc = hb_block_norm((const float *)d_ds.p, 1, nan, ref_dev, ref_has_nodata, ref_nodata, (long)nr,
+                           (double *)d_norm.p, d_work.p, wb, stream);
+        if (rc) return rc;
+        norm = (const double *)d_norm.p;
+    }
+    if (inpaint) HB_CUDA_OK(d_sums.alloc(nr * sizeof(float) * 3));
+    rc = hb_fit_same_grid((const float *)d_ds.p, 1, nan, ref_dev, ref_has_nodata, ref_nodata, hr, wr, model, kh, kw, r2,
+                          norm, params, inpaint ? (float *)d_sums.p : nullptr, stream);
+    if (rc) return rc;
+    if (inpaint) {
+        const size_t wb = hb_inpaint_workspace_bytes(hr, wr);
+        HB_CUDA_OK(d_work2.alloc(wb));
+        rc = hb_inpaint_refit(params, (const float *)d_sums.p, hr, wr, r2_thresh, 100.0, d_work2.p, wb, stream);
+        if (rc) return rc;
+    }
+    // source grid -> reference (param) grid is the inverse of the reference -> source map
+    return hb_upsample_apply(src_dev, src_dtype, hs, ws, src_has_nodata, src_nodata, params, hr, wr, 1.0 / sx, -ox / sx,
+                             1.0 / sy, -oy / sy, nullptr, corr_dev, stream);
+}
+
 // One (band, block) of RasterFuse._process_block (homonim/fuse.py:304-307) for proc_crs = ref, host buffers in/out.
 extern "C" int hb_fuse_refspace_host(const void *src_host, int src_dtype, long hs, long ws, int src_has_nodata,
                                      double src_nodata, const float *ref_host, long hr, long wr, int ref_has_nodata,
@@ -62,44 +113,17 @@ extern "C" int hb_fuse_refspace_host(const void *src_host, int src_dtype, long h
     const int r2 = (want_r2 || inpaint) ? 1 : 0;
     const size_t ns = (size_t)hs * ws, nr = (size_t)hr * wr;
     const size_t src_bytes = ns * hb_dtype_size(src_dtype);
-    const double nan = __builtin_nan("");
 
-    DevBuf d_src(st), d_ref(st), d_ds(st), d_params(st), d_sums(st), d_corr(st), d_norm(st), d_work(st), d_work2(st);
+    DevBuf d_src(st), d_ref(st), d_params(st), d_corr(st);
     HB_CUDA_OK(d_src.alloc(src_bytes));
     HB_CUDA_OK(d_ref.alloc(nr * sizeof(float)));
-    HB_CUDA_OK(d_ds.alloc(nr * sizeof(float)));
     HB_CUDA_OK(d_params.alloc(nr * sizeof(float) * 3));
     HB_CUDA_OK(d_corr.alloc(ns * sizeof(float)));
     HB_CUDA_OK(cudaMemcpyAsync(d_src.p, src_host, src_bytes, cudaMemcpyHostToDevice, st));
     HB_CUDA_OK(cudaMemcpyAsync(d_ref.p, ref_host, nr * sizeof(float), cudaMemcpyHostToDevice, st));
-
-    int rc = hb_downsample_average(d_src.p, src_dtype, hs, ws, src_has_nodata, src_nodata, (float *)d_ds.p, hr, wr, sx,
-                                   ox, sy, oy, stream);
-    if (rc) return rc;
-    const double *norm = nullptr;
-    if (model == HB_MODEL_GAIN_BLK_OFFSET) {
-        const size_t wb = hb_block_norm_workspace_bytes((long)nr);
-        HB_CUDA_OK(d_norm.alloc(2 * sizeof(double)));
-        HB_CUDA_OK(d_work.alloc(wb));
-        rc = hb_block_norm((const float *)d_ds.p, 1, nan, (const float *)d_ref.p, ref_has_nodata, ref_nodata, (long)nr,
-                           (double *)d_norm.p, d_work.p, wb, stream);
-        if (rc) return rc;
-        norm = (const double *)d_norm.p;
-    }
-    if (inpaint) HB_CUDA_OK(d_sums.alloc(nr * sizeof(float) * 3));
-    rc = hb_fit_same_grid((const float *)d_ds.p, 1, nan, (const float *)d_ref.p, ref_has_nodata, ref_nodata, hr, wr,
-                          model, kh, kw, r2, norm, (float *)d_params.p, inpaint ? (float *)d_sums.p : nullptr, stream);
-    if (rc) return rc;
-    if (inpaint) {
-        const size_t wb = hb_inpaint_workspace_bytes(hr, wr);
-        HB_CUDA_OK(d_work2.alloc(wb));
-        rc = hb_inpaint_refit((float *)d_params.p, (const float *)d_sums.p, hr, wr, r2_thresh, 100.0, d_work2.p, wb,
-                              stream);
-        if (rc) return rc;
-    }
-    // source grid -> reference (param) grid is the inverse of the reference -> source map
-    rc = hb_upsample_apply(d_src.p, src_dtype, hs, ws, src_has_nodata, src_nodata, (const float *)d_params.p, hr, wr,
-                           1.0 / sx, -ox / sx, 1.0 / sy, -oy / sy, nullptr, (float *)d_corr.p, stream);
+    const int rc = hb_fuse_refspace(d_src.p, src_dtype, hs, ws, src_has_nodata, src_nodata, (const float *)d_ref.p, hr, wr,
+                                    ref_has_nodata, ref_nodata, sx, ox, sy, oy, model, kh, kw, want_r2, do_inpaint,
+                                    r2_thresh, (float *)d_corr.p, (float *)d_params.p, stream);
     if (rc) return rc;
     HB_CUDA_OK(cudaMemcpyAsync(corr_host, d_corr.p, ns * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (params_host)

@@ -185,8 +185,8 @@ class RasterFuse:
         transform = ref_ra.transform * Affine.translation(col0, row0)
         return RasterArray(array, ref_ra.crs, transform, nodata=ref_ra.nodata)
 
-    def _process_band(self, band_i: int, model: KernelModel, out=None, stage: bool = False
-                      ) -> Tuple[RasterArray, RasterArray]:
+    def _process_band(self, band_i: int, model: KernelModel, out=None, stage: bool = False,
+                      want_params: bool = True) -> Tuple[RasterArray, Optional[RasterArray]]:
         """
         One band of reference fuse.py:295-319 (``_process_block`` with a single block): read -> fit -> apply.
         ``stage``: copy a host band to the device once up front (fit and apply both read it) and leave the results
@@ -196,6 +196,10 @@ class RasterFuse:
         ref_ra = self._ref_block(band_i)
         if stage and not src_ra.is_device:
             src_ra, ref_ra = src_ra.to_device(), ref_ra.to_device()
+        if isinstance(model, RefSpaceModel) and model.can_fuse(src_ra, ref_ra):
+            # fit + apply as one native call (same kernels, same order; the parameters are only materialised for the
+            # caller when a parameter raster was asked for)
+            return model.fuse(src_ra, ref_ra, out=out, want_params=want_params)
         param_ra = model.fit(src_ra, ref_ra)          # fuse.py:306
         corr_ra = model.apply(src_ra, param_ra, out=out)       # fuse.py:307
         return corr_ra, param_ra
@@ -256,11 +260,12 @@ class RasterFuse:
         def run_band(band_i):
             direct = (not to_host) and plain_f32       # the apply kernel writes its plane of corr_all itself
             corr_ra, param_ra = self._process_band(band_i, kernel_model, out=corr_all[band_i] if direct else None,
-                                                   stage=True)
+                                                   stage=True, want_params=param_filename is not None)
             if not direct:
                 plane = _convert_dtype(corr_ra, out_dtype, out_nodata)
                 corr_all[band_i].copy_(plane, non_blocking=True)
-            param_planes[band_i] = param_ra if (src_on_device or param_filename is None) else param_ra.to_host()
+            if param_ra is not None:
+                param_planes[band_i] = param_ra if (src_on_device or param_filename is None) else param_ra.to_host()
 
         # Bands are independent (the reference runs (band, block) jobs on a thread pool, fuse.py:396-408).  On the
         # GPU each band is enqueued on its own CUDA stream, so that the small latency-bound kernels of one band (fit
@@ -277,7 +282,7 @@ class RasterFuse:
                     run_band(band_i)
             for st in streams:
                 main.wait_stream(st)
-            for t in [corr_all] + [p.array for p in param_planes]:
+            for t in [corr_all] + [p.array for p in param_planes if p is not None]:
                 if is_tensor(t) and t.is_cuda:
                     t.record_stream(main)
         else:

@@ -403,6 +403,48 @@ class RefSpaceModel(KernelModel):
         params = self._fit_planes(src_ds, NAN, ref_t, ref_ra.nodata)                         # :482
         return RasterArray(_result(params, on_device), ref_ra.crs, ref_ra.transform, nodata=NAN)
 
+    def can_fuse(self, src_ra: RasterArray, ref_ra: RasterArray) -> bool:
+        """ True when fit + apply of this pair can run as ONE native call (`fuse`): the default resampling pair, no
+        partial-coverage masking, and no per-entry-point timer active. """
+        if self._mask_partial or KernelTimer.active is not None:
+            return False
+        if self._get_resampling(src_ra.res, ref_ra.res) != Resampling.average:
+            return False
+        return self._get_resampling(ref_ra.res, src_ra.res) == Resampling.cubic_spline
+
+    def fuse(self, src_ra: RasterArray, ref_ra: RasterArray, out=None, want_params: bool = False
+             ) -> Tuple[RasterArray, Optional[RasterArray]]:
+        """
+        ``apply(src_ra, fit(src_ra, ref_ra))`` -- one (band, block) of ``RasterFuse._process_block`` (fuse.py:304-307)
+        -- as a single native call (``hb_fuse_refspace``): the same kernels in the same order, without the host work
+        between them.  Returns ``(corr_ra, param_ra or None)``.
+        """
+        _require_torch()
+        on_device = (src_ra.is_device and ref_ra.is_device) or out is not None
+        src_t, ref_t = _to_device(src_ra.array), _to_device(ref_ra.array)
+        ref_t = _as_f32_plane(ref_t, ref_ra.nodata).contiguous()
+        hs, ws = src_ra.shape
+        hr, wr = ref_ra.shape
+        gm = grid_map(src_ra.transform, ref_ra.transform)         # reference grid -> source grid
+        corr = self._check_out(out, hs, ws, src_t.device)
+        want_r2 = self._wants_r2()
+        inpaint = self._model == Model.gain_offset and self._r2_inpaint_thresh is not None
+        params = None
+        if want_params:
+            params = torch.empty((3 if want_r2 else 2, hr, wr), dtype=torch.float32, device=src_t.device)
+        s_has, s_nd = _nodata_args(src_ra.nodata)
+        r_has, r_nd = _nodata_args(ref_ra.nodata)
+        kh, kw = self._kernel_shape
+        _call('hb_fuse_refspace', src_t.data_ptr(), _plane_code(src_t), hs, ws, s_has, s_nd, ref_t.data_ptr(), hr, wr,
+              r_has, r_nd, gm.sx, gm.ox, gm.sy, gm.oy, _MODEL_CODES[self._model], kh, kw, int(want_r2), int(inpaint),
+              float(self._r2_inpaint_thresh) if inpaint else 0.0, corr.data_ptr(),
+              params.data_ptr() if params is not None else None, _stream())
+        corr_ra = RasterArray(_result(corr, on_device), src_ra.crs, src_ra.transform, nodata=NAN)
+        param_ra = None
+        if params is not None:
+            param_ra = RasterArray(_result(params, on_device), ref_ra.crs, ref_ra.transform, nodata=NAN)
+        return corr_ra, param_ra
+
     def apply(self, src_ra: RasterArray, param_ra: RasterArray, out=None) -> RasterArray:
         _require_torch()
         lib = _native.lib()

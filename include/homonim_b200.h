@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 1
+#define HB_ABI_VERSION 2
 
 /* storage dtype of a source raster plane */
 enum { HB_U8 = 0, HB_U16 = 1, HB_F32 = 2 };
@@ -137,6 +137,19 @@ int hb_full_coverage_mask(const uint8_t *in_mask_dev, long hi, long wi, const fl
 /* validity mask of a raster plane as uint8 (RasterArray.mask / mask_ra, raster_array.py:298-327) */
 int hb_valid_mask(const void *src_dev, int src_dtype, long n, int has_nodata, double nodata, uint8_t *mask_dev,
                   void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * One (band, block) of RasterFuse._process_block (homonim/fuse.py:304-307: model.fit + model.apply) for proc_crs = ref
+ * with DEVICE pointers, in one call: hb_downsample_average -> [hb_block_norm] -> hb_fit_same_grid ->
+ * [hb_inpaint_refit] -> hb_upsample_apply, all enqueued on `stream` (asynchronous).  Device scratch is allocated with
+ * cudaMallocAsync on `stream`.  params_dev: optional [2|3][hr][wr] float32 output of the fitted parameters (3 planes
+ * when want_r2 != 0 or in-painting is on); may be NULL.  (sx, ox, sy, oy) maps REFERENCE-grid coordinates to
+ * SOURCE-grid coordinates.  r2_thresh is ignored unless model == HB_MODEL_GAIN_OFFSET and do_inpaint != 0.
+ * --------------------------------------------------------------------------------------------------------------- */
+int hb_fuse_refspace(const void *src_dev, int src_dtype, long hs, long ws, int src_has_nodata, double src_nodata,
+                     const float *ref_dev, long hr, long wr, int ref_has_nodata, double ref_nodata, double sx, double ox,
+                     double sy, double oy, int model, int kh, int kw, int want_r2, int do_inpaint, double r2_thresh,
+                     float *corr_dev, float *params_dev, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Host-buffer convenience entry point: one (band, block) of RasterFuse._process_block (homonim/fuse.py:304-307)

@@ -246,3 +246,26 @@ def test_grid_mismatch_raises():
         km.fit(ra50, ra100)
     with pytest.raises(ValueError):
         km.apply(ra50, ra100)
+
+
+@pytest.mark.parametrize('model, kernel_shape, thresh', [
+    (Model.gain_offset, (15, 15), 0.25), (Model.gain_blk_offset, (5, 5), None), (Model.gain, (1, 1), None),
+])
+def test_fused_call_equals_fit_then_apply(model, kernel_shape, thresh):
+    """ RefSpaceModel.fuse (one hb_fuse_refspace call per band, what RasterFuse.process uses) runs the same kernels in
+    the same order as fit() followed by apply(): bit-identical corrected pixels and parameters. """
+    from homonim_b200 import RasterArray, RefSpaceModel
+    src_ra, ref_ra = make_pair(110, 93, 20, bands=1, dtype='uint16', mu=3000.0, seed=9, device='cuda', src_nodata=0)
+    src = RasterArray(src_ra.array[0].contiguous(), src_ra.crs, src_ra.transform, nodata=0)
+    ref = RasterArray(ref_ra.array[0].contiguous(), ref_ra.crs, ref_ra.transform, nodata=float('nan'))
+    km = RefSpaceModel(model, kernel_shape, find_r2=True, r2_inpaint_thresh=thresh)
+    assert km.can_fuse(src, ref)
+    params = km.fit(src, ref)
+    corr = km.apply(src, params)
+    corr_f, params_f = km.fuse(src, ref, want_params=True)
+    assert torch.equal(corr_f.array.nan_to_num(-1.0), corr.array.nan_to_num(-1.0))
+    assert torch.equal(torch.isnan(corr_f.array), torch.isnan(corr.array))
+    assert torch.equal(params_f.array.nan_to_num(-7.0, posinf=-8.0, neginf=-9.0),
+                       params.array.nan_to_num(-7.0, posinf=-8.0, neginf=-9.0))
+    corr_n, none = km.fuse(src, ref)
+    assert none is None and torch.equal(corr_n.array.nan_to_num(-1.0), corr.array.nan_to_num(-1.0))
