@@ -21,7 +21,14 @@ constexpr int kThreads = 256;
 // 1. average down-sampling
 // =====================================================================================================================
 constexpr int kDsVec = 8;                        // source pixels per thread per row
-constexpr int kDsSpan = kThreads * kDsVec;       // source columns staged per CTA
+#ifndef HB_DS_THREADS
+#define HB_DS_THREADS 256
+#endif
+#ifndef HB_DS_MIN_CTAS
+#define HB_DS_MIN_CTAS 3
+#endif
+constexpr int kDsThreads = HB_DS_THREADS;
+constexpr int kDsSpan = kDsThreads * kDsVec;     // source columns staged per CTA
 
 template <typename T> struct Raw8;               // 8 consecutive source pixels, vector-loaded
 template <> struct Raw8<uint16_t> {
@@ -87,7 +94,7 @@ __device__ __forceinline__ void ds_fetch(const T *row, long c, long ws, T (&v)[8
 // <= 2 fractionally covered rows are added in double).  Phase 2: one thread per destination pixel combines its
 // footprint columns from shared memory with the fractional edge weights.
 template <typename T, bool ALIGNED>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kDsThreads, HB_DS_MIN_CTAS)
 downsample_average_kernel(const T *__restrict__ src, long hs, long ws, NoData nd, float *__restrict__ dst, long hd,
                           long wd, double sx, double ox, double sy, double oy, int ndc, int chunks)
 {
@@ -110,7 +117,7 @@ downsample_average_kernel(const T *__restrict__ src, long hs, long ws, NoData nd
     if (iy0u == iy1u) iy1u++;                                   // footprint inside one source row
     const long iy0 = max(iy0u, 0L), iy1 = min(iy1u, hs);
     if (iy0 >= iy1) {
-        for (long j = j0 + t; j < j1; j += kThreads) dst[i * wd + j] = qnan;
+        for (long j = j0 + t; j < j1; j += kDsThreads) dst[i * wd + j] = qnan;
         return;
     }
     const double wy_first = (iy0u + 1 == iy1u) ? 1.0 : 1.0 - (y_min - (double)iy0u);
@@ -257,7 +264,7 @@ downsample_average_kernel(const T *__restrict__ src, long hs, long ws, NoData nd
     __syncthreads();
 
     // ---- phase 2: one thread per destination pixel ----------------------------------------------------------------
-    for (long j = j0 + t; j < j1; j += kThreads) {
+    for (long j = j0 + t; j < j1; j += kDsThreads) {
         const double x_min = sx * (double)j + ox, x_max = sx * (double)(j + 1) + ox;
         const long ix0u = (long)floor(x_min + 1e-10);
         long ix1u = (long)ceil(x_max - 1e-10);
@@ -296,10 +303,10 @@ int launch_downsample(const void *src, long hs, long ws, NoData nd, float *dst, 
     HB_REQUIRE(blocks > 0 && blocks < 2147483647L, "hb_downsample_average: grid too large");
     const bool aligned = ((ws * (long)sizeof(T)) % 16 == 0) && (((uintptr_t)src) % 16 == 0);
     if (aligned)
-        downsample_average_kernel<T, true><<<(unsigned)blocks, kThreads, 0, stream>>>(
+        downsample_average_kernel<T, true><<<(unsigned)blocks, kDsThreads, 0, stream>>>(
             (const T *)src, hs, ws, nd, dst, hd, wd, sx, ox, sy, oy, (int)ndc, (int)chunks);
     else
-        downsample_average_kernel<T, false><<<(unsigned)blocks, kThreads, 0, stream>>>(
+        downsample_average_kernel<T, false><<<(unsigned)blocks, kDsThreads, 0, stream>>>(
             (const T *)src, hs, ws, nd, dst, hd, wd, sx, ox, sy, oy, (int)ndc, (int)chunks);
     HB_LAUNCH_OK("downsample_average_kernel");
     return 0;
