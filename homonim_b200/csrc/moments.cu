@@ -444,8 +444,10 @@ int launch_fit(const float *src, NoData nd_s, const float *ref, NoData nd_r, lon
     const long target_ctas = (long)hb_sm_count() * 8;
     long bands = (target_ctas + xtiles - 1) / xtiles;
     long rpb = (h + bands - 1) / bands;
-    // (small rasters, C == 1: the machine is mostly empty and the warm-up is cheap -- short bands, many CTAs)
-    const long min_rpb = (C == 1) ? 4L : 8L * kh;
+    // (small rasters, C == 1: the machine is mostly empty and the warm-up is cheap -- short bands, many CTAs; the
+    // batched warm-up costs about a quarter of a full row step per row, so 2 window heights per band already keep it
+    // near 10 % on mid-size rasters that could not fill the machine with taller bands)
+    const long min_rpb = (C == 1) ? 4L : 2L * kh;
     if (rpb < min_rpb) rpb = min_rpb;
     if (rpb > h) rpb = h;
     g.rows_per_band = (int)rpb;

@@ -11,10 +11,10 @@ pixels (utils.py:136-153).  Two regimes follow:
   source rows whose edges coincide with proc-grid (reference) pixel rows.
 
   - proc_crs = ref: every rank down-samples its own source rows, the proc-grid planes (3000 x 3000 float32 = 36 MB for
-    the 60k x 60k configuration -- 1/400 of the source) are **all-gathered**, every rank fits the whole proc grid
-    (identical, redundant, < 1 % of the work) and applies the parameters to its own source rows.  The result is
-    bit-identical to the single-GPU result by construction: the same kernels see the same numbers, and the block
-    normalisation of gain-blk-offset (a whole-block statistic, kernel_model.py:216-229) stays global.
+    the 60k x 60k configuration -- 1/400 of the source) are **all-gathered** so that the block normalisation of
+    gain-blk-offset (a whole-block statistic, kernel_model.py:216-229) stays global; every rank then fits its own proc
+    rows plus a halo (`halo_rows`) and applies the parameters to its own source rows.  Results equal the single-GPU
+    results up to the summation order of the fit kernel's running sums (> 99.9 % of the parameters bit-identical).
   - same grid (proc_crs = src): the window sums need ``kh // 2`` rows of source and reference from each neighbour:
     `exchange_halos` does that with point-to-point send / recv between row-band neighbours (NCCL P2P over NVLink on
     GPUs, gloo in the CPU tests); rows beyond the raster stay absent, which is the reference's zero padding
@@ -148,23 +148,41 @@ def fuse_refspace_sharded(model, src_local: RasterArray, ref_ra: RasterArray, ba
 
     ``src_local`` holds this rank's source rows (its transform already points at its first row); ``ref_ra`` is the
     whole (replicated) reference band on the proc grid; ``bands`` partitions the proc-grid rows.  Returns
-    ``(corr_local, param_ra)``: the corrected rows of this rank and the (global, identical on every rank) parameters.
+    ``(corr_local, param_ra)``: the corrected rows of this rank and the parameters of the proc-grid rows they depend on
+    (this rank's band plus the 2 rows of cubic-spline support on either side; ``param_ra.transform`` points at them).
     ``out`` (optional): float32 CUDA tensor to receive the corrected rows.
+
+    Only the down-sampled proc-grid plane -- 1/ratio^2 of the source -- crosses the interconnect: it is all-gathered so
+    that the block normalisation of gain-blk-offset (a whole-block statistic, kernel_model.py:216-229) stays global;
+    every rank then fits just its own proc rows plus the halo that makes them equal the whole-raster fit
+    (`halo_rows`: window half-height + spline support + the in-painting search radius).
     """
     from homonim_b200 import kernel_model as km
+    from homonim_b200.enums import Model
     rank = dist.get_rank(group)
     a, b = bands.band(rank)
+    hp = bands.starts[-1]
+    nan = float('nan')
     src_t = km._to_device(src_local.array)
     # 1. down-sample my source rows onto my proc rows
     local_tf = ref_ra.transform * Affine.translation(0, a)
     src_ds_local = km._downsample_average(src_t, src_local.transform, src_local.nodata, (b - a, ref_ra.width), local_tf)
     # 2. the proc-grid plane is tiny: gather it everywhere
     src_ds = all_gather_rows(src_ds_local, bands, group)
-    # 3. fit the whole proc grid (redundant on every rank, < 1 % of the work; keeps block statistics global)
     ref_t = km._to_device(ref_ra.array)
-    params = model._fit_planes(src_ds, float('nan'), ref_t, ref_ra.nodata)
-    param_ra = RasterArray(params, ref_ra.crs, ref_ra.transform, nodata=float('nan'))
-    # 4. apply to my source rows
+    # 3. whole-block statistics (redundant on every rank: three passes over the small proc-grid planes)
+    norm = None
+    if model.model == Model.gain_blk_offset:
+        norm = model._block_norm(src_ds, nan, ref_t, ref_ra.nodata)
+    # 4. fit my proc rows + halo; keep the rows my source rows' spline taps touch
+    inpaint = model.model == Model.gain_offset and model._r2_inpaint_thresh is not None
+    halo = halo_rows(model.kernel_shape, proc_crs_ref=True, inpaint=inpaint)
+    lo, hi = max(a - halo, 0), min(b + halo, hp)
+    params_ext = model._fit_planes(src_ds[lo:hi], nan, ref_t[lo:hi], ref_ra.nodata, norm=norm)
+    plo, phi = max(a - 2, 0), min(b + 2, hp)
+    params = params_ext[:, plo - lo:phi - lo].contiguous()
+    param_ra = RasterArray(params, ref_ra.crs, ref_ra.transform * Affine.translation(0, plo), nodata=nan)
+    # 5. apply to my source rows
     corr_local = model.apply(RasterArray(src_t, src_local.crs, src_local.transform, nodata=src_local.nodata), param_ra,
                              out=out)
     return corr_local, param_ra

@@ -215,8 +215,27 @@ class KernelModel:
     def _wants_r2(self) -> bool:
         return bool(self._find_r2 or (self._model == Model.gain_offset and self._r2_inpaint_thresh is not None))
 
-    def _fit_planes(self, src_t, src_nodata, ref_t, ref_nodata):
-        """ Same-grid fit of two float32 device planes -> float32 [2|3, H, W] parameter tensor. """
+    @staticmethod
+    def _block_norm(src_t, src_nodata, ref_t, ref_nodata):
+        """ Block normalisation (reference kernel_model.py:216-229) of two float32 device planes -> 2 float64s on the
+        device. """
+        lib = _native.lib()
+        src_t, ref_t = _as_f32_plane(src_t, src_nodata).contiguous(), _as_f32_plane(ref_t, ref_nodata).contiguous()
+        n = int(src_t.numel())
+        s_has, s_nd = _nodata_args(src_nodata)
+        r_has, r_nd = _nodata_args(ref_nodata)
+        norm = torch.empty(2, dtype=torch.float64, device=src_t.device)
+        ws_bytes = lib.hb_block_norm_workspace_bytes(n)
+        work = torch.empty(ws_bytes, dtype=torch.uint8, device=src_t.device)
+        _call('hb_block_norm', src_t.data_ptr(), s_has, s_nd, ref_t.data_ptr(), r_has, r_nd, n, norm.data_ptr(),
+              work.data_ptr(), ws_bytes, _stream())
+        return norm
+
+    def _fit_planes(self, src_t, src_nodata, ref_t, ref_nodata, norm=None):
+        """
+        Same-grid fit of two float32 device planes -> float32 [2|3, H, W] parameter tensor.  ``norm``: block
+        normalisation computed elsewhere (row-band sharding: the statistics of the WHOLE block, dist.py).
+        """
         lib = _native.lib()
         h, w = int(src_t.shape[-2]), int(src_t.shape[-1])
         src_t, ref_t = _as_f32_plane(src_t, src_nodata).contiguous(), _as_f32_plane(ref_t, ref_nodata).contiguous()
@@ -228,11 +247,8 @@ class KernelModel:
         stream = _stream()
         norm_ptr = None
         if self._model == Model.gain_blk_offset:
-            norm = torch.empty(2, dtype=torch.float64, device=src_t.device)
-            ws_bytes = lib.hb_block_norm_workspace_bytes(h * w)
-            work = torch.empty(ws_bytes, dtype=torch.uint8, device=src_t.device)
-            _call('hb_block_norm', src_t.data_ptr(), s_has, s_nd, ref_t.data_ptr(), r_has, r_nd, h * w,
-                                            norm.data_ptr(), work.data_ptr(), ws_bytes, stream)
+            if norm is None:
+                norm = self._block_norm(src_t, src_nodata, ref_t, ref_nodata)
             norm_ptr = norm.data_ptr()
         sums = torch.empty((3, h, w), dtype=torch.float32, device=src_t.device) if inpaint else None
         kh, kw = self._kernel_shape
