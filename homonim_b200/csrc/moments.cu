@@ -18,6 +18,9 @@
 
 namespace {
 
+#ifndef HB_FIT_MIN_CTAS
+#define HB_FIT_MIN_CTAS 4
+#endif
 constexpr int kFitThreads = 128;
 constexpr int kFitWarps = kFitThreads / 32;
 constexpr int kMaxHalfW = 64;                    // kw <= 129
@@ -86,7 +89,7 @@ __device__ __forceinline__ void pixel_terms(float s, float r, bool valid, double
 
 // MODEL: HB_MODEL_*; WANT_R2: third band; NQ: number of double sums carried (2, 4 or 5); C: columns per thread
 template <int MODEL, bool WANT_R2, int NQ, int C, bool ALIGNED>
-__global__ void __launch_bounds__(kFitThreads)
+__global__ void __launch_bounds__(kFitThreads, (NQ >= 5 && C == 4) ? HB_FIT_MIN_CTAS - 1 : HB_FIT_MIN_CTAS)
 fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__restrict__ ref, NoData nd_r,
                      FitGeom g, const double *__restrict__ norm, float *__restrict__ params,
                      float *__restrict__ sums_out)
@@ -439,17 +442,30 @@ int launch_fit(const float *src, NoData nd_s, const float *ref, NoData nd_r, lon
     g.hw_al = ((hw + C - 1) / C) * C;
     g.tw_out = kFitThreads * C - 2 * g.hw_al;
     const long xtiles = (w + g.tw_out - 1) / g.tw_out;
-    // rows per band: enough CTAs to fill the machine a few times, but at least ~8 window heights per band so that the
-    // (kh - 1)-row warm-up of every band stays a small fraction of its work
-    const long target_ctas = (long)hb_sm_count() * 8;
-    long bands = (target_ctas + xtiles - 1) / xtiles;
-    long rpb = (h + bands - 1) / bands;
-    // (small rasters, C == 1: the machine is mostly empty and the warm-up is cheap -- short bands, many CTAs; the
-    // batched warm-up costs about a quarter of a full row step per row, so 2 window heights per band already keep it
-    // near 10 % on mid-size rasters that could not fill the machine with taller bands)
-    const long min_rpb = (C == 1) ? 4L : 2L * kh;
-    if (rpb < min_rpb) rpb = min_rpb;
+    // rows per band: every band re-reads (kh - 1) warm-up rows, so bands should be tall -- ~8 window heights -- unless
+    // that leaves SMs idle (mid-size rasters: go down to 2 window heights to get one CTA per resident slot).  Small
+    // rasters (C == 1) are latency-bound with the machine mostly empty: short bands, many CTAs.
+    const long slots = (long)hb_sm_count() * HB_FIT_MIN_CTAS;
+    long rpb;
+    if (C == 1) {
+        const long bands_t = ((long)hb_sm_count() * 8 + xtiles - 1) / xtiles;
+        rpb = (h + bands_t - 1) / bands_t;
+        if (rpb < 4) rpb = 4;
+    } else {
+        // score = (fraction of the last wave of resident CTAs that is filled) x (fraction of row fetches that are not
+        // warm-up); candidates from 2 to 16 window heights
+        double best = -1.0;
+        rpb = 8L * kh;
+        for (long cand = 16L * kh; cand >= 2L * kh; cand -= (kh + 1) / 2) {
+            const long c = cand > h ? h : cand;
+            const long ctas = xtiles * ((h + c - 1) / c);
+            const long waves = (ctas + slots - 1) / slots;
+            const double score = ((double)ctas / (double)(waves * slots)) * ((double)c / (double)(c + kh - 1));
+            if (score > best) { best = score; rpb = c; }
+        }
+    }
     if (rpb > h) rpb = h;
+    long bands;
     g.rows_per_band = (int)rpb;
     bands = (h + rpb - 1) / rpb;
     HB_REQUIRE(bands <= 65535, "hb_fit_same_grid: too many row bands");
