@@ -25,7 +25,7 @@ struct NormState {
     unsigned long long rank[4];    // remaining rank inside the current prefix; queries: src k, src k+1, ref k, ref k+1
     unsigned int prefix[4];        // key prefix found so far
     float gamma;                   // numpy's interpolation weight
-    int pad;
+    unsigned int ticket;           // CTAs that have finished the current level (the last one resolves it)
     unsigned long long hist[4][kBins];
 };
 
@@ -50,6 +50,22 @@ __device__ __forceinline__ void warp_hist_add(unsigned int *hist, unsigned int b
     if ((int)(threadIdx.x & 31) == leader) atomicAdd(hist + bin, (unsigned int)__popc(peers));
 }
 
+// the same, with a fast path for the common case that every active lane of the warp hits the same bin (neighbouring
+// pixels of an image share the upper key bits)
+__device__ __forceinline__ void warp_hist_add_fast(unsigned int *hist, unsigned int bin, bool active)
+{
+    const unsigned int amask = __ballot_sync(0xffffffffu, active);
+    if (amask == 0u || !active) return;
+    int same = 0;
+    __match_all_sync(amask, bin, &same);
+    if (same) {
+        if ((int)(threadIdx.x & 31) == __ffs(amask) - 1) atomicAdd(hist + bin, (unsigned int)__popc(amask));
+        return;
+    }
+    const unsigned int peers = __match_any_sync(amask, bin);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(hist + bin, (unsigned int)__popc(peers));
+}
+
 __device__ __forceinline__ double block_sum(double v, double *s_red)
 {
 #pragma unroll
@@ -70,56 +86,100 @@ __device__ __forceinline__ double block_sum(double v, double *s_red)
 // LEVEL 0: histogram of key >> 20 for both planes (queries share them: hist[0] = src, hist[2] = ref), count, sums
 // LEVEL 1: histogram of (key >> 8) & 0xfff for keys matching each query's 12-bit prefix; squared deviations
 // LEVEL 2: histogram of key & 0xff for keys matching each query's 24-bit prefix
+template <int LEVEL> __device__ void norm_resolve(NormState *__restrict__ st, double *__restrict__ norm);
+
+// One pixel's contribution at LEVEL (all lanes of the warp call this together).
 template <int LEVEL>
+__device__ __forceinline__ void norm_pixel(float s, float r, bool valid, unsigned int *s_hist, const unsigned int (&prefix)[4],
+                                           double mean_s, double mean_r, double &acc_s, double &acc_r,
+                                           unsigned long long &cnt)
+{
+    constexpr int bins = (LEVEL == 2) ? 256 : kBins;
+    const unsigned int ks = float_key(s), kr = float_key(r);
+    if (LEVEL == 0) {
+        if (valid) { acc_s += (double)s; acc_r += (double)r; cnt++; }
+        warp_hist_add_fast(s_hist + 0 * bins, ks >> 20, valid);
+        warp_hist_add_fast(s_hist + 2 * bins, kr >> 20, valid);
+    } else {
+        if (LEVEL == 1 && valid) {
+            const double ds = (double)s - mean_s, dr = (double)r - mean_r;
+            acc_s += ds * ds; acc_r += dr * dr;
+        }
+        // which of the four queries does this pixel's key still match?  (almost always none: skip with one vote)
+        constexpr int sh = (LEVEL == 1) ? 20 : 8;
+        unsigned int m = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const unsigned int k = (q < 2) ? ks : kr;
+            if (valid && ((k >> sh) == prefix[q])) m |= 1u << q;
+        }
+        if (__ballot_sync(0xffffffffu, m != 0u) == 0u) return;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const unsigned int k = (q < 2) ? ks : kr;
+            const unsigned int bin = (LEVEL == 1) ? ((k >> 8) & 0xfffu) : (k & 0xffu);
+            warp_hist_add(s_hist + q * bins, bin, (m >> q) & 1u);
+        }
+    }
+}
+
+// LEVEL 0: histogram of key >> 20 for both planes (queries share them: hist[0] = src, hist[2] = ref), count, sums
+// LEVEL 1: histogram of (key >> 8) & 0xfff for keys matching each query's 12-bit prefix; squared deviations
+// LEVEL 2: histogram of key & 0xff for keys matching each query's 24-bit prefix
+// The last CTA to finish a level resolves it (norm_resolve) -- no separate one-CTA launches between the passes.
+template <int LEVEL, bool VEC>
 __global__ void __launch_bounds__(kNormThreads)
 norm_level_kernel(const float *__restrict__ src, NoData nd_s, const float *__restrict__ ref, NoData nd_r, long n,
-                  NormState *__restrict__ st)
+                  NormState *__restrict__ st, double *__restrict__ norm)
 {
     extern __shared__ unsigned int s_hist[];               // [4][bins]
     __shared__ double s_red[kNormThreads / 32];
+    __shared__ int s_last;
     constexpr int bins = (LEVEL == 2) ? 256 : kBins;
     for (int i = threadIdx.x; i < 4 * bins; i += blockDim.x) s_hist[i] = 0;
     unsigned int prefix[4] = {0, 0, 0, 0};
     double mean_s = 0.0, mean_r = 0.0;
     if (LEVEL > 0) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) prefix[q] = st->prefix[q];
-        mean_s = st->mean[0]; mean_r = st->mean[1];
+        for (int q = 0; q < 4; q++) prefix[q] = __ldcg(&st->prefix[q]);
+        mean_s = __ldcg(&st->mean[0]); mean_r = __ldcg(&st->mean[1]);
     }
     __syncthreads();
 
     double acc_s = 0.0, acc_r = 0.0;
     unsigned long long cnt = 0;
     const long stride = (long)gridDim.x * blockDim.x;
-    const long n_round = ((n + 31) / 32) * 32;              // keep warps converged for the ballot / match
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        float s = 0.f, r = 0.f;
-        bool valid = false;
-        if (i < n) {
-            s = __ldg(src + i); r = __ldg(ref + i);
-            valid = hb_valid(s, nd_s) && hb_valid(r, nd_r);
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long done = 0;                                          // pixels covered by the vector loop
+    if (VEC) {
+        // 4 consecutive pixels per thread and iteration (16-byte loads of both planes)
+        const long n4 = n / 4, n4_round = ((n4 + 31) / 32) * 32;   // keep warps converged for the votes
+        for (long g = tid; g < n4_round; g += stride) {
+            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), r4 = s4;
+            const bool in = g < n4;
+            if (in) {
+                s4 = __ldg(reinterpret_cast<const float4 *>(src) + g);
+                r4 = __ldg(reinterpret_cast<const float4 *>(ref) + g);
+            }
+            const float sv[4] = {s4.x, s4.y, s4.z, s4.w}, rv[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const bool valid = in && hb_valid(sv[k], nd_s) && hb_valid(rv[k], nd_r);
+                norm_pixel<LEVEL>(sv[k], rv[k], valid, s_hist, prefix, mean_s, mean_r, acc_s, acc_r, cnt);
+            }
         }
-        const unsigned int ks = float_key(s), kr = float_key(r);
-        if (LEVEL == 0) {
-            if (valid) { acc_s += (double)s; acc_r += (double)r; cnt++; }
-            warp_hist_add(s_hist + 0 * bins, ks >> 20, valid);
-            warp_hist_add(s_hist + 2 * bins, kr >> 20, valid);
-        } else if (LEVEL == 1) {
-            if (valid) {
-                const double ds = (double)s - mean_s, dr = (double)r - mean_r;
-                acc_s += ds * ds; acc_r += dr * dr;
+        done = n4 * 4;
+    }
+    {
+        const long rem = n - done, rem_round = ((rem + 31) / 32) * 32;
+        for (long i = tid; i < rem_round; i += stride) {
+            float s = 0.f, r = 0.f;
+            bool valid = false;
+            if (i < rem) {
+                s = __ldg(src + done + i); r = __ldg(ref + done + i);
+                valid = hb_valid(s, nd_s) && hb_valid(r, nd_r);
             }
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const unsigned int k = (q < 2) ? ks : kr;
-                warp_hist_add(s_hist + q * bins, (k >> 8) & 0xfffu, valid && ((k >> 20) == prefix[q]));
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const unsigned int k = (q < 2) ? ks : kr;
-                warp_hist_add(s_hist + q * bins, k & 0xffu, valid && ((k >> 8) == prefix[q]));
-            }
+            norm_pixel<LEVEL>(s, r, valid, s_hist, prefix, mean_s, mean_r, acc_s, acc_r, cnt);
         }
     }
     __syncthreads();
@@ -139,19 +199,28 @@ norm_level_kernel(const float *__restrict__ src, NoData nd_s, const float *__res
             if (threadIdx.x == 0) atomicAdd(&st->n, (unsigned long long)(tc + 0.5));
         }
     }
+    // ---- the last CTA to arrive resolves the level -------------------------------------------------------------------
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        norm_resolve<LEVEL>(st, norm);
+    }
 }
 
-// One CTA, 4 warps: warp q finds the bin of query q's rank in hist[q] (or the shared level-0 histogram), updates the
-// prefix and the remaining rank, and clears the histogram for the next level.  After level 2 the four order
-// statistics are known and thread 0 finishes the normalisation.
+// Run by every thread of ONE CTA (the last to finish the level): warp q < 4 finds the bin of query q's rank in hist[q]
+// (or the shared level-0 histogram), updates the prefix and the remaining rank; all threads then clear the histograms
+// for the next level / next call.  After level 2 the four order statistics are known and thread 0 finishes the
+// normalisation.  (Global state is read with ld.cg: it was written by other CTAs' atomics.)
 template <int LEVEL>
-__global__ void __launch_bounds__(128) norm_resolve_kernel(NormState *__restrict__ st, double *__restrict__ norm)
+__device__ void norm_resolve(NormState *__restrict__ st, double *__restrict__ norm)
 {
     constexpr int bins = (LEVEL == 2) ? 256 : kBins;
-    constexpr int per_lane = bins / 32;
     __shared__ float s_val[4];
-    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned long long n = st->n;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long n = __ldcg(&st->n);
 
     if (LEVEL == 0 && threadIdx.x == 0) {
         // numpy >= 2, float32 input: q = 1 / float32(100); virtual index = n*q + (1 + q*(1 - 1 - 1)) - 1 in float32
@@ -171,48 +240,74 @@ __global__ void __launch_bounds__(128) norm_resolve_kernel(NormState *__restrict
         st->rank[0] = (unsigned long long)k0; st->rank[1] = (unsigned long long)k1;
         st->rank[2] = (unsigned long long)k0; st->rank[3] = (unsigned long long)k1;
         const double dn = n ? (double)n : 1.0;
-        st->mean[0] = st->sum[0] / dn; st->mean[1] = st->sum[1] / dn;
+        st->mean[0] = __ldcg(&st->sum[0]) / dn; st->mean[1] = __ldcg(&st->sum[1]) / dn;
     }
     __syncthreads();
-    if (n > 0) {
-        const int hq = (LEVEL == 0) ? (q & 2) : q;              // level 0: queries share the per-plane histogram
-        const unsigned long long *h = st->hist[hq];
-        const unsigned long long rank = st->rank[q];
-        unsigned long long local = 0;
-        for (int i = 0; i < per_lane; i++) local += h[lane * per_lane + i];
-        unsigned long long incl = local;
+    // every thread sums a few consecutive bins of each query's histogram (independent loads: one L2 round trip), a block
+    // scan locates the thread -- and then the bin -- that holds each query's rank
+    __shared__ unsigned long long s_wtot[4][kNormThreads / 32];
+    constexpr int per_thread = (bins >= kNormThreads) ? bins / kNormThreads : 1;
+    const bool t_active = (int)threadIdx.x * per_thread < bins;
+    const int warp = threadIdx.x >> 5;
+    unsigned long long local[4], incl[4], rk[4];
+    unsigned int pf[4];
+#pragma unroll
+    for (int qq = 0; qq < 4; qq++) {
+        // (ranks / prefixes are read by everybody BEFORE the barrier below; the winners overwrite them after it)
+        rk[qq] = __ldcg(&st->rank[qq]);
+        pf[qq] = __ldcg(&st->prefix[qq]);
+        const int hq = (LEVEL == 0) ? (qq & 2) : qq;          // level 0: queries share the per-plane histogram
+        unsigned long long acc = 0;
+        if (n > 0 && t_active) {
+#pragma unroll
+            for (int i = 0; i < per_thread; i++) acc += __ldcg(&st->hist[hq][threadIdx.x * per_thread + i]);
+        }
+        local[qq] = acc;
+        unsigned long long in = acc;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += up;
+            const unsigned long long up = __shfl_up_sync(0xffffffffu, in, d);
+            if (lane >= d) in += up;
         }
-        const unsigned long long excl = incl - local;
-        const bool mine = (rank >= excl) && (rank < incl);
-        const unsigned int who = __ballot_sync(0xffffffffu, mine);
-        if (who != 0 && lane == (__ffs(who) - 1)) {
-            unsigned long long below = excl;
-            int bin = lane * per_lane;
-            for (int i = 0; i < per_lane; i++) {
-                const unsigned long long c = h[lane * per_lane + i];
-                if (rank < below + c) { bin = lane * per_lane + i; break; }
-                below += c;
+        incl[qq] = in;
+        if (lane == 31) s_wtot[qq][warp] = in;
+    }
+    __syncthreads();
+    if (n > 0 && t_active) {
+#pragma unroll
+        for (int qq = 0; qq < 4; qq++) {
+            unsigned long long off = 0;
+            for (int w = 0; w < warp; w++) off += s_wtot[qq][w];
+            const unsigned long long rank = rk[qq];
+            const unsigned long long excl = off + incl[qq] - local[qq];
+            if (rank >= excl && rank < excl + local[qq]) {      // exactly one thread per query
+                const int hq = (LEVEL == 0) ? (qq & 2) : qq;
+                unsigned long long below = excl;
+                int bin = threadIdx.x * per_thread;
+                for (int i = 0; i < per_thread; i++) {
+                    const unsigned long long c = __ldcg(&st->hist[hq][threadIdx.x * per_thread + i]);
+                    if (rank < below + c) { bin = threadIdx.x * per_thread + i; break; }
+                    below += c;
+                }
+                const unsigned int old_prefix = pf[qq];
+                const unsigned int p = (LEVEL == 0) ? (unsigned int)bin
+                                      : (LEVEL == 1) ? ((old_prefix << 12) | (unsigned int)bin)
+                                                     : ((old_prefix << 8) | (unsigned int)bin);
+                st->rank[qq] = rank - below;
+                st->prefix[qq] = p;
+                if (LEVEL == 2) s_val[qq] = key_float(p);
             }
-            st->rank[q] = rank - below;
-            const unsigned int p = (LEVEL == 0) ? (unsigned int)bin
-                                  : (LEVEL == 1) ? ((st->prefix[q] << 12) | (unsigned int)bin)
-                                                 : ((st->prefix[q] << 8) | (unsigned int)bin);
-            st->prefix[q] = p;
-            if (LEVEL == 2) s_val[q] = key_float(p);
         }
     }
     __syncthreads();
     // clear the histograms for the next level / next call
     for (int i = threadIdx.x; i < 4 * kBins; i += blockDim.x) st->hist[i / kBins][i % kBins] = 0ull;
+    if (threadIdx.x == 0) st->ticket = 0u;
     if (LEVEL == 2 && threadIdx.x == 0) {
         double n0 = 0.0, n1 = 0.0;
         if (n > 0) {
             const double dn = (double)n;
-            const float std_s = (float)sqrt(st->ssd[0] / dn), std_r = (float)sqrt(st->ssd[1] / dn);   // np.std(f32) -> f32
+            const float std_s = (float)sqrt(__ldcg(&st->ssd[0]) / dn), std_r = (float)sqrt(__ldcg(&st->ssd[1]) / dn);   // np.std(f32) -> f32
             n0 = (double)__fdiv_rn(std_r, std_s);                                                      // :227
             const float t = st->gamma;
             float p[2];
@@ -238,6 +333,7 @@ __global__ void norm_init_kernel(NormState *st)
         st->n = 0; st->sum[0] = st->sum[1] = 0.0; st->ssd[0] = st->ssd[1] = 0.0; st->mean[0] = st->mean[1] = 0.0;
         for (int q = 0; q < 4; q++) { st->rank[q] = 0; st->prefix[q] = 0; }
         st->gamma = 0.f;
+        st->ticket = 0u;
     }
 }
 
@@ -260,29 +356,31 @@ extern "C" int hb_block_norm(const float *src_dev, int src_has_nodata, double sr
     const NoData nd_s = hb_make_nodata(src_has_nodata, src_nodata), nd_r = hb_make_nodata(ref_has_nodata, ref_nodata);
     cudaStream_t st = (cudaStream_t)stream;
     NormState *state = (NormState *)workspace_dev;
-    long blocks = (n + kNormThreads - 1) / kNormThreads;
+    long blocks = (n / 4 + kNormThreads - 1) / kNormThreads;
+    if (blocks < 1) blocks = 1;
     const long cap = (long)hb_sm_count() * 2;
     if (blocks > cap) blocks = cap;
     const size_t smem01 = 4 * kBins * sizeof(unsigned int), smem2 = 4 * 256 * sizeof(unsigned int);
     static thread_local bool attr_set = false;
     if (!attr_set) {
-        HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
-        HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
+        HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
+        HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
+        HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
+        HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
         attr_set = true;
     }
     norm_init_kernel<<<1, 256, 0, st>>>(state);
     HB_LAUNCH_OK("norm_init_kernel");
-    norm_level_kernel<0><<<(unsigned)blocks, kNormThreads, smem01, st>>>(src_dev, nd_s, ref_dev, nd_r, n, state);
-    HB_LAUNCH_OK("norm_level_kernel<0>");
-    norm_resolve_kernel<0><<<1, 128, 0, st>>>(state, norm_dev);
-    HB_LAUNCH_OK("norm_resolve_kernel<0>");
-    norm_level_kernel<1><<<(unsigned)blocks, kNormThreads, smem01, st>>>(src_dev, nd_s, ref_dev, nd_r, n, state);
-    HB_LAUNCH_OK("norm_level_kernel<1>");
-    norm_resolve_kernel<1><<<1, 128, 0, st>>>(state, norm_dev);
-    HB_LAUNCH_OK("norm_resolve_kernel<1>");
-    norm_level_kernel<2><<<(unsigned)blocks, kNormThreads, smem2, st>>>(src_dev, nd_s, ref_dev, nd_r, n, state);
-    HB_LAUNCH_OK("norm_level_kernel<2>");
-    norm_resolve_kernel<2><<<1, 128, 0, st>>>(state, norm_dev);
-    HB_LAUNCH_OK("norm_resolve_kernel<2>");
+    const bool vec = (((uintptr_t)src_dev) % 16 == 0) && (((uintptr_t)ref_dev) % 16 == 0);
+#define HB_NORM_LEVEL(L_, SMEM_)                                                                                      \
+    do {                                                                                                              \
+        if (vec) norm_level_kernel<L_, true><<<(unsigned)blocks, kNormThreads, SMEM_, st>>>(src_dev, nd_s, ref_dev, nd_r, n, state, norm_dev); \
+        else norm_level_kernel<L_, false><<<(unsigned)blocks, kNormThreads, SMEM_, st>>>(src_dev, nd_s, ref_dev, nd_r, n, state, norm_dev);    \
+        HB_LAUNCH_OK("norm_level_kernel");                                                                            \
+    } while (0)
+    HB_NORM_LEVEL(0, smem01);
+    HB_NORM_LEVEL(1, smem01);
+    HB_NORM_LEVEL(2, smem2);
+#undef HB_NORM_LEVEL
     return 0;
 }
