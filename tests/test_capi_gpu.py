@@ -284,3 +284,78 @@ def test_full_size_same_grid_properties():
     assert float(same.float().mean()) > 0.999
     fin = torch.isfinite(a) & torch.isfinite(b)
     assert float(((a - b).abs()[fin] / a.abs()[fin].clamp_min(1e-3)).max()) <= RTOL
+
+
+# ---- the polynomial fast path of the up-sampler (csrc/upsample_poly.cu): destination >= ~3.4x finer, width % 4 == 0 ----
+_POLY_CASES = [
+    # dtype, nodata, ratio, shift (source-grid pixels), extra destination pixels beyond the coarse raster, pattern
+    ('uint16', 0, 20, (0, 0), 0, 'holes'),
+    ('uint16', 0, 4, (0, 0), 0, 'holes'),
+    ('uint8', 0, 7, (2.0, 3.0), 0, 'holes'),
+    ('float32', NAN, 5, (1.3, 2.6), 0, 'holes'),           # mis-aligned grids
+    ('float32', NAN, 3.5, (0.4, 0.9), 0, 'holes'),         # non-integer ratio, near the eligibility limit
+    ('float32', -9999.0, 6.4, (0.0, 0.0), 0, 'band'),      # value nodata; one band invalid where the other is not
+    ('uint16', 0, 8, (-12.0, -20.0), 24, 'holes'),         # destination larger than the coarse raster on every side
+    ('uint16', 65535, 10, (0, 0), 0, 'single'),            # isolated invalid coarse pixels
+    ('float32', NAN, 12, (0, 0), 0, 'spikes'),             # parameter spikes / infinities next to normal values
+    ('uint8', None, 16, (0, 0), 0, 'none'),                # no nodata at all
+    ('float32', NAN, 33, (5.0, 1.0), 0, 'checker'),        # every cell dirty
+]
+
+
+@pytest.mark.parametrize('dtype, nodata, ratio, shift, extra, pattern', _POLY_CASES)
+def test_upsample_apply_fast_path(dtype, nodata, ratio, shift, extra, pattern):
+    """ hb_upsample_apply on geometries that take the packed-float32 polynomial kernel + classification pre-pass +
+    double-precision fix-up, against RefSpaceModel.apply of the oracle: masks exact, values within 1e-4. """
+    _, kmnp = _oracle()
+    rng = np.random.default_rng(11)
+    hp, wp = 31, 27
+    hs = int(hp * ratio) + 2 * extra
+    ws = (int(wp * ratio) + 2 * extra) // 4 * 4               # the fast path needs a width that is a multiple of 4
+    src = _rand_src(rng, hs, ws, dtype, nodata if nodata is not None else 0, holes=nodata is not None)
+    yy, xx = np.mgrid[0:hp, 0:wp]
+    params = np.stack([0.7 + 0.1 * np.sin(xx / 5.0) + 0.05 * rng.normal(size=(hp, wp)),
+                       20.0 + 30.0 * np.cos(yy / 7.0) + 5.0 * rng.normal(size=(hp, wp))]).astype('float32')
+    if pattern == 'holes':
+        params[:, 8:12, 10:15] = NAN
+        params[:, :2, :] = NAN
+        params[:, 20, 3] = NAN
+    elif pattern == 'band':
+        params[0, 5:9, 5:9] = NAN
+        params[1, 7:12, 8:13] = NAN
+    elif pattern == 'single':
+        params[:, rng.integers(0, hp, 12), rng.integers(0, wp, 12)] = NAN
+    elif pattern == 'spikes':
+        params[0, 10, 10] = 4000.0
+        params[0, 15, 4] = -3.0
+        params[0, 22, 20] = np.inf
+        params[1, 22, 20] = -np.inf
+        params[0, 3, 18] = 0.0
+    elif pattern == 'checker':
+        params[:, (yy + xx) % 3 == 0] = NAN
+    src_tf = TF_LO * Affine.scale(1.0 / ratio) * Affine.translation(shift[0] - extra, shift[1] - extra)
+    pad = int(2 * ratio) + 4
+    fill = nodata if nodata is not None else 0
+    src_pad = np.full((hs + 2 * pad, ws + 2 * pad), fill, dtype=src.dtype)
+    src_pad[pad:pad + hs, pad:pad + ws] = src
+    pad_tf = src_tf * Affine.translation(-pad, -pad)
+    with np.errstate(all='ignore'):
+        expected = kmnp.refspace_apply(src_pad, tuple(pad_tf), nodata, params, tuple(TF_LO), (3, 5))[pad:pad + hs,
+                                                                                                       pad:pad + ws]
+    from homonim_b200 import CRS, Model, RasterArray, RefSpaceModel
+    crs = CRS.from_epsg(3857)
+    km = RefSpaceModel(Model.gain_blk_offset, (3, 5))
+    lib = _native.lib()
+    lib.hb_reset_launch_count()
+    got = km.apply(RasterArray(torch.from_numpy(src).cuda(), crs, src_tf, nodata=nodata),
+                   RasterArray(torch.from_numpy(params).cuda(), crs, TF_LO, nodata=NAN)).array.cpu().numpy()
+    assert lib.hb_launch_count() == 3, 'expected the pre-pass + polynomial + fix-up kernels'
+    expected = expected.astype('float32')
+    assert_same_mask(got, expected, 'fast up-sample + apply')
+    # infinities must agree exactly; finite values within the 1e-4 contract relative to the magnitude of the terms of
+    # gain*src + offset (next to a spike the sum cancels: a purely relative test on the result is ill-posed)
+    inf = np.isinf(expected)
+    assert np.array_equal(got[inf], expected[inf])
+    fin = np.isfinite(expected)
+    scale = np.maximum(np.abs(expected[fin]), 1e-3 * np.mean(np.abs(expected[fin])))
+    assert np.max(np.abs(got[fin].astype('float64') - expected[fin]) / scale) <= RTOL
