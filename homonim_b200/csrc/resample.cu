@@ -702,13 +702,13 @@ int launch_upsample(const void *src, NoData nd, const float *coarse, long hs, lo
                          (ws % 4 == 0) && (((uintptr_t)out) % 16 == 0);
     NoData ndk = nd;
     if (!ndk.int_ok) ndk.ivalue = -1;                       // integer sources: no pixel can equal it
-    // ---- fast path (upsample_poly.cu): aligned rasters, >= ~3.4 destination pixels per coarse pixel, no coverage mask
+    // ---- fast paths (upsample_poly.cu): aligned rasters, >= ~1.6 destination pixels per coarse pixel, no coverage mask
     if (aligned && cover == nullptr) {
         UpPolyGeom pg;
         pg.hs = hs; pg.ws = ws; pg.hp = hp; pg.wp = wp; pg.sx = sx; pg.ox = ox; pg.sy = sy; pg.oy = oy;
         if (hb_up_poly_eligible(pg)) {
             if (APPLY) return hb_up_poly_apply(src, hb_dtype_code<T>(), ndk, coarse, pg, out, stream);
-            return hb_up_poly_resample(coarse, NB, pg, out, stream);
+            if (NB == 1) return hb_up_poly_resample(coarse, 1, pg, out, stream);   // (double precision: feeds a fit)
         }
     }
 #define HB_UP_LAUNCH(AL_, MC_)                                                                                        \

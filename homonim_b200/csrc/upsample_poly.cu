@@ -1,5 +1,8 @@
-// upsample_poly.cu -- the fast path of the cubic-spline up-sampler (sm_100a), used by hb_upsample_apply /
-// hb_resample_up when the destination is >= ~3.4x finer than the coarse (parameter) grid.
+// upsample_poly.cu -- the fast paths of the cubic-spline up-sampler (sm_100a), used by hb_upsample_apply /
+// hb_resample_up when the destination is >= ~1.6x finer than the coarse (parameter) grid:
+//   upsample_poly_kernel        fused up-sample + apply, >= ~3.4 destination pixels per coarse pixel (packed float32)
+//   upsample_yfirst_kernel      fused up-sample + apply at smaller ratios (packed float32)
+//   upsample_yfirst_f64_kernel  plain one-band up-sampling in double (SrcSpaceModel's reference up-sampling)
 //
 // Replaces, for RefSpaceModel.apply (reference kernel_model.py:484-503): the GDAL GRA_CubicSpline warp of the gain and
 // offset planes onto the source grid, the two float32 planes it writes, and numpy's gain*src + offset pass (:461).
@@ -64,6 +67,20 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b)
 }
 __device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
 
+// the same on values that LIVE in 64-bit registers (long-lived packed state: keeps the register allocator from
+// scattering the halves of a pair, which costs two moves per use)
+typedef unsigned long long pk2;
+__device__ __forceinline__ pk2 pk(float lo, float hi)
+{
+    pk2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float pk_lo(pk2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
+__device__ __forceinline__ float pk_hi(pk2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
+__device__ __forceinline__ pk2 pk_fma(pk2 a, pk2 b, pk2 c) { pk2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ pk2 pk_mul(pk2 a, pk2 b) { pk2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 // ---- geometry shared by the fast kernel and the fix-up kernel (identical expressions => identical cell indices) -----
 __device__ __forceinline__ double up_src_coord(double scale, double off, long i) { return scale * ((double)i + 0.5) + off; }
 __device__ __forceinline__ long up_cell(double scale, double off, long i)
@@ -115,6 +132,29 @@ __device__ __forceinline__ void up_axis_weights(double scale, double off, long i
 #pragma unroll
         for (int t = 0; t < 4; t++) w[t] *= norm;
     }
+}
+
+// The same without the normalisation: raw B-spline weights with out-of-range taps zeroed, their sum, and whether the
+// pixel's centre coarse pixel is in range (for GDAL's exact rule on the PRODUCT of the two axis sums).
+__device__ __forceinline__ void up_axis_weights_raw(double scale, double off, long i, long n, double (&w)[4], long &k,
+                                                    double &sum, bool &ok)
+{
+    const double c = up_src_coord(scale, off, i);
+    const double kd = floor(c - 0.5);
+    k = (long)kd;
+    bspline_weights(c - 0.5 - kd, w);
+    long centre = (long)floor(c + 1e-10);
+    if (centre == n) centre--;
+    ok = (c >= 0.0) && centre >= 0 && centre < n;
+    sum = 0.0;
+    bool all_in = true;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const long tap = k - 1 + t;
+        if (tap < 0 || tap >= n) { w[t] = 0.0; all_in = false; }
+        sum += w[t];
+    }
+    if (all_in) sum = 1.0;                                  // (the four weights sum to 1 up to rounding)
 }
 
 // ---- cp.async (LDGSTS) ---------------------------------------------------------------------------------------------
@@ -521,6 +561,361 @@ upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restric
 }
 
 // =====================================================================================================================
+// fast kernel for small ratios (about 1.6 .. 9 destination pixels per coarse pixel): "y first"
+// =====================================================================================================================
+// At small ratios the tap rows change every few destination rows and re-interpolating 4 pixel columns through them
+// (upsample_poly_kernel) would dominate.  Here a lane keeps the 4 tap rows x 6 window columns of its 4 pixels in
+// registers (shifted / reloaded when the tap rows change) and every destination row (1) combines the 4 tap rows with
+// the row's y-weights per window column (packed over column pairs) and (2) combines the 6 columns with each pixel's
+// x-weights (packed over pixel pairs; a pixel's 4 weights sit at its window offset 0..2 inside the 6-column window,
+// zeros elsewhere).  Same classification / fix-up / edge rules / cp.async ring as upsample_poly_kernel.
+constexpr int kYfCols = 6;
+
+template <typename T, int NB, bool APPLY>
+__global__ void __launch_bounds__(kThreads, 2)
+upsample_yfirst_kernel(const T *__restrict__ src, NoData nd, const void *__restrict__ coarse_v,
+                       const uint8_t *__restrict__ flags, UpPolyGeom g, int rows_per_cta, float *__restrict__ out)
+{
+    constexpr int NOUT = (NB == 2 && !APPLY) ? 2 : 1;
+    constexpr int kLaneBytes = APPLY ? SrcQuad<T>::kBytes : 0;
+    constexpr int kRowBytes = 32 * kLaneBytes;
+    constexpr int kStageBytes = kRb * kRowBytes;
+    constexpr int kRingBytes = kStages * kStageBytes;
+    constexpr int kWBytes = kYfCols * 32 * (int)sizeof(float4);            // x-weights of one warp
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long Y0 = (long)blockIdx.y * rows_per_cta;
+    const int nrows = (int)min((long)rows_per_cta, g.hs - Y0);
+    const float qnan = __int_as_float(0x7fc00000);
+
+    RowEntry *s_rows = reinterpret_cast<RowEntry *>(smem_raw);
+    int *s_ky = reinterpret_cast<int *>(smem_raw + kMaxRows * sizeof(RowEntry));
+    if ((int)threadIdx.x < nrows) {
+        double wy[4];
+        long ky;
+        up_axis_weights(g.sy, g.oy, Y0 + threadIdx.x, g.hp, wy, ky);
+        RowEntry e;
+#pragma unroll
+        for (int j = 0; j < 4; j++) e.wy[j] = (float)wy[j];
+        s_rows[threadIdx.x] = e;
+        s_ky[threadIdx.x] = (int)min(max(ky, -4L), g.hp + 4);
+    }
+    __syncthreads();                                        // the only CTA barrier
+
+    const long X0 = ((long)blockIdx.x * kWarps + warp) * kWarpW + (long)lane * kPpt;
+    if (X0 - lane * kPpt >= g.ws) return;
+    const bool lane_in = X0 < g.ws;
+    unsigned char *warp_base = smem_raw + kRowTableBytes + warp * (kWBytes + kRingBytes);
+    float4 *s_w = reinterpret_cast<float4 *>(warp_base) + lane;            // s_w[c * 32]: window column c, 4 pixels
+    const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(warp_base + kWBytes + lane * kLaneBytes);
+
+    const long pitch_b = g.ws * (long)sizeof(T);
+    const char *pf = APPLY ? reinterpret_cast<const char *>(src + Y0 * g.ws + X0) : nullptr;
+    int pf_left = nrows;
+    uint32_t pf_dst = ring_sa;
+    auto prefetch = [&]() {
+        if (APPLY && lane_in) {
+            for (int rr = 0; rr < kRb; rr++) {
+                if (rr < pf_left) cp_async_lane<kLaneBytes>(pf_dst + rr * kRowBytes, pf);
+                pf += pitch_b;
+            }
+        }
+        pf_left -= kRb;
+        pf_dst = (pf_dst + kStageBytes == ring_sa + kRingBytes) ? ring_sa : pf_dst + kStageBytes;
+        cp_async_commit();
+    };
+    if (APPLY) {
+#pragma unroll
+        for (int st = 0; st < kStages - 1; st++) prefetch();
+    }
+
+    // ---- row-invariant lane geometry: edge-aware x-weights placed in the lane's 6-column window -> shared memory -------
+    int col0 = 0, cellA = 0, ncell = 1;                     // first window column; first flag column; cells spanned
+    bool geom_ok = lane_in;
+    {
+        float w6[kPpt][kYfCols];
+        long kx0 = 0, kx3 = 0;
+#pragma unroll
+        for (int k = 0; k < kPpt; k++) {
+            double wx[4];
+            long kx;
+            up_axis_weights(g.sx, g.ox, X0 + k, g.wp, wx, kx);
+            if (k == 0) kx0 = kx;
+            kx3 = kx;
+            const long sh = kx - kx0;                       // 0 .. 2
+            geom_ok = geom_ok && sh >= 0 && sh <= 2;
+#pragma unroll
+            for (int c = 0; c < kYfCols; c++) {
+                const long i = c - sh;
+                w6[k][c] = (i >= 0 && i < 4) ? (float)wx[i < 0 ? 0 : (i > 3 ? 3 : i)] : 0.f;
+            }
+        }
+        col0 = (int)min(max(kx0 - 1, -8L), g.wp + 8);
+        cellA = (int)min(max(kx0 + 1, -1L), g.wp + 2);
+        ncell = (int)min(max(kx3 - kx0, 0L), 2L) + 1;
+#pragma unroll
+        for (int c = 0; c < kYfCols; c++) s_w[c * 32] = make_float4(w6[0][c], w6[1][c], w6[2][c], w6[3][c]);
+    }
+    const int fw = (int)g.wp + 2, hp = (int)g.hp, wp = (int)g.wp;
+    auto cell_flags = [&](int ky, int cell) -> unsigned {
+        if (ky < -1 || ky > hp || cell < 0 || cell >= fw) return 6u;
+        return flags[(long)(ky + 1) * fw + cell];
+    };
+    int coff[kYfCols];                                      // clamped window columns (taps outside have weight 0)
+#pragma unroll
+    for (int c = 0; c < kYfCols; c++) coff[c] = min(max(col0 + c, 0), wp - 1);
+    const int ncols_used = 3 + ncell;                       // columns beyond are never weighted: not read (may be NaN)
+
+    const typename SrcQuad<T>::Key nd_key = SrcQuad<T>::key(nd);
+    pk2 t[NB][4][kYfCols / 2];                              // tap rows x window column pairs (packed float32 pairs)
+    int q_ky = INT_MIN;
+    bool do_store = false;
+    float *orow = out + Y0 * g.ws + X0;
+    const long out_pitch = g.ws;
+    uint32_t ring_rd = ring_sa;
+    auto load_tap_row = [&](int ky, int j) {
+        const long row_off = (long)min(max(ky - 1 + j, 0), hp - 1) * wp;
+        float v[NB][kYfCols];
+#pragma unroll
+        for (int c = 0; c < kYfCols; c++) {
+            if (NB == 2) {
+                const float2 x = (c < ncols_used) ? __ldg(reinterpret_cast<const float2 *>(coarse_v) + row_off + coff[c])
+                                                  : make_float2(0.f, 0.f);
+                v[0][c] = x.x; v[NB - 1][c] = x.y;
+            } else {
+                v[0][c] = (c < ncols_used) ? __ldg(reinterpret_cast<const float *>(coarse_v) + row_off + coff[c]) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+#pragma unroll
+            for (int p = 0; p < kYfCols / 2; p++) t[b][j][p] = pk(v[b][2 * p], v[b][2 * p + 1]);
+    };
+#pragma unroll 1
+    for (int r = 0; r < nrows; r++, orow += out_pitch) {
+        if (APPLY && (r & (kRb - 1)) == 0) {
+            prefetch();
+            cp_async_wait<kStages - 1>();
+        }
+        const int ky = s_ky[r];
+        if (ky != q_ky) {                                   // (warp-uniform) new tap rows
+            // 0: CLEAN, 1: SKIP (DIRTY -> fix-up kernel, or beyond the raster), 2: DEAD; the lane spans ncell cells
+            unsigned f_or = 0, f_and = 7u;
+            bool each_ok = true;                            // every cell CLEAN or OUT
+            for (int c = 0; c < ncell; c++) {
+                const unsigned f = cell_flags(ky, cellA + c);
+                f_or |= f; f_and &= f;
+                each_ok = each_ok && (f & 5u);
+            }
+            const int state = (!lane_in || !geom_ok) ? 1 : ((each_ok && (f_or & 1u)) ? 0 : ((f_and & 2u) ? 2 : 1));
+            do_store = (state != 1);
+            if (state == 2) {
+#pragma unroll
+                for (int b = 0; b < NB; b++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+#pragma unroll
+                        for (int p = 0; p < kYfCols / 2; p++) t[b][j][p] = pk(qnan, qnan);
+            } else if (state == 0) {
+                // (always reload all four rows: the lane may have been DEAD / DIRTY for the previous tap rows)
+#pragma unroll
+                for (int j = 0; j < 4; j++) load_tap_row(ky, j);
+            }
+            q_ky = ky;
+        }
+        // ---- one destination row ---------------------------------------------------------------------------------------
+        const RowEntry ri = s_rows[r];
+        pk2 A[NB][kYfCols / 2];                             // y-combination per window column pair
+        {
+            const pk2 y0 = pk(ri.wy[0], ri.wy[0]), y1 = pk(ri.wy[1], ri.wy[1]), y2 = pk(ri.wy[2], ri.wy[2]),
+                      y3 = pk(ri.wy[3], ri.wy[3]);
+#pragma unroll
+            for (int b = 0; b < NB; b++)
+#pragma unroll
+                for (int p = 0; p < kYfCols / 2; p++)
+                    A[b][p] = pk_fma(t[b][3][p], y3, pk_fma(t[b][2][p], y2, pk_fma(t[b][1][p], y1, pk_mul(t[b][0][p], y0))));
+        }
+        pk2 o[NB][2];                                       // per band, pixel pairs (0,1) and (2,3)
+#pragma unroll
+        for (int c = 0; c < kYfCols; c++) {
+            const float4 w = s_w[c * 32];
+            const pk2 w01 = pk(w.x, w.y), w23 = pk(w.z, w.w);
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const float a = (c & 1) ? pk_hi(A[b][c / 2]) : pk_lo(A[b][c / 2]);
+                const pk2 aa = pk(a, a);
+                o[b][0] = (c == 0) ? pk_mul(w01, aa) : pk_fma(w01, aa, o[b][0]);
+                o[b][1] = (c == 0) ? pk_mul(w23, aa) : pk_fma(w23, aa, o[b][1]);
+            }
+        }
+        float4 res[NOUT];
+        if constexpr (APPLY) {
+            float2 s[2];
+            bool ok[4];
+            SrcQuad<T>::get_shared(ring_rd, nd_key, s, ok);
+            ring_rd = (ring_rd + kRowBytes == ring_sa + kRingBytes) ? ring_sa : ring_rd + kRowBytes;
+            const pk2 c0 = pk_fma(o[0][0], pk(s[0].x, s[0].y), o[NB - 1][0]);   // corr = gain*src + offset
+            const pk2 c1 = pk_fma(o[0][1], pk(s[1].x, s[1].y), o[NB - 1][1]);
+            res[0] = make_float4(ok[0] ? pk_lo(c0) : qnan, ok[1] ? pk_hi(c0) : qnan, ok[2] ? pk_lo(c1) : qnan,
+                                 ok[3] ? pk_hi(c1) : qnan);
+        } else {
+            res[0] = make_float4(pk_lo(o[0][0]), pk_hi(o[0][0]), pk_lo(o[0][1]), pk_hi(o[0][1]));
+            if constexpr (NOUT == 2)
+                res[1] = make_float4(pk_lo(o[NB - 1][0]), pk_hi(o[NB - 1][0]), pk_lo(o[NB - 1][1]), pk_hi(o[NB - 1][1]));
+        }
+        if (do_store) {
+            hb_stg_stream16(orow, res[0]);
+            if constexpr (NOUT == 2) hb_stg_stream16(orow + g.hs * g.ws, res[1]);
+        }
+    }
+}
+
+// =====================================================================================================================
+// plain up-sampling of ONE band in double precision ("y first" organisation)
+// =====================================================================================================================
+// SrcSpaceModel up-samples the reference image onto the source grid and FITS on the result (kernel_model.py:518-524).
+// The reference's float32 numerator N*sum(sr) - sum(s)*sum(r) cancels catastrophically, so last-bit differences of the
+// up-sampled pixels are amplified past 1e-4 in the parameters: this path must round like GDAL does -- double
+// accumulation, one rounding to float32 -- and cannot use the packed-float32 kernels above.
+struct __align__(16) RowEntryD { double wy[4]; double sum; double pad; };   // sum: NaN when the row's centre is out of range
+
+__global__ void __launch_bounds__(kThreads, 2)
+upsample_yfirst_f64_kernel(const float *__restrict__ coarse, const uint8_t *__restrict__ flags, UpPolyGeom g,
+                           int rows_per_cta, float *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long Y0 = (long)blockIdx.y * rows_per_cta;
+    const int nrows = (int)min((long)rows_per_cta, g.hs - Y0);
+    const float qnan = __int_as_float(0x7fc00000);
+    const double dnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    RowEntryD *s_rows = reinterpret_cast<RowEntryD *>(smem_raw);
+    int *s_ky = reinterpret_cast<int *>(smem_raw + kMaxRows * sizeof(RowEntryD));
+    if ((int)threadIdx.x < nrows) {
+        RowEntryD e;
+        long ky;
+        bool ok;
+        up_axis_weights_raw(g.sy, g.oy, Y0 + threadIdx.x, g.hp, e.wy, ky, e.sum, ok);
+        if (!ok) e.sum = dnan;
+        e.pad = 0.0;
+        s_rows[threadIdx.x] = e;
+        s_ky[threadIdx.x] = (int)min(max(ky, -4L), g.hp + 4);
+    }
+    __syncthreads();
+
+    const long X0 = ((long)blockIdx.x * kWarps + warp) * kWarpW + (long)lane * kPpt;
+    if (X0 - lane * kPpt >= g.ws) return;
+    const bool lane_in = X0 < g.ws;
+    // x-weights of the warp: s_w[(c * 2 + h) * 32 + lane] = window column c, pixels (2h, 2h + 1), as double2
+    double2 *s_w = reinterpret_cast<double2 *>(smem_raw + kMaxRows * (sizeof(RowEntryD) + sizeof(int)) +
+                                               warp * (kYfCols * 2 * 32 * sizeof(double2))) + lane;
+    int col0 = 0, cellA = 0, ncell = 1;
+    bool geom_ok = lane_in;
+    double xsum[kPpt];                                      // sum of the in-range x-weights per pixel (NaN: centre out of range)
+    {
+        double w6[kPpt][kYfCols];
+        long kx0 = 0, kx3 = 0;
+#pragma unroll
+        for (int k = 0; k < kPpt; k++) {
+            double wx[4];
+            long kx;
+            bool ok;
+            up_axis_weights_raw(g.sx, g.ox, X0 + k, g.wp, wx, kx, xsum[k], ok);
+            if (!ok) xsum[k] = dnan;
+            if (k == 0) kx0 = kx;
+            kx3 = kx;
+            const long sh = kx - kx0;
+            geom_ok = geom_ok && sh >= 0 && sh <= 2;
+#pragma unroll
+            for (int c = 0; c < kYfCols; c++) {
+                const long i = c - sh;
+                w6[k][c] = (i >= 0 && i < 4) ? wx[i < 0 ? 0 : (i > 3 ? 3 : i)] : 0.0;
+            }
+        }
+        col0 = (int)min(max(kx0 - 1, -8L), g.wp + 8);
+        cellA = (int)min(max(kx0 + 1, -1L), g.wp + 2);
+        ncell = (int)min(max(kx3 - kx0, 0L), 2L) + 1;
+#pragma unroll
+        for (int c = 0; c < kYfCols; c++) {
+            s_w[(c * 2 + 0) * 32] = make_double2(w6[0][c], w6[1][c]);
+            s_w[(c * 2 + 1) * 32] = make_double2(w6[2][c], w6[3][c]);
+        }
+    }
+    const int fw = (int)g.wp + 2, hp = (int)g.hp, wp = (int)g.wp;
+    auto cell_flags = [&](int ky, int cell) -> unsigned {
+        if (ky < -1 || ky > hp || cell < 0 || cell >= fw) return 6u;
+        return flags[(long)(ky + 1) * fw + cell];
+    };
+    int coff[kYfCols];
+#pragma unroll
+    for (int c = 0; c < kYfCols; c++) coff[c] = min(max(col0 + c, 0), wp - 1);
+    const int ncols_used = 3 + ncell;
+
+    const bool x_plain = (xsum[0] == 1.0) && (xsum[1] == 1.0) && (xsum[2] == 1.0) && (xsum[3] == 1.0);
+    double t[4][kYfCols];
+    int q_ky = INT_MIN;
+    bool do_store = false;
+    float *orow = out + Y0 * g.ws + X0;
+#pragma unroll 1
+    for (int r = 0; r < nrows; r++, orow += g.ws) {
+        const int ky = s_ky[r];
+        if (ky != q_ky) {
+            unsigned f_or = 0, f_and = 7u;
+            bool each_ok = true;
+            for (int c = 0; c < ncell; c++) {
+                const unsigned f = cell_flags(ky, cellA + c);
+                f_or |= f; f_and &= f;
+                each_ok = each_ok && (f & 5u);
+            }
+            const int state = (!lane_in || !geom_ok) ? 1 : ((each_ok && (f_or & 1u)) ? 0 : ((f_and & 2u) ? 2 : 1));
+            do_store = (state != 1);
+            if (state == 2) {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int c = 0; c < kYfCols; c++) t[j][c] = dnan;
+            } else if (state == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float *p = coarse + (long)min(max(ky - 1 + j, 0), hp - 1) * wp;
+#pragma unroll
+                    for (int c = 0; c < kYfCols; c++) t[j][c] = (c < ncols_used) ? (double)__ldg(p + coff[c]) : 0.0;
+                }
+            }
+            q_ky = ky;
+        }
+        const RowEntryD ri = s_rows[r];
+        double A[kYfCols];
+#pragma unroll
+        for (int c = 0; c < kYfCols; c++)
+            A[c] = fma(t[3][c], ri.wy[3], fma(t[2][c], ri.wy[2], fma(t[1][c], ri.wy[1], t[0][c] * ri.wy[0])));
+        double o[kPpt];
+#pragma unroll
+        for (int c = 0; c < kYfCols; c++) {
+            const double2 w01 = s_w[(c * 2 + 0) * 32], w23 = s_w[(c * 2 + 1) * 32];
+            if (c == 0) { o[0] = w01.x * A[0]; o[1] = w01.y * A[0]; o[2] = w23.x * A[0]; o[3] = w23.y * A[0]; }
+            else {
+                o[0] = fma(w01.x, A[c], o[0]); o[1] = fma(w01.y, A[c], o[1]);
+                o[2] = fma(w23.x, A[c], o[2]); o[3] = fma(w23.y, A[c], o[3]);
+            }
+        }
+        // GDAL's rule on the sum of the usable weights = (x sum) * (y sum): divide unless within 1e-5 of 1; a NaN sum
+        // marks a pixel whose centre coarse pixel is out of range
+        if (!(ri.sum == 1.0 && x_plain)) {
+#pragma unroll
+            for (int k = 0; k < kPpt; k++) {
+                const double wsum = xsum[k] * ri.sum;
+                if (wsum != wsum) o[k] = dnan;
+                else if (wsum < 0.99999 || wsum > 1.00001) o[k] /= wsum;
+            }
+        }
+        if (do_store) hb_stg_stream16(orow, make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]));
+        (void)qnan;
+    }
+}
+
+// =====================================================================================================================
 // fix-up kernel: the destination pixels of the DIRTY cells, GDAL's general rules, double arithmetic, tap by tap
 // =====================================================================================================================
 // (gr_cubic_spline_up in oracle/gdal_restate.c: centre pixel in range and valid in some band; out-of-range / invalid
@@ -680,16 +1075,19 @@ int launch_poly(const void *src, NoData nd, const float *coarse, const UpPolyGeo
         HB_LAUNCH_OK("upsample_prep_kernel");
     }
     {
+        // a lane spanning 3 coarse cells (fewer than ~3.4 destination pixels per coarse pixel): the "y first" kernel
+        const bool yfirst = (g.sx > 0.3);
         const size_t ring = APPLY ? (size_t)kStages * kRb * 32 * kPpt * sizeof(T) : 0;
-        const size_t smem = kRowTableBytes + (5 * 32 * sizeof(float4) + ring) * kWarps;
+        const size_t smem = kRowTableBytes + ((yfirst ? kYfCols : 5) * 32 * sizeof(float4) + ring) * kWarps;
         const long cta_w = (long)kWarpW * kWarps;
         const long gx = (g.ws + cta_w - 1) / cta_w;
-        auto kern = upsample_poly_kernel<T, NB, APPLY>;
+        auto kern = yfirst ? upsample_yfirst_kernel<T, NB, APPLY> : upsample_poly_kernel<T, NB, APPLY>;
         if (smem > 48 * 1024)
             HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // rows per CTA: as many as possible (fewer row tables / weight set-ups per pixel) such that the grid is just
         // under a whole number of waves of resident CTAs (every warp streams the same amount: no ragged tail)
-        static int ctas_per_sm = 0;
+        static int ctas_cache[2] = {0, 0};
+        int &ctas_per_sm = ctas_cache[yfirst ? 1 : 0];
         if (ctas_per_sm == 0) {
             int n = 0;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kThreads, smem) != cudaSuccess || n < 1) n = 1;
@@ -726,8 +1124,8 @@ int launch_poly(const void *src, NoData nd, const float *coarse, const UpPolyGeo
 
 bool hb_up_poly_eligible(const UpPolyGeom &g)
 {
-    // a lane's 4 pixels must span at most 2 coarse cells: 3 * sx < 1 (with margin); the row direction only needs sy <= 1
-    return g.sx <= 0.3 && g.sy <= 1.0 + 1e-9 && (g.ws % kPpt == 0);
+    // a lane's 4 pixels must span at most 3 coarse cells: 3 * sx < 2 (with margin); the row direction only needs sy <= 1
+    return g.sx <= 0.62 && g.sy <= 1.0 + 1e-9 && (g.ws % kPpt == 0);
 }
 
 int hb_up_poly_apply(const void *src, int src_dtype, NoData nd, const float *params, const UpPolyGeom &g, float *out,
@@ -743,7 +1141,53 @@ int hb_up_poly_apply(const void *src, int src_dtype, NoData nd, const float *par
 
 int hb_up_poly_resample(const float *coarse, int nb, const UpPolyGeom &g, float *out, cudaStream_t stream)
 {
-    NoData none = hb_make_nodata(0, 0.0);
-    if (nb == 1) return launch_poly<float, 1, false>(nullptr, none, coarse, g, out, stream);
-    return launch_poly<float, 2, false>(nullptr, none, coarse, g, out, stream);
+    // one band, double precision (see upsample_yfirst_f64_kernel); the caller keeps two-band requests on its general kernel
+    HB_REQUIRE(nb == 1, "hb_up_poly_resample: one band per call");
+    const long fw = g.wp + 2, ncell = (g.hp + 2) * fw;
+    HB_REQUIRE(ncell < 2147483000L, "up-sampling: coarse raster too large");
+    const size_t off_list = 16, off_flags = off_list + (((size_t)ncell * 4 + 15) / 16) * 16;
+    const size_t total = off_flags + (((size_t)ncell + 15) / 16) * 16;
+    char *wsb = nullptr;
+    HB_CUDA_OK(hb_pool_keep_memory());
+    HB_CUDA_OK(cudaMallocAsync((void **)&wsb, total, stream));
+    int *count = (int *)wsb, *list = (int *)(wsb + off_list);
+    uint8_t *flags = (uint8_t *)(wsb + off_flags);
+    HB_CUDA_OK(cudaMemsetAsync(count, 0, 16, stream));
+    {
+        dim3 pgrid((unsigned)((fw + kPrepW - 1) / kPrepW), (unsigned)((g.hp + 2 + kPrepH - 1) / kPrepH));
+        HB_REQUIRE(pgrid.y <= 65535u, "up-sampling: coarse raster has too many rows (%ld)", g.hp);
+        upsample_prep_kernel<1, false><<<pgrid, kPrepW * kPrepH, 0, stream>>>(coarse, g.hp, g.wp, nullptr, flags, list, count);
+        HB_LAUNCH_OK("upsample_prep_kernel");
+    }
+    {
+        const size_t smem = kMaxRows * (sizeof(RowEntryD) + sizeof(int)) + (size_t)kWarps * kYfCols * 2 * 32 * sizeof(double2);
+        static bool attr_done = false;
+        if (!attr_done) {
+            HB_CUDA_OK(cudaFuncSetAttribute(upsample_yfirst_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = true;
+        }
+        const long cta_w = (long)kWarpW * kWarps;
+        const long gx = (g.ws + cta_w - 1) / cta_w;
+        const long slots = (long)hb_sm_count() * 2;
+        long rpc = kMaxRows;
+        double best = -1.0;
+        for (long cand = kMaxRows; cand >= 32; cand -= 4) {
+            const long ctas = gx * ((g.hs + cand - 1) / cand);
+            const long waves = (ctas + slots - 1) / slots;
+            const double eff = (double)ctas / (double)(waves * slots) * (cand >= 64 ? 1.0 : 0.97);
+            if (eff > best + 0.02) { best = eff; rpc = cand; }
+        }
+        dim3 grid((unsigned)gx, (unsigned)((g.hs + rpc - 1) / rpc));
+        HB_REQUIRE(grid.y <= 65535u, "up-sampling destination has too many rows (%ld)", g.hs);
+        upsample_yfirst_f64_kernel<<<grid, kThreads, smem, stream>>>(coarse, flags, g, (int)rpc, out);
+        HB_LAUNCH_OK("upsample_yfirst_f64_kernel");
+    }
+    {
+        const unsigned blocks = (unsigned)hb_sm_count() * 16;
+        upsample_fixup_kernel<float, 1, false><<<blocks, kFixThreads, 0, stream>>>(nullptr, hb_make_nodata(0, 0.0), coarse,
+                                                                                 g, out, list, count);
+        HB_LAUNCH_OK("upsample_fixup_kernel");
+    }
+    HB_CUDA_OK(cudaFreeAsync(wsb, stream));
+    return 0;
 }

@@ -9,12 +9,13 @@ struct UpPolyGeom {
     double sx, ox, sy, oy;    // destination pixel index -> coarse pixel coordinate: c = s * (i + 0.5) + o
 };
 
-// the fast path needs >= ~3.4 destination pixels per coarse pixel and a destination width that is a multiple of 4
+// the fast paths need >= ~1.6 destination pixels per coarse pixel and a destination width that is a multiple of 4
 // (the caller also checks pointer / pitch alignment)
 bool hb_up_poly_eligible(const UpPolyGeom &g);
 
 // corr = up(gain) * src + up(offset)      (params: float32 [2][hp][wp], NaN = nodata; nd.ivalue = -1 if not an integer)
 int hb_up_poly_apply(const void *src, int src_dtype, NoData nd, const float *params, const UpPolyGeom &g, float *out,
                      cudaStream_t stream);
-// plain up-sampling of 1 or 2 float32 bands (out: [nb][hs][ws])
+// plain up-sampling of ONE float32 band in double precision (out: [hs][ws]); two-band requests stay on the caller's
+// general kernel
 int hb_up_poly_resample(const float *coarse, int nb, const UpPolyGeom &g, float *out, cudaStream_t stream);

@@ -300,6 +300,14 @@ _POLY_CASES = [
     ('float32', NAN, 12, (0, 0), 0, 'spikes'),             # parameter spikes / infinities next to normal values
     ('uint8', None, 16, (0, 0), 0, 'none'),                # no nodata at all
     ('float32', NAN, 33, (5.0, 1.0), 0, 'checker'),        # every cell dirty
+    # small ratios: the "y first" kernel (a lane spans up to 3 coarse cells)
+    ('uint16', 0, 2, (0, 0), 0, 'holes'),
+    ('float32', NAN, 2, (0.5, 0.5), 0, 'single'),
+    ('uint8', 0, 3, (0, 0), 0, 'holes'),                   # Landsat 30 m vs Sentinel-2 10 m
+    ('float32', NAN, 2.5, (0.3, 0.7), 4, 'band'),
+    ('uint16', 0, 1.7, (0, 0), 0, 'holes'),
+    ('float32', NAN, 8, (3.0, 2.0), 0, 'spikes'),
+    ('uint16', 0, 5, (0, 0), 0, 'checker'),
 ]
 
 
@@ -359,3 +367,28 @@ def test_upsample_apply_fast_path(dtype, nodata, ratio, shift, extra, pattern):
     fin = np.isfinite(expected)
     scale = np.maximum(np.abs(expected[fin]), 1e-3 * np.mean(np.abs(expected[fin])))
     assert np.max(np.abs(got[fin].astype('float64') - expected[fin]) / scale) <= RTOL
+
+
+@pytest.mark.parametrize('nb', [1, 2])
+@pytest.mark.parametrize('ratio, shift', [(2, (0, 0)), (3, (0.5, 0.25)), (2.5, (1.0, 0.0)), (6, (0, 0)), (24, (2.0, 5.0))])
+def test_resample_up_fast_paths(nb, ratio, shift):
+    """ Plain cubic-spline up-sampling (SrcSpaceModel's reference up-sampling) on widths that take the fast kernel: it
+    feeds a fit whose float32 arithmetic amplifies last-bit differences, so it has to round like GDAL (double). """
+    gr, _ = _oracle()
+    rng = np.random.default_rng(5)
+    hp, wp = 38, 36
+    coarse = rng.normal(1.0, 0.2, (nb, hp, wp)).astype('float32')
+    coarse[:, 10:13, 5:9] = NAN
+    coarse[0, 30, 20] = NAN
+    coarse[:, :, -1] = NAN
+    hd, wd = int(hp * ratio) + 3, (int(wp * ratio) + 2) // 4 * 4
+    dst_tf = TF_LO * Affine.scale(1.0 / ratio) * Affine.translation(*shift)
+    arr = coarse if nb == 2 else coarse[0]
+    expected = gr.reproject_array(arr, tuple(TF_LO), NAN, (hd, wd), tuple(dst_tf), NAN, 'cubic_spline')
+    lib = _native.lib()
+    lib.hb_reset_launch_count()
+    got = hkm._resample_up(torch.from_numpy(arr).cuda(), TF_LO, NAN, (hd, wd), dst_tf).cpu().numpy()
+    # one band: pre-pass + double-precision "y first" kernel + fix-up; two bands stay on the general kernel
+    assert lib.hb_launch_count() == (3 if nb == 1 else 1)
+    assert_same_mask(got, expected, 'cubic_spline')
+    assert rel_err(got, expected, 1e-3) <= 1e-6
