@@ -55,6 +55,19 @@ __device__ __forceinline__ double hb_ddiv(double a, double b)
     return fma(rem, r, q);
 }
 
+// one step of an inclusive warp scan of doubles: v += (value of lane - d), for lanes >= d.  The shuffle's own
+// "source lane in range" predicate guards the add (one predicated DADD instead of an add and two selects).
+__device__ __forceinline__ double scan_step(double v, int d)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v), ulo, uhi, p;
+    asm volatile("{\n\t.reg .pred q;\n\tshfl.sync.up.b32 %0|q, %3, %5, 0, 0xffffffff;\n\t"
+                 "shfl.sync.up.b32 %1, %4, %5, 0, 0xffffffff;\n\tselp.s32 %2, 1, 0, q;\n\t}"
+                 : "=r"(ulo), "=r"(uhi), "=r"(p) : "r"(lo), "r"(hi), "r"(d));
+    const double up = __hiloint2double(uhi, ulo);
+    if (p) v += up;
+    return v;
+}
+
 // contribution of one pixel to the running sums
 template <int NQ, bool NORM>
 __device__ __forceinline__ void pixel_terms(float s, float r, bool valid, double n0, double n1, double (&q)[NQ],
@@ -274,10 +287,7 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
         for (int k = 0; k < NQ; k++) {
             double incl = pre[C - 1][k];
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const double up = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += up;
-            }
+            for (int d = 1; d < 32; d <<= 1) incl = scan_step(incl, d);
             excl[k] = incl - pre[C - 1][k];
             if (lane == 31) s_tot[buf][k][warp] = incl;
         }
@@ -321,18 +331,19 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
                 N = VN[i];
             } else {
 #pragma unroll
+                // (all loads unconditional, corrections selected: no divergent branches in the row loop)
+                const int wb1 = min(wb + 1, kFitWarps - 1);
                 for (int k = 0; k < NQ; k++) {
-                    double v = s_q[buf][k][sa];
-                    if (cross) v += s_tot[buf][k][wb];
-                    if (cross2) v += s_tot[buf][k][wb + 1];
-                    if (b >= 0) v -= s_q[buf][k][sb];
+                    const double qa = s_q[buf][k][sa], qb = s_q[buf][k][sb];
+                    const double t0 = s_tot[buf][k][wb], t1 = s_tot[buf][k][wb1];
+                    double v = qa + (cross ? t0 : -0.0);     // (x + -0.0 == x and x - 0.0 == x for every x, signed zeros too)
+                    v += cross2 ? t1 : -0.0;
+                    v -= (b >= 0) ? qb : 0.0;
                     W[k] = v;
                 }
                 if (HAS_N) {
-                    int v = s_n[buf][sa];
-                    if (cross) v += s_ntot[buf][wb];
-                    if (cross2) v += s_ntot[buf][wb + 1];
-                    if (b >= 0) v -= s_n[buf][sb];
+                    int v = s_n[buf][sa] + (cross ? s_ntot[buf][wb] : 0) + (cross2 ? s_ntot[buf][wb1] : 0);
+                    v -= (b >= 0) ? s_n[buf][sb] : 0;
                     N = v;
                 }
             }
