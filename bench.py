@@ -230,7 +230,8 @@ def run_sharded(args, cfg, rank, world, local_rank):
     barrier()
     stop, samples = threading.Event(), []
     sampler = threading.Thread(target=_clock_sampler, args=(stop, samples, local_rank), daemon=True)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     lib.hb_reset_launch_count()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -245,7 +246,8 @@ def run_sharded(args, cfg, rank, world, local_rank):
         step()
         kernel_ms = timer.results()
     stop.set()
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
@@ -345,9 +347,11 @@ def main():
     barrier()
 
     # ---- timed region: device-resident inputs -----------------------------------------------------------------------
+    # clocks are sampled on rank 0 only (nvidia-smi is not free: 8 ranks polling it would compete with the timed loop)
     stop, samples = threading.Event(), []
     sampler = threading.Thread(target=_clock_sampler, args=(stop, samples, local_rank), daemon=True)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     lib.hb_reset_launch_count()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -369,7 +373,8 @@ def main():
         kernel_ms = timer.results()
     serial_ms = s0.elapsed_time(s1)
     stop.set()
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

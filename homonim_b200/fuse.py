@@ -109,6 +109,7 @@ class RasterFuse:
         self._closed = True
         self._corr_lock = threading.Lock()
         self._param_lock = threading.Lock()
+        self._plans: Dict[int, tuple] = {}
 
     @staticmethod
     def _resolve_proc_crs(src: RasterArray, ref: RasterArray, proc_crs: ProcCrs = ProcCrs.auto) -> ProcCrs:
@@ -185,6 +186,31 @@ class RasterFuse:
         transform = ref_ra.transform * Affine.translation(col0, row0)
         return RasterArray(array, ref_ra.crs, transform, nodata=ref_ra.nodata)
 
+    def _band_plan(self, band_i: int):
+        """
+        Per-band inputs of the one-call path, prepared once and re-used by later ``process`` calls on unchanged rasters
+        (the reference's reader likewise fixes its windows when the pair is opened, raster_pair.py:280-296): the source
+        band view, the reference block as a contiguous float32 device plane, and the grid map between them.  The cache
+        key holds the tensors' identities and version counters, so in-place edits of either raster invalidate it.
+        """
+        src_arr, ref_arr = self._src.array, self._ref.array
+        key = (src_arr.data_ptr(), src_arr._version, tuple(src_arr.shape), ref_arr.data_ptr(), ref_arr._version,
+               tuple(ref_arr.shape), self._src_bands[band_i], self._ref_bands[band_i])
+        plan = self._plans.get(band_i)
+        if plan is not None and plan[0] == key:
+            return plan[1:]
+        from homonim_b200.geometry import grid_map
+        src_ra = _band(self._src, self._src_bands[band_i])
+        ref_ra = self._ref_block(band_i)
+        ref_t = ref_ra.array
+        if ref_t.dtype != torch.float32:
+            ref_t = ref_t.to(torch.float32)
+        ref_t = ref_t.contiguous()
+        gm = grid_map(src_ra.transform, ref_ra.transform)         # reference grid -> source grid
+        plan = (key, src_ra, ref_ra, ref_t, gm)
+        self._plans[band_i] = plan
+        return plan[1:]
+
     def _process_band(self, band_i: int, model: KernelModel, out=None, stage: bool = False,
                       want_params: bool = True) -> Tuple[RasterArray, Optional[RasterArray]]:
         """
@@ -192,6 +218,17 @@ class RasterFuse:
         ``stage``: copy a host band to the device once up front (fit and apply both read it) and leave the results
         on the device; otherwise results live where the inputs live.
         """
+        if self._src.is_device and self._ref.is_device and isinstance(model, RefSpaceModel):
+            # device-resident rasters, proc_crs = ref: one native call per band on cached, prepared planes
+            src_ra, ref_ra, ref_t, gm = self._band_plan(band_i)
+            if model.can_fuse(src_ra, ref_ra):
+                corr, params = model._fuse_planes(src_ra.array, src_ra.nodata, ref_t, ref_ra.nodata, gm, out,
+                                                  want_params)
+                corr_ra = RasterArray(corr, src_ra.crs, src_ra.transform, nodata=float('nan'))
+                param_ra = None
+                if params is not None:
+                    param_ra = RasterArray(params, ref_ra.crs, ref_ra.transform, nodata=float('nan'))
+                return corr_ra, param_ra
         src_ra = _band(self._src, self._src_bands[band_i])
         ref_ra = self._ref_block(band_i)
         if stage and not src_ra.is_device:

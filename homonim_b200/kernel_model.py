@@ -439,27 +439,33 @@ class RefSpaceModel(KernelModel):
         on_device = (src_ra.is_device and ref_ra.is_device) or out is not None
         src_t, ref_t = _to_device(src_ra.array), _to_device(ref_ra.array)
         ref_t = _as_f32_plane(ref_t, ref_ra.nodata).contiguous()
-        hs, ws = src_ra.shape
-        hr, wr = ref_ra.shape
         gm = grid_map(src_ra.transform, ref_ra.transform)         # reference grid -> source grid
+        corr, params = self._fuse_planes(src_t, src_ra.nodata, ref_t, ref_ra.nodata, gm, out, want_params)
+        corr_ra = RasterArray(_result(corr, on_device), src_ra.crs, src_ra.transform, nodata=NAN)
+        param_ra = None
+        if params is not None:
+            param_ra = RasterArray(_result(params, on_device), ref_ra.crs, ref_ra.transform, nodata=NAN)
+        return corr_ra, param_ra
+
+    def _fuse_planes(self, src_t, src_nodata, ref_t, ref_nodata, gm, out=None, want_params: bool = False):
+        """ `fuse` on prepared device planes (``ref_t``: contiguous float32; ``gm``: reference grid -> source grid):
+        returns ``(corr, params or None)`` device tensors.  The lean inner call of ``RasterFuse.process``. """
+        hs, ws = int(src_t.shape[-2]), int(src_t.shape[-1])
+        hr, wr = int(ref_t.shape[-2]), int(ref_t.shape[-1])
         corr = self._check_out(out, hs, ws, src_t.device)
         want_r2 = self._wants_r2()
         inpaint = self._model == Model.gain_offset and self._r2_inpaint_thresh is not None
         params = None
         if want_params:
             params = torch.empty((3 if want_r2 else 2, hr, wr), dtype=torch.float32, device=src_t.device)
-        s_has, s_nd = _nodata_args(src_ra.nodata)
-        r_has, r_nd = _nodata_args(ref_ra.nodata)
+        s_has, s_nd = _nodata_args(src_nodata)
+        r_has, r_nd = _nodata_args(ref_nodata)
         kh, kw = self._kernel_shape
         _call('hb_fuse_refspace', src_t.data_ptr(), _plane_code(src_t), hs, ws, s_has, s_nd, ref_t.data_ptr(), hr, wr,
               r_has, r_nd, gm.sx, gm.ox, gm.sy, gm.oy, _MODEL_CODES[self._model], kh, kw, int(want_r2), int(inpaint),
               float(self._r2_inpaint_thresh) if inpaint else 0.0, corr.data_ptr(),
               params.data_ptr() if params is not None else None, _stream())
-        corr_ra = RasterArray(_result(corr, on_device), src_ra.crs, src_ra.transform, nodata=NAN)
-        param_ra = None
-        if params is not None:
-            param_ra = RasterArray(_result(params, on_device), ref_ra.crs, ref_ra.transform, nodata=NAN)
-        return corr_ra, param_ra
+        return corr, params
 
     def apply(self, src_ra: RasterArray, param_ra: RasterArray, out=None) -> RasterArray:
         _require_torch()
