@@ -63,34 +63,37 @@ extern "C" int hb_fuse_refspace(const void *src_dev, int src_dtype, long hs, lon
     const size_t nr = (size_t)hr * wr;
     const double nan = __builtin_nan("");
 
-    DevBuf d_ds(st), d_params(st), d_sums(st), d_norm(st), d_work(st), d_work2(st);
-    HB_CUDA_OK(d_ds.alloc(nr * sizeof(float)));
-    float *params = params_dev;
-    if (params == nullptr) {
-        HB_CUDA_OK(d_params.alloc(nr * sizeof(float) * 3));
-        params = (float *)d_params.p;
-    }
-    int rc = hb_downsample_average(src_dev, src_dtype, hs, ws, src_has_nodata, src_nodata, (float *)d_ds.p, hr, wr, sx,
-                                   ox, sy, oy, stream);
+    // one stream-ordered allocation for all the proc-grid scratch of this call
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    const bool blk = (model == HB_MODEL_GAIN_BLK_OFFSET);
+    const size_t b_ds = al(nr * sizeof(float)), b_params = params_dev ? 0 : al(nr * sizeof(float) * 3),
+                 b_sums = inpaint ? al(nr * sizeof(float) * 3) : 0, b_norm = blk ? al(2 * sizeof(double)) : 0,
+                 b_work = blk ? al(hb_block_norm_workspace_bytes((long)nr)) : 0,
+                 b_work2 = inpaint ? al(hb_inpaint_workspace_bytes(hr, wr)) : 0;
+    DevBuf scratch(st);
+    HB_CUDA_OK(scratch.alloc(b_ds + b_params + b_sums + b_norm + b_work + b_work2));
+    char *base = (char *)scratch.p;
+    float *d_ds = (float *)base;
+    float *params = params_dev ? params_dev : (float *)(base + b_ds);
+    float *d_sums = (float *)(base + b_ds + b_params);
+    double *d_norm = (double *)(base + b_ds + b_params + b_sums);
+    void *d_work = base + b_ds + b_params + b_sums + b_norm;
+    void *d_work2 = base + b_ds + b_params + b_sums + b_norm + b_work;
+
+    int rc = hb_downsample_average(src_dev, src_dtype, hs, ws, src_has_nodata, src_nodata, d_ds, hr, wr, sx, ox, sy, oy,
+                                   stream);
     if (rc) return rc;
     const double *norm = nullptr;
-    if (model == HB_MODEL_GAIN_BLK_OFFSET) {
-        const size_t wb = hb_block_norm_workspace_bytes((long)nr);
-        HB_CUDA_OK(d_norm.alloc(2 * sizeof(double)));
-        HB_CUDA_OK(d_work.alloc(wb));
-        rc = hb_block_norm((const float *)d_ds.p, 1, nan, ref_dev, ref_has_nodata, ref_nodata, (long)nr,
-                           (double *)d_norm.p, d_work.p, wb, stream);
+    if (blk) {
+        rc = hb_block_norm(d_ds, 1, nan, ref_dev, ref_has_nodata, ref_nodata, (long)nr, d_norm, d_work, b_work, stream);
         if (rc) return rc;
-        norm = (const double *)d_norm.p;
+        norm = d_norm;
     }
-    if (inpaint) HB_CUDA_OK(d_sums.alloc(nr * sizeof(float) * 3));
-    rc = hb_fit_same_grid((const float *)d_ds.p, 1, nan, ref_dev, ref_has_nodata, ref_nodata, hr, wr, model, kh, kw, r2,
-                          norm, params, inpaint ? (float *)d_sums.p : nullptr, stream);
+    rc = hb_fit_same_grid(d_ds, 1, nan, ref_dev, ref_has_nodata, ref_nodata, hr, wr, model, kh, kw, r2, norm, params,
+                          inpaint ? d_sums : nullptr, stream);
     if (rc) return rc;
     if (inpaint) {
-        const size_t wb = hb_inpaint_workspace_bytes(hr, wr);
-        HB_CUDA_OK(d_work2.alloc(wb));
-        rc = hb_inpaint_refit(params, (const float *)d_sums.p, hr, wr, r2_thresh, 100.0, d_work2.p, wb, stream);
+        rc = hb_inpaint_refit(params, d_sums, hr, wr, r2_thresh, 100.0, d_work2, b_work2, stream);
         if (rc) return rc;
     }
     // source grid -> reference (param) grid is the inverse of the reference -> source map

@@ -269,3 +269,26 @@ def test_fused_call_equals_fit_then_apply(model, kernel_shape, thresh):
                        params.array.nan_to_num(-7.0, posinf=-8.0, neginf=-9.0))
     corr_n, none = km.fuse(src, ref)
     assert none is None and torch.equal(corr_n.array.nan_to_num(-1.0), corr.array.nan_to_num(-1.0))
+
+
+def test_process_plan_cache_follows_in_place_edits():
+    """ RasterFuse.process caches per-band prepared inputs between calls; in-place edits of the source or reference
+    tensors (and a different band selection) must be picked up. """
+    src_ra, ref_ra = make_pair(64, 56, 8, bands=2, dtype='uint16', mu=3000.0, seed=13, device='cuda', src_nodata=0)
+    kw = dict(model=Model.gain_blk_offset, kernel_shape=(5, 5))
+    with RasterFuse(src_ra, ref_ra) as fuse:
+        first, _ = fuse.process(**kw)
+        again, _ = fuse.process(**kw)
+        assert torch.equal(first.array.nan_to_num(-1), again.array.nan_to_num(-1))
+        ref_ra.array.mul_(1.5)                                   # in place: same storage, new version counter
+        scaled, _ = fuse.process(**kw)
+        fresh_src, fresh_ref = RasterArray(src_ra.array.clone(), src_ra.crs, src_ra.transform, nodata=0), \
+            RasterArray(ref_ra.array.clone(), ref_ra.crs, ref_ra.transform, nodata=float('nan'))
+        with RasterFuse(fresh_src, fresh_ref) as fuse2:
+            expect, _ = fuse2.process(**kw)
+        assert torch.equal(scaled.array.nan_to_num(-1), expect.array.nan_to_num(-1))
+        assert not torch.equal(scaled.array.nan_to_num(-1), first.array.nan_to_num(-1))
+        src_ra.array[0, :40, :40] = 0                            # new nodata in band 1 of the source
+        holed, _ = fuse.process(**kw)
+        assert bool(torch.isnan(holed.array[0, :40, :40]).all())
+        assert torch.equal(holed.array[1].nan_to_num(-1), scaled.array[1].nan_to_num(-1))
