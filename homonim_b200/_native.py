@@ -15,10 +15,10 @@ from ctypes import c_char_p, c_double, c_int, c_long, c_size_t, c_void_p
 
 from homonim_b200.errors import NativeLibraryError
 
-HB_U8, HB_U16, HB_F32 = 0, 1, 2
+HB_U8, HB_U16, HB_F32, HB_I16 = 0, 1, 2, 3
 HB_MODEL_GAIN, HB_MODEL_GAIN_BLK_OFFSET, HB_MODEL_GAIN_OFFSET = 0, 1, 2
 HB_UP_CUBIC_SPLINE, HB_UP_NEAREST = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _PKG_DIR = pathlib.Path(__file__).resolve().parent
 LIB_PATH = _PKG_DIR / 'libhomonim_b200.so'
@@ -51,6 +51,7 @@ SIGNATURES = {
                                c_double, c_double, c_double, c_int, c_void_p]),
     'hb_full_coverage_mask': (c_int, [c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_double, c_double, c_double,
                                       c_double, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'hb_convert_dtype': (c_int, [c_void_p, c_long, c_int, c_int, c_double, c_void_p, c_void_p]),
     'hb_valid_mask': (c_int, [c_void_p, c_int, c_long, c_int, c_double, c_void_p, c_void_p]),
     'hb_fuse_refspace': (c_int, [c_void_p, c_int, c_long, c_long, c_int, c_double, c_void_p, c_long, c_long, c_int,
                                  c_double, c_double, c_double, c_double, c_double, c_int, c_int, c_int, c_int, c_int,

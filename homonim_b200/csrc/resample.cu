@@ -775,6 +775,44 @@ __global__ void valid_mask_kernel(const T *__restrict__ src, long n, NoData nd, 
         mask[i] = hb_valid(hb_to_f32<T>(src[i]), nd) ? 1 : 0;
 }
 
+// ---- output dtype conversion (raster_array.py:353-387) ------------------------------------------------------------------
+template <typename O> struct OutCvt;
+template <> struct OutCvt<float> {
+    static __device__ __forceinline__ float cvt(float v, float nd) { return isnan(v) ? nd : v; }
+};
+template <typename O> struct OutCvt {
+    // np.round (half to even) in float32, clip to the integer range, cast; NaN -> nodata
+    static __device__ __forceinline__ O cvt(float v, float nd)
+    {
+        constexpr float lo = std::is_signed<O>::value ? -32768.f : 0.f;
+        constexpr float hi = sizeof(O) == 1 ? 255.f : (std::is_signed<O>::value ? 32767.f : 65535.f);
+        const float r = fminf(fmaxf(rintf(v), lo), hi);
+        return isnan(v) ? (O)nd : (O)(int)r;
+    }
+};
+
+template <typename O>
+__global__ void convert_dtype_kernel(const float *__restrict__ src, long n, float nd, O *__restrict__ dst)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long n4 = n / 4;
+    const bool vec = (((uintptr_t)src) % 16 == 0) && (((uintptr_t)dst) % (4 * sizeof(O)) == 0);
+    long done = 0;
+    if (vec) {
+        for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += stride) {
+            const uint4 raw = hb_ldg_stream16(src + 4 * g);
+            const float v[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z),
+                                __uint_as_float(raw.w)};
+            struct __align__(4 * sizeof(O)) Pack { O o[4]; } pk;
+#pragma unroll
+            for (int k = 0; k < 4; k++) pk.o[k] = OutCvt<O>::cvt(v[k], nd);
+            reinterpret_cast<Pack *>(dst)[g] = pk;
+        }
+        done = n4 * 4;
+    }
+    for (long i = done + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = OutCvt<O>::cvt(src[i], nd);
+}
+
 // ---- full-coverage mask (kernel_model.py:375-409) -------------------------------------------------------------------
 // step 1: param pixel is "covered" iff it is valid and every in-range pixel of the other image's mask under its
 //         footprint is valid (== GDAL average of the 0/1 mask is exactly 1) and the footprint is not empty.
@@ -918,6 +956,39 @@ extern "C" int hb_apply_same_grid(const void *src_dev, int src_dtype, int has_no
         default: HB_REQUIRE(false, "hb_apply_same_grid: unknown dtype %d", src_dtype);
     }
     HB_LAUNCH_OK("apply_same_grid_kernel");
+    return 0;
+}
+
+extern "C" int hb_convert_dtype(const float *src_dev, long n, int out_dtype, int has_nodata, double nodata, void *dst_dev,
+                                void *stream)
+{
+    HB_REQUIRE(src_dev && dst_dev && n > 0, "hb_convert_dtype: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const float nd = has_nodata ? (float)nodata : 0.f;
+    const unsigned grid = grid_for((n + 3) / 4, 256, 16);
+    switch (out_dtype) {
+        case HB_U8:
+            HB_REQUIRE(!has_nodata || (nodata >= 0 && nodata <= 255 && nodata == floor(nodata)),
+                       "hb_convert_dtype: nodata %g cannot be safely cast to uint8", nodata);
+            convert_dtype_kernel<uint8_t><<<grid, 256, 0, st>>>(src_dev, n, nd, (uint8_t *)dst_dev);
+            break;
+        case HB_U16:
+            HB_REQUIRE(!has_nodata || (nodata >= 0 && nodata <= 65535 && nodata == floor(nodata)),
+                       "hb_convert_dtype: nodata %g cannot be safely cast to uint16", nodata);
+            convert_dtype_kernel<uint16_t><<<grid, 256, 0, st>>>(src_dev, n, nd, (uint16_t *)dst_dev);
+            break;
+        case HB_I16:
+            HB_REQUIRE(!has_nodata || (nodata >= -32768 && nodata <= 32767 && nodata == floor(nodata)),
+                       "hb_convert_dtype: nodata %g cannot be safely cast to int16", nodata);
+            convert_dtype_kernel<int16_t><<<grid, 256, 0, st>>>(src_dev, n, nd, (int16_t *)dst_dev);
+            break;
+        case HB_F32:
+            convert_dtype_kernel<float><<<grid, 256, 0, st>>>(src_dev, n, has_nodata ? (float)nodata : __builtin_nanf(""),
+                                                             (float *)dst_dev);
+            break;
+        default: HB_REQUIRE(false, "hb_convert_dtype: unsupported output dtype %d", out_dtype);
+    }
+    HB_LAUNCH_OK("convert_dtype_kernel");
     return 0;
 }
 

@@ -349,6 +349,16 @@ def _convert_dtype(ra: RasterArray, dtype: str, nodata):
     is_nan_nd = nodata is not None and isinstance(nodata, float) and np.isnan(nodata)
     if dtype in ('float32', None) and (nodata is None or is_nan_nd):
         return array
+    _OUT_CODES = {'uint8': 0, 'uint16': 1, 'float32': 2, 'int16': 3}
+    if is_tensor(array) and array.is_cuda and array.dtype == torch.float32 and dtype in _OUT_CODES:
+        # one native pass: round half-to-even, clip, cast, nodata substitution
+        from homonim_b200 import kernel_model as km
+        src = array.contiguous()
+        out = torch.empty(src.shape, dtype=getattr(torch, dtype), device=src.device)
+        has, nd = (0, 0.0) if nodata is None else (1, float(nodata))
+        km._call('hb_convert_dtype', src.data_ptr(), src.numel(), _OUT_CODES[dtype], has, nd, out.data_ptr(),
+                 km._stream())
+        return out
     if is_tensor(array):
         mask = ~torch.isnan(array)
         out = array

@@ -30,10 +30,10 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 2
+#define HB_ABI_VERSION 3
 
 /* storage dtype of a source raster plane */
-enum { HB_U8 = 0, HB_U16 = 1, HB_F32 = 2 };
+enum { HB_U8 = 0, HB_U16 = 1, HB_F32 = 2, HB_I16 = 3 };   /* HB_I16: output of hb_convert_dtype only */
 /* homonim.enums.Model (homonim/enums.py:22-42) */
 enum { HB_MODEL_GAIN = 0, HB_MODEL_GAIN_BLK_OFFSET = 1, HB_MODEL_GAIN_OFFSET = 2 };
 /* up-sampling methods of hb_resample_up */
@@ -133,6 +133,13 @@ int hb_resample_up(const float *src_dev, long nb, long hs, long ws, int has_noda
 int hb_full_coverage_mask(const uint8_t *in_mask_dev, long hi, long wi, const float *params_dev, long hp, long wp,
                           double sx, double ox, double sy, double oy, int kh, int kw, uint8_t *out_dev,
                           void *workspace_dev, void *stream);
+
+/* Output dtype conversion of a corrected float32 plane (nodata = NaN), RasterArray._convert_array_dtype
+ * (raster_array.py:353-387) as used by to_rio_dataset (:493-500): integer outputs are rounded half-to-even and clipped
+ * to the type's range; NaN pixels become `nodata` (0 when has_nodata == 0).  out_dtype: HB_U8, HB_U16, HB_I16 or HB_F32
+ * (nodata substitution only).  One pass: 4 bytes read + sizeof(out) written per pixel. */
+int hb_convert_dtype(const float *src_dev, long n, int out_dtype, int has_nodata, double nodata, void *dst_dev,
+                     void *stream);
 
 /* validity mask of a raster plane as uint8 (RasterArray.mask / mask_ra, raster_array.py:298-327) */
 int hb_valid_mask(const void *src_dev, int src_dtype, long n, int has_nodata, double nodata, uint8_t *mask_dev,

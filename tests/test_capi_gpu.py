@@ -392,3 +392,50 @@ def test_resample_up_fast_paths(nb, ratio, shift):
     assert lib.hb_launch_count() == (3 if nb == 1 else 1)
     assert_same_mask(got, expected, 'cubic_spline')
     assert rel_err(got, expected, 1e-3) <= 1e-6
+
+
+@pytest.mark.parametrize('dtype, nodata', [('uint8', 0), ('uint16', 0), ('uint16', 65535), ('int16', -32768),
+                                           ('uint16', None), ('float32', -9999.0)])
+def test_convert_dtype(dtype, nodata):
+    """ hb_convert_dtype against RasterArray._convert_array_dtype (raster_array.py:353-387) restated with numpy: round
+    half to even in float32, clip to the integer range, cast, nodata where the corrected pixel is NaN. """
+    rng = np.random.default_rng(8)
+    n = 100003
+    corr = (rng.normal(300.0, 400.0, n)).astype('float32')
+    corr[::7] = np.round(corr[::7]) + 0.5                           # exact ties
+    corr[5:50] = [-1e9, 1e9, 65535.4, 65535.5, 65536.0, -0.5, 0.5, 1.5, 2.5, 254.5, 255.5, 32767.5, -32768.5] + [0.0] * 32
+    corr[rng.integers(0, n, 5000)] = NAN
+    mask = ~np.isnan(corr)
+    exp = corr.copy()
+    if dtype != 'float32':
+        info = np.iinfo(dtype)
+        with np.errstate(invalid='ignore'):
+            exp = np.clip(np.round(exp), info.min, info.max)
+            exp = np.where(mask, exp, 0).astype(dtype)
+    if nodata is not None:
+        exp[~mask] = nodata
+    lib = _native.lib()
+    src = torch.from_numpy(corr).cuda()
+    out = torch.empty(n, dtype=getattr(torch, dtype), device='cuda')
+    code = {'uint8': _native.HB_U8, 'uint16': _native.HB_U16, 'int16': _native.HB_I16, 'float32': _native.HB_F32}[dtype]
+    _native.check(lib.hb_convert_dtype(src.data_ptr(), n, code, int(nodata is not None),
+                                       float(nodata) if nodata is not None else 0.0, out.data_ptr(), _stream()))
+    got = out.cpu().numpy()
+    if dtype == 'float32':
+        assert np.array_equal(got, exp)
+    else:
+        assert np.array_equal(got.astype('int64'), exp.astype('int64'))
+
+
+def test_process_out_profile_dtype():
+    """ RasterFuse.process(out_profile=dict(dtype='uint16', nodata=0)): the corrected image converted on the device. """
+    from homonim_b200 import Model, RasterFuse
+    from homonim_b200.synthetic import make_pair
+    src_ra, ref_ra = make_pair(40, 36, 8, bands=2, dtype='uint16', mu=3000.0, seed=3, device='cuda', src_nodata=0)
+    with RasterFuse(src_ra, ref_ra) as fuse:
+        f32, _ = fuse.process(model=Model.gain_blk_offset, kernel_shape=(5, 5))
+        u16, _ = fuse.process(model=Model.gain_blk_offset, kernel_shape=(5, 5), out_profile=dict(dtype='uint16', nodata=0))
+    assert u16.array.dtype == torch.uint16 and u16.nodata == 0
+    a = f32.array.cpu().numpy()
+    exp = np.where(np.isnan(a), 0, np.clip(np.round(np.nan_to_num(a)), 0, 65535)).astype('uint16')
+    assert np.array_equal(u16.array.cpu().numpy().view('uint16'), exp)
