@@ -292,3 +292,64 @@ def test_process_plan_cache_follows_in_place_edits():
         holed, _ = fuse.process(**kw)
         assert bool(torch.isnan(holed.array[0, :40, :40]).all())
         assert torch.equal(holed.array[1].nan_to_num(-1), scaled.array[1].nan_to_num(-1))
+
+
+def _random_pair(rng, dtype):
+    """ A small source / reference pair on random (mis-aligned, non-integer ratio) north-up grids, numpy arrays. """
+    from homonim_b200 import Affine
+    ratio = float(rng.choice([2.0, 2.5, 3.0, 4.0, 5.0, 6.4, 8.0, 12.0, 20.0]))
+    hp, wp = int(rng.integers(14, 30)), int(rng.integers(14, 30))
+    ws = int(wp * ratio) // 4 * 4 if rng.random() < 0.7 else int(wp * ratio) - int(rng.integers(1, 4))
+    hs = int(hp * ratio) - int(rng.integers(0, 3))
+    mu = {'uint8': 120.0, 'uint16': 3000.0, 'float32': 0.3}[dtype]
+    yy, xx = np.mgrid[0:hs, 0:ws]
+    tex = np.sin(xx / (3.0 * ratio)) * np.cos(yy / (4.0 * ratio)) + 0.3 * np.sin((xx + 2 * yy) / (1.7 * ratio))
+    src = mu * (1.0 + 0.3 * tex) + 0.02 * mu * rng.standard_normal((hs, ws))
+    nodata = float('nan') if dtype == 'float32' else 0
+    if dtype != 'float32':
+        src = np.clip(np.round(src), 1, np.iinfo(dtype).max)
+    src = src.astype(dtype)
+    for _ in range(int(rng.integers(0, 4))):                       # nodata rectangles, some touching the border
+        y, x = int(rng.integers(0, hs)), int(rng.integers(0, ws))
+        src[y:y + int(rng.integers(2, 4 * ratio)), x:x + int(rng.integers(2, 4 * ratio))] = nodata
+    # reference: 3 pixels larger than the source on every side, origin shifted by a random fraction of a source pixel
+    res = 0.5
+    ref_res = res * ratio
+    shift = (float(rng.choice([0.0, 0.0, rng.random() * ratio])), float(rng.choice([0.0, 0.0, rng.random() * ratio])))
+    src_tf = Affine(res, 0, 1000.0, 0, -res, 5000.0)
+    ref_tf = Affine(ref_res, 0, 1000.0 - 3 * ref_res - shift[0] * res, 0, -ref_res, 5000.0 + 3 * ref_res + shift[1] * res)
+    hr, wr = hp + 7, wp + 7
+    ry, rx = np.mgrid[0:hr, 0:wr]
+    gain = 0.6 + 0.2 * np.sin(rx / 5.0 + ry / 9.0)
+    ref = (gain * mu * (1.0 + 0.3 * np.sin((rx - 3) / 3.0) * np.cos((ry - 3) / 4.0)) + 0.05 * mu
+           + 0.01 * mu * rng.standard_normal((hr, wr))).astype('float32')
+    return src, src_tf, nodata, ref, ref_tf
+
+
+@pytest.mark.parametrize('seed', range(24))
+def test_refspace_random_geometry_vs_oracle(seed):
+    """ proc_crs = ref on random grids (non-integer ratios, sub-pixel offsets, widths that do / do not take the fast
+    kernels, nodata touching the borders): masks exact, parameters and corrected pixels within 1e-4 of the oracle. """
+    kmnp = _oracle()
+    rng = np.random.default_rng(1000 + seed)
+    dtype = ['uint8', 'uint16', 'float32'][seed % 3]
+    model, kernel_shape, thresh = [(Model.gain, (1, 1), None), (Model.gain_blk_offset, (5, 5), None),
+                                   (Model.gain_offset, (5, 5), 0.25), (Model.gain_blk_offset, (3, 7), None)][seed % 4]
+    src, src_tf, nodata, ref, ref_tf = _random_pair(rng, dtype)
+    crs = CRS.from_epsg(32735)
+    src_ra = RasterArray(torch.from_numpy(src).cuda(), crs, src_tf, nodata=nodata)
+    ref_ra = RasterArray(torch.from_numpy(ref).cuda(), crs, ref_tf, nodata=float('nan'))
+    with RasterFuse(src_ra, ref_ra, proc_crs=ProcCrs.ref) as fuse:
+        corr_ra, param_ra = fuse.process(model=model, kernel_shape=kernel_shape, param_filename='p',
+                                         model_config=dict(r2_inpaint_thresh=thresh))
+    with np.errstate(all='ignore'):
+        exp_params, _, exp_corr = kmnp.fuse_band_blocks(src, tuple(src_tf), nodata, ref, tuple(ref_tf), float('nan'),
+                                                        model, kernel_shape, 'ref', True, thresh)
+    got_params = param_ra.to_host().array
+    valid_src = src[src != nodata] if not np.isnan(nodata) else src[~np.isnan(src)]
+    if kernel_shape == (1, 1):
+        got_params, exp_params = got_params[:2], exp_params[:2]
+    check_params(got_params, exp_params, float(np.mean(valid_src.astype('float64'))), f'seed {seed} params',
+                 r2_robust=model == Model.gain_blk_offset)
+    check_corr(corr_ra.to_host().array[0] if corr_ra.array.ndim == 3 else corr_ra.to_host().array,
+               exp_corr.astype('float32'), f'seed {seed} corr')
