@@ -105,7 +105,7 @@ template <int MODEL, bool WANT_R2, int NQ, int C, bool ALIGNED>
 __global__ void __launch_bounds__(kFitThreads, (NQ >= 5 && C == 4) ? HB_FIT_MIN_CTAS - 1 : HB_FIT_MIN_CTAS)
 fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__restrict__ ref, NoData nd_r,
                      FitGeom g, const double *__restrict__ norm, float *__restrict__ params,
-                     float *__restrict__ sums_out)
+                     float *__restrict__ sums_out, float *__restrict__ corr_out)
 {
     constexpr bool NORM = (MODEL == HB_MODEL_GAIN_BLK_OFFSET);
     constexpr bool HAS_N = (NQ > 2);
@@ -405,6 +405,25 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
             o_rs[i] = fR; o_ss[i] = fS; o_n[i] = mask ? fN : -1.f;   // count plane: -1 marks "outside the mask"
         }
         // ---- store -------------------------------------------------------------------------------------------------
+        if (corr_out != nullptr) {
+            // fused apply (KernelModel.apply, kernel_model.py:461): corr = gain * src + offset with the centre row's
+            // ORIGINAL source pixels (re-read: they entered the window kh/2 rows ago, an L2 hit), two float32
+            // roundings as numpy; the parameters are not materialised
+            float sc[C], rdummy[C];
+            load_row(y, sc, rdummy);
+            float oc[C];
+#pragma unroll
+            for (int i = 0; i < C; i++) oc[i] = __fadd_rn(__fmul_rn(o_gain[i], sc[i]), o_off[i]);
+            float *crow = corr_out + y * g.w;
+            if (vec_ok && C == 4) {
+                *reinterpret_cast<float4 *>(crow + cx) = make_float4(oc[0], oc[C > 1 ? 1 : 0], oc[C > 2 ? 2 : 0], oc[C > 3 ? 3 : 0]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < C; i++)
+                    if (col_in[i]) crow[cx + i] = oc[i];
+            }
+            continue;
+        }
         float *prow = params + y * g.w;
         if (vec_ok) {
             if (C == 4) {
@@ -445,7 +464,7 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
 
 template <int MODEL, bool WANT_R2, int NQ, int C>
 int launch_fit(const float *src, NoData nd_s, const float *ref, NoData nd_r, long h, long w, int kh, int kw,
-               const double *norm, float *params, float *sums, cudaStream_t stream)
+               const double *norm, float *params, float *sums, float *corr, cudaStream_t stream)
 {
     FitGeom g;
     g.h = h; g.w = w; g.kh = kh; g.kw = kw;
@@ -482,61 +501,81 @@ int launch_fit(const float *src, NoData nd_s, const float *ref, NoData nd_r, lon
     HB_REQUIRE(bands <= 65535, "hb_fit_same_grid: too many row bands");
     dim3 grid((unsigned)xtiles, (unsigned)bands);
     const bool aligned = (C == 4) && (w % 4 == 0) && (((uintptr_t)src) % 16 == 0) && (((uintptr_t)ref) % 16 == 0) &&
-                         (((uintptr_t)params) % 16 == 0) && (sums == nullptr || ((uintptr_t)sums) % 16 == 0);
+                         (((uintptr_t)params) % 16 == 0) && (sums == nullptr || ((uintptr_t)sums) % 16 == 0) &&
+                         (corr == nullptr || ((uintptr_t)corr) % 16 == 0);
     if (aligned)
         fit_same_grid_kernel<MODEL, WANT_R2, NQ, C, true><<<grid, kFitThreads, 0, stream>>>(src, nd_s, ref, nd_r, g,
-                                                                                           norm, params, sums);
+                                                                                           norm, params, sums, corr);
     else
         fit_same_grid_kernel<MODEL, WANT_R2, NQ, C, false><<<grid, kFitThreads, 0, stream>>>(src, nd_s, ref, nd_r, g,
-                                                                                            norm, params, sums);
+                                                                                            norm, params, sums, corr);
     HB_LAUNCH_OK("fit_same_grid_kernel");
     return 0;
 }
 
 template <int MODEL, bool WANT_R2, int NQ>
 int launch_fit_c(const float *src, NoData nd_s, const float *ref, NoData nd_r, long h, long w, int kh, int kw,
-                 const double *norm, float *params, float *sums, cudaStream_t stream)
+                 const double *norm, float *params, float *sums, float *corr, cudaStream_t stream)
 {
     // small rasters: 1 column per thread (128-column strips) so that the grid still spreads over the SMs
     if (h * w < (long)4 << 20)
-        return launch_fit<MODEL, WANT_R2, NQ, 1>(src, nd_s, ref, nd_r, h, w, kh, kw, norm, params, sums, stream);
-    return launch_fit<MODEL, WANT_R2, NQ, 4>(src, nd_s, ref, nd_r, h, w, kh, kw, norm, params, sums, stream);
+        return launch_fit<MODEL, WANT_R2, NQ, 1>(src, nd_s, ref, nd_r, h, w, kh, kw, norm, params, sums, corr, stream);
+    return launch_fit<MODEL, WANT_R2, NQ, 4>(src, nd_s, ref, nd_r, h, w, kh, kw, norm, params, sums, corr, stream);
 }
 
 }  // namespace
+
+static int fit_dispatch(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
+                        int ref_has_nodata, double ref_nodata, long h, long w, int model, int kh, int kw, int want_r2,
+                        const double *norm_dev, float *params_dev, float *sums_dev, float *corr_dev, void *stream,
+                        const char *who)
+{
+    HB_REQUIRE(src_dev && ref_dev && (params_dev || corr_dev) && h > 0 && w > 0, "%s: bad arguments", who);
+    HB_REQUIRE(kh >= 1 && kw >= 1 && (kh & 1) && (kw & 1), "%s: kernel shape must be odd and >= 1", who);
+    HB_REQUIRE(kw / 2 <= kMaxHalfW, "%s: kernel width %d > %d is not supported", who, kw, 2 * kMaxHalfW + 1);
+    HB_REQUIRE(kh / 2 <= 63, "%s: kernel height %d > 127 is not supported", who, kh);
+    const NoData nd_s = hb_make_nodata(src_has_nodata, src_nodata), nd_r = hb_make_nodata(ref_has_nodata, ref_nodata);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (model) {
+        case HB_MODEL_GAIN:
+            HB_REQUIRE(sums_dev == nullptr, "%s: sums are only produced for the gain-offset model", who);
+            if (want_r2)
+                return launch_fit_c<HB_MODEL_GAIN, true, 5>(src_dev, nd_s, ref_dev, nd_r, h, w, kh, kw, nullptr,
+                                                            params_dev, nullptr, corr_dev, st);
+            return launch_fit_c<HB_MODEL_GAIN, false, 2>(src_dev, nd_s, ref_dev, nd_r, h, w, kh, kw, nullptr,
+                                                         params_dev, nullptr, corr_dev, st);
+        case HB_MODEL_GAIN_BLK_OFFSET:
+            HB_REQUIRE(norm_dev != nullptr, "%s: gain-blk-offset needs the block normalisation", who);
+            HB_REQUIRE(sums_dev == nullptr, "%s: sums are only produced for the gain-offset model", who);
+            if (want_r2)
+                return launch_fit_c<HB_MODEL_GAIN_BLK_OFFSET, true, 5>(src_dev, nd_s, ref_dev, nd_r, h, w, kh, kw,
+                                                                       norm_dev, params_dev, nullptr, corr_dev, st);
+            return launch_fit_c<HB_MODEL_GAIN_BLK_OFFSET, false, 2>(src_dev, nd_s, ref_dev, nd_r, h, w, kh, kw,
+                                                                    norm_dev, params_dev, nullptr, corr_dev, st);
+        case HB_MODEL_GAIN_OFFSET:
+            if (want_r2)
+                return launch_fit_c<HB_MODEL_GAIN_OFFSET, true, 5>(src_dev, nd_s, ref_dev, nd_r, h, w, kh, kw, nullptr,
+                                                                   params_dev, sums_dev, corr_dev, st);
+            return launch_fit_c<HB_MODEL_GAIN_OFFSET, false, 4>(src_dev, nd_s, ref_dev, nd_r, h, w, kh, kw, nullptr,
+                                                                params_dev, sums_dev, corr_dev, st);
+    }
+    HB_REQUIRE(false, "%s: unknown model %d", who, model);
+}
 
 extern "C" int hb_fit_same_grid(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
                                 int ref_has_nodata, double ref_nodata, long h, long w, int model, int kh, int kw,
                                 int want_r2, const double *norm_dev, float *params_dev, float *sums_dev, void *stream)
 {
-    HB_REQUIRE(src_dev && ref_dev && params_dev && h > 0 && w > 0, "hb_fit_same_grid: bad arguments");
-    HB_REQUIRE(kh >= 1 && kw >= 1 && (kh & 1) && (kw & 1), "hb_fit_same_grid: kernel shape must be odd and >= 1");
-    HB_REQUIRE(kw / 2 <= kMaxHalfW, "hb_fit_same_grid: kernel width %d > %d is not supported", kw, 2 * kMaxHalfW + 1);
-    HB_REQUIRE(kh / 2 <= 63, "hb_fit_same_grid: kernel height %d > 127 is not supported", kh);
-    const NoData nd_s = hb_make_nodata(src_has_nodata, src_nodata), nd_r = hb_make_nodata(ref_has_nodata, ref_nodata);
-    cudaStream_t st = (cudaStream_t)stream;
-    switch (model) {
-        case HB_MODEL_GAIN:
-            HB_REQUIRE(sums_dev == nullptr, "hb_fit_same_grid: sums are only produced for the gain-offset model");
-            if (want_r2)
-                return launch_fit_c<HB_MODEL_GAIN, true, 5>(src_dev, nd_s, ref_dev, nd_r, h, w, kh, kw, nullptr,
-                                                            params_dev, nullptr, st);
-            return launch_fit_c<HB_MODEL_GAIN, false, 2>(src_dev, nd_s, ref_dev, nd_r, h, w, kh, kw, nullptr,
-                                                         params_dev, nullptr, st);
-        case HB_MODEL_GAIN_BLK_OFFSET:
-            HB_REQUIRE(norm_dev != nullptr, "hb_fit_same_grid: gain-blk-offset needs the block normalisation");
-            HB_REQUIRE(sums_dev == nullptr, "hb_fit_same_grid: sums are only produced for the gain-offset model");
-            if (want_r2)
-                return launch_fit_c<HB_MODEL_GAIN_BLK_OFFSET, true, 5>(src_dev, nd_s, ref_dev, nd_r, h, w, kh, kw,
-                                                                       norm_dev, params_dev, nullptr, st);
-            return launch_fit_c<HB_MODEL_GAIN_BLK_OFFSET, false, 2>(src_dev, nd_s, ref_dev, nd_r, h, w, kh, kw,
-                                                                    norm_dev, params_dev, nullptr, st);
-        case HB_MODEL_GAIN_OFFSET:
-            if (want_r2)
-                return launch_fit_c<HB_MODEL_GAIN_OFFSET, true, 5>(src_dev, nd_s, ref_dev, nd_r, h, w, kh, kw, nullptr,
-                                                                   params_dev, sums_dev, st);
-            return launch_fit_c<HB_MODEL_GAIN_OFFSET, false, 4>(src_dev, nd_s, ref_dev, nd_r, h, w, kh, kw, nullptr,
-                                                                params_dev, sums_dev, st);
-    }
-    HB_REQUIRE(false, "hb_fit_same_grid: unknown model %d", model);
+    HB_REQUIRE(params_dev != nullptr, "hb_fit_same_grid: bad arguments");
+    return fit_dispatch(src_dev, src_has_nodata, src_nodata, ref_dev, ref_has_nodata, ref_nodata, h, w, model, kh, kw,
+                        want_r2, norm_dev, params_dev, sums_dev, nullptr, stream, "hb_fit_same_grid");
+}
+
+extern "C" int hb_fit_apply_same_grid(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
+                                      int ref_has_nodata, double ref_nodata, long h, long w, int model, int kh, int kw,
+                                      const double *norm_dev, float *corr_dev, void *stream)
+{
+    HB_REQUIRE(corr_dev != nullptr, "hb_fit_apply_same_grid: bad arguments");
+    return fit_dispatch(src_dev, src_has_nodata, src_nodata, ref_dev, ref_has_nodata, ref_nodata, h, w, model, kh, kw, 0,
+                        norm_dev, nullptr, nullptr, corr_dev, stream, "hb_fit_apply_same_grid");
 }

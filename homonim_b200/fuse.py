@@ -233,6 +233,9 @@ class RasterFuse:
         ref_ra = self._ref_block(band_i)
         if stage and not src_ra.is_device:
             src_ra, ref_ra = src_ra.to_device(), ref_ra.to_device()
+        if isinstance(model, SrcSpaceModel) and not want_params and model.can_fuse(src_ra, ref_ra):
+            # fit + apply in one kernel: the parameters are not wanted, so they are never written
+            return model.fuse(src_ra, ref_ra, out=out), None
         if isinstance(model, RefSpaceModel) and model.can_fuse(src_ra, ref_ra):
             # fit + apply as one native call (same kernels, same order; the parameters are only materialised for the
             # caller when a parameter raster was asked for)

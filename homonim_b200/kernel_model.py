@@ -508,6 +508,38 @@ class RefSpaceModel(KernelModel):
 class SrcSpaceModel(KernelModel):
     """ Fit and apply on the source grid (reference kernel_model.py:506-535). """
 
+    def can_fuse(self, src_ra: RasterArray, ref_ra: RasterArray) -> bool:
+        """ True when apply(fit()) can run with the apply step fused into the fit kernel (`fuse`): the parameters are
+        final after the fit (no R2 in-painting), no partial-coverage masking, no per-entry-point timer active. """
+        if self._mask_partial or KernelTimer.active is not None:
+            return False
+        return not (self._model == Model.gain_offset and self._r2_inpaint_thresh is not None)
+
+    def fuse(self, src_ra: RasterArray, ref_ra: RasterArray, out=None) -> RasterArray:
+        """
+        ``apply(src_ra, fit(src_ra, ref_ra))`` without materialising the parameters: the reference image is resampled to
+        the source grid (kernel_model.py:518-520) and ``hb_fit_apply_same_grid`` writes the corrected pixels straight
+        from the fit kernel's epilogue (8 bytes in + 4 out per pixel instead of 16 + 16).  Bit-identical to the two-step
+        path.
+        """
+        _require_torch()
+        on_device = (src_ra.is_device and ref_ra.is_device) or out is not None
+        resampling = self._get_resampling(ref_ra.res, src_ra.res)
+        src_t, ref_t = _to_device(src_ra.array), _to_device(ref_ra.array)
+        ref_us = _resample_plane(ref_t, ref_ra.transform, ref_ra.nodata, src_ra.shape, src_ra.transform, resampling)
+        src_f = _as_f32_plane(src_t, src_ra.nodata).contiguous()
+        h, w = int(src_f.shape[-2]), int(src_f.shape[-1])
+        corr = self._check_out(out, h, w, src_f.device)
+        norm = None
+        if self._model == Model.gain_blk_offset:
+            norm = self._block_norm(src_f, src_ra.nodata, ref_us, NAN)
+        s_has, s_nd = _nodata_args(src_ra.nodata)
+        kh, kw = self._kernel_shape
+        _call('hb_fit_apply_same_grid', src_f.data_ptr(), s_has, s_nd, ref_us.data_ptr(), 1, NAN, h, w,
+              _MODEL_CODES[self._model], kh, kw, norm.data_ptr() if norm is not None else None, corr.data_ptr(),
+              _stream())
+        return RasterArray(_result(corr, on_device), src_ra.crs, src_ra.transform, nodata=NAN)
+
     def fit(self, src_ra: RasterArray, ref_ra: RasterArray) -> RasterArray:
         _require_torch()
         on_device = src_ra.is_device and ref_ra.is_device

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 3
+#define HB_ABI_VERSION 4
 
 /* storage dtype of a source raster plane */
 enum { HB_U8 = 0, HB_U16 = 1, HB_F32 = 2, HB_I16 = 3 };   /* HB_I16: output of hb_convert_dtype only */
@@ -81,6 +81,15 @@ int hb_block_norm(const float *src_dev, int src_has_nodata, double src_nodata, c
 int hb_fit_same_grid(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
                      int ref_has_nodata, double ref_nodata, long h, long w, int model, int kh, int kw, int want_r2,
                      const double *norm_dev, float *params_dev, float *sums_dev, void *stream);
+
+/* Same-grid fit fused with the apply step: corr = gain * src + offset (KernelModel.apply, kernel_model.py:442-463) of the
+ * parameters hb_fit_same_grid would produce, written straight from the fit kernel's epilogue -- the parameters never
+ * reach memory (8 bytes in + 4 out per pixel instead of 16 + 16 for fit then apply).  For the models / options whose
+ * parameters are final after the fit: gain, gain-blk-offset (norm_dev as for hb_fit_same_grid), and gain-offset without
+ * R2 in-painting.  corr_dev: float32 [h][w]; NaN where either input is invalid. */
+int hb_fit_apply_same_grid(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
+                           int ref_has_nodata, double ref_nodata, long h, long w, int model, int kh, int kw,
+                           const double *norm_dev, float *corr_dev, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Low-R2 in-painting and gain refit: kernel_model.py:361-371 (rasterio.fill.fillnodata == GDALFillNodata with

@@ -353,3 +353,32 @@ def test_refspace_random_geometry_vs_oracle(seed):
                  r2_robust=model == Model.gain_blk_offset)
     check_corr(corr_ra.to_host().array[0] if corr_ra.array.ndim == 3 else corr_ra.to_host().array,
                exp_corr.astype('float32'), f'seed {seed} corr')
+
+
+@pytest.mark.parametrize('model, kernel_shape, thresh', [
+    (Model.gain_offset, (7, 5), None), (Model.gain_blk_offset, (5, 5), None), (Model.gain, (3, 3), None),
+])
+def test_srcspace_fused_equals_fit_then_apply(model, kernel_shape, thresh):
+    """ SrcSpaceModel.fuse (apply fused into the fit kernel's epilogue, hb_fit_apply_same_grid -- what RasterFuse.process
+    uses when no parameter raster is asked for) is bit-identical to fit() followed by apply(). """
+    from homonim_b200 import SrcSpaceModel
+    src_ra, ref_ra = make_pair(150, 131, 2, bands=1, dtype='float32', mu=0.3, seed=4, device='cuda',
+                               src_nodata=float('nan'))
+    src = RasterArray(src_ra.array[0].contiguous(), src_ra.crs, src_ra.transform, nodata=float('nan'))
+    ref = RasterArray(ref_ra.array[0].contiguous(), ref_ra.crs, ref_ra.transform, nodata=float('nan'))
+    km = SrcSpaceModel(model, kernel_shape, r2_inpaint_thresh=thresh)
+    assert km.can_fuse(src, ref)
+    corr = km.apply(src, km.fit(src, ref))
+    fused = km.fuse(src, ref)
+    assert torch.equal(torch.isnan(fused.array), torch.isnan(corr.array))
+    assert torch.equal(fused.array.nan_to_num(-1.0, posinf=-2.0, neginf=-3.0),
+                       corr.array.nan_to_num(-1.0, posinf=-2.0, neginf=-3.0))
+    assert not SrcSpaceModel(Model.gain_offset, (5, 5), r2_inpaint_thresh=0.25).can_fuse(src, ref)
+    # through RasterFuse.process: without a parameter raster the fused kernel runs, with one the two-step path does
+    # (both on the reference block cropped to the source extent)
+    with RasterFuse(src_ra, ref_ra, proc_crs=ProcCrs.src) as fuse:
+        kw = dict(model=model, kernel_shape=kernel_shape, model_config=dict(r2_inpaint_thresh=thresh))
+        got, none = fuse.process(**kw)
+        two_step, params = fuse.process(param_filename='p', **kw)
+    assert none is None and params is not None
+    assert torch.equal(got.array.nan_to_num(-1.0), two_step.array.nan_to_num(-1.0))
