@@ -934,6 +934,8 @@ upsample_fixup_kernel(const T *__restrict__ src, NoData nd, const float *__restr
 {
     constexpr int NOUT = (NB == 2 && !APPLY) ? 2 : 1;
     constexpr int kFixWarps = kFixThreads / 32;
+    __shared__ double s_wy[kFixWarps][32][4];
+    __shared__ int s_jc[kFixWarps][32];
     const int lane = threadIdx.x & 31;
     const long warp_id = (long)blockIdx.x * kFixWarps + (threadIdx.x >> 5);
     const long n_warps = (long)gridDim.x * kFixWarps;
@@ -945,9 +947,18 @@ upsample_fixup_kernel(const T *__restrict__ src, NoData nd, const float *__restr
         const long idx = list[e / kFixSplit];
         const int part = (int)(e % kFixSplit);
         const long ky = idx / fw - 1, kx = idx % fw - 1;
-        // destination rows / columns of the cell: the i with up_cell(i) == k (monotone in i)
-        long ya = up_first_index(g.sy, g.oy, ky, g.hs), yb = up_first_index(g.sy, g.oy, ky + 1, g.hs);
-        const long xa = up_first_index(g.sx, g.ox, kx, g.ws), xb = up_first_index(g.sx, g.ox, kx + 1, g.ws);
+        // destination rows / columns of the cell: the i with up_cell(i) == k (monotone in i); the four bounds are
+        // independent chains of double-precision operations: one lane each
+        long ya, yb, xa, xb;
+        {
+            long mine = 0;
+            if (lane == 0) mine = up_first_index(g.sy, g.oy, ky, g.hs);
+            else if (lane == 1) mine = up_first_index(g.sy, g.oy, ky + 1, g.hs);
+            else if (lane == 2) mine = up_first_index(g.sx, g.ox, kx, g.ws);
+            else if (lane == 3) mine = up_first_index(g.sx, g.ox, kx + 1, g.ws);
+            ya = __shfl_sync(0xffffffffu, mine, 0); yb = __shfl_sync(0xffffffffu, mine, 1);
+            xa = __shfl_sync(0xffffffffu, mine, 2); xb = __shfl_sync(0xffffffffu, mine, 3);
+        }
         if (yb <= ya || xb <= xa) continue;
         {
             const long chunk = (yb - ya + kFixSplit - 1) / kFixSplit;
@@ -955,6 +966,21 @@ upsample_fixup_kernel(const T *__restrict__ src, NoData nd, const float *__restr
             yb = min(yb, ya + chunk);
             if (yb <= ya) continue;
         }
+        // the rows' y-weights and centre rows are the same for every column: lane r prepares row ya + r once
+        const bool cached = (yb - ya) <= 32;
+        __syncwarp();
+        if (cached && ya + lane < yb) {
+            const double srcy = up_src_coord(g.sy, g.oy, ya + lane);
+            long cy = (long)floor(srcy + 1e-10);
+            if (cy == g.hp) cy--;
+            const long jc = cy - (ky - 1);
+            double wy[4];
+            bspline_weights(srcy - 0.5 - (double)ky, wy);
+#pragma unroll
+            for (int j = 0; j < 4; j++) s_wy[threadIdx.x >> 5][lane][j] = wy[j];
+            s_jc[threadIdx.x >> 5][lane] = (srcy >= 0.0 && jc >= 0 && jc <= 2) ? (int)jc : -1;
+        }
+        __syncwarp();
         // every 4-pixel group (= lane of the fast kernel) that touches the cell was skipped there: do whole groups
         const long ga = (xa / kPpt) * kPpt, gb = min(((xb - 1) / kPpt + 1) * kPpt, g.ws);
         for (long X = ga + lane; X < gb; X += 32) {
@@ -1015,17 +1041,26 @@ upsample_fixup_kernel(const T *__restrict__ src, NoData nd, const float *__restr
                 for (int u = 0; u < kBatch; u++) {
                     const long Y = Yc + u;
                     if (Y >= yb) break;
-                    const double srcy = up_src_coord(g.sy, g.oy, Y);
-                    long cy = (long)floor(srcy + 1e-10);
-                    if (cy == g.hp) cy--;
-                    const long jc = cy - (ky - 1);           // 0 .. 2
-                    bool c_ok = (srcy >= 0.0) && (jc == 0 ? cen[0] : (jc == 1 ? cen[1] : (jc == 2 ? cen[2] : false)));
+                    int jc;                                  // tap row of the centre pixel (0 .. 2), -1: out of range
+                    double wy[4];
+                    if (cached) {
+                        const int ri = (int)(Y - ya);
+                        jc = s_jc[threadIdx.x >> 5][ri];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) wy[j] = s_wy[threadIdx.x >> 5][ri][j];
+                    } else {
+                        const double srcy = up_src_coord(g.sy, g.oy, Y);
+                        long cy = (long)floor(srcy + 1e-10);
+                        if (cy == g.hp) cy--;
+                        const long j0 = cy - (ky - 1);
+                        jc = (srcy >= 0.0 && j0 >= 0 && j0 <= 2) ? (int)j0 : -1;
+                        bspline_weights(srcy - 0.5 - (double)ky, wy);
+                    }
+                    bool c_ok = (jc == 0 ? cen[0] : (jc == 1 ? cen[1] : (jc == 2 ? cen[2] : false)));
                     const float s = sv[u];
                     if (APPLY) c_ok = c_ok && hb_valid(s, nd);
                     float r[2] = {qnan, qnan};
                     if (c_ok) {
-                        double wy[4];
-                        bspline_weights(srcy - 0.5 - (double)ky, wy);
 #pragma unroll
                         for (int b = 0; b < NB; b++) {
                             double acc = 0.0, acc_w = 0.0;
