@@ -40,8 +40,14 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kPpt = 4;                    // destination pixels per lane
 constexpr int kWarpW = 32 * kPpt;          // destination columns per warp
-constexpr int kRb = 4;                     // rows per cp.async stage
-constexpr int kStages = 4;                 // stages in flight per warp
+#ifndef HB_POLY_RB
+#define HB_POLY_RB 4
+#endif
+#ifndef HB_POLY_STAGES
+#define HB_POLY_STAGES 4
+#endif
+constexpr int kRb = HB_POLY_RB;                     // rows per cp.async stage
+constexpr int kStages = HB_POLY_STAGES;                 // stages in flight per warp
 constexpr int kMaxRows = 128;              // destination rows per CTA (upper bound)
 constexpr int kRowTableBytes = kMaxRows * (16 + 4);   // per-CTA row table: 4 float y-weights + tap row per row
 
@@ -76,8 +82,8 @@ __device__ __forceinline__ pk2 pk(float lo, float hi)
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
     return r;
 }
-__device__ __forceinline__ float pk_lo(pk2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
-__device__ __forceinline__ float pk_hi(pk2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
+__device__ __forceinline__ float pk_lo(pk2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); (void)hi; return lo; }
+__device__ __forceinline__ float pk_hi(pk2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); (void)lo; return hi; }
 __device__ __forceinline__ pk2 pk_fma(pk2 a, pk2 b, pk2 c) { pk2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ pk2 pk_mul(pk2 a, pk2 b) { pk2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
