@@ -129,6 +129,17 @@ static inline cudaError_t hb_pool_keep_memory()
     return err;
 }
 
+// True exactly once per (call site, device): for per-device one-time set-up such as cudaFuncSetAttribute (function
+// attributes belong to the device that is current when they are set).  `mask` is a call-site static.
+#include <atomic>
+static inline bool hb_first_on_device(std::atomic<unsigned long long> &mask)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    const unsigned long long bit = 1ull << dev;
+    return (mask.fetch_or(bit) & bit) == 0ull;
+}
+
 static inline int hb_sm_count()
 {
     static int sms = 0;

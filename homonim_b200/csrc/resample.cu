@@ -276,7 +276,7 @@ downsample_average_kernel(const T *__restrict__ src, long hs, long ws, NoData nd
         // shared-memory reads of a warp spread over the banks (the sum is over the same terms, in a fixed order)
         const long ncol = ix1 - ix0;
         long x = ix0 + ((ncol > 0) ? (long)(t % (int)ncol) : 0);
-        for (long i = 0; i < ncol; i++) {
+        for (long it = 0; it < ncol; it++) {
             double wx = 1.0;
             if (x == ix0u) wx = (ix0u + 1 == ix1u) ? 1.0 : 1.0 - (x_min - (double)ix0u);
             else if (x + 1 == ix1u) wx = 1.0 - ((double)ix1u - x_max);

@@ -1202,11 +1202,9 @@ int hb_up_poly_resample(const float *coarse, int nb, const UpPolyGeom &g, float 
     }
     {
         const size_t smem = kMaxRows * (sizeof(RowEntryD) + sizeof(int)) + (size_t)kWarps * kYfCols * 2 * 32 * sizeof(double2);
-        static bool attr_done = false;
-        if (!attr_done) {
+        static std::atomic<unsigned long long> attr_done{0ull};
+        if (hb_first_on_device(attr_done))
             HB_CUDA_OK(cudaFuncSetAttribute(upsample_yfirst_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_done = true;
-        }
         const long cta_w = (long)kWarpW * kWarps;
         const long gx = (g.ws + cta_w - 1) / cta_w;
         const long slots = (long)hb_sm_count() * 2;
