@@ -94,7 +94,7 @@ __device__ __forceinline__ void ds_fetch(const T *row, long c, long ws, T (&v)[8
 // <= 2 fractionally covered rows are added in double).  Phase 2: one thread per destination pixel combines its
 // footprint columns from shared memory with the fractional edge weights.
 template <typename T, bool ALIGNED>
-__global__ void __launch_bounds__(kDsThreads, HB_DS_MIN_CTAS)
+__global__ void __launch_bounds__(kDsThreads, (sizeof(T) == 4) ? HB_DS_MIN_CTAS - 1 : HB_DS_MIN_CTAS)
 downsample_average_kernel(const T *__restrict__ src, long hs, long ws, NoData nd, float *__restrict__ dst, long hd,
                           long wd, double sx, double ox, double sy, double oy, int ndc, int chunks)
 {
@@ -229,15 +229,45 @@ downsample_average_kernel(const T *__restrict__ src, long hs, long ws, NoData nd
         uint32_t icnt[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) { colsum[k] = 0.0; icnt[k] = 0; }
-#pragma unroll 4
-        for (long y = ya; y < yb; y++) {
-            T v[8]; uint32_t inb;
-            ds_fetch<T, ALIGNED>(src + y * ws, c, ws, v, inb);
+        if (ALIGNED && c >= 0 && c + 8 <= ws) {
+            // fast path (every vector of this thread inside the raster): 5 rows = ten 16-byte loads issued together
+            constexpr int kFb = 5;
+            const T *p = src + ya * ws + c;
+            for (long yb0 = ya; yb0 < yb; yb0 += kFb) {
+                uint4 raw[kFb][2];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const bool ok = ((inb >> k) & 1u) && ds_valid<T>(v[k], ndk);
-                colsum[k] += ok ? (double)v[k] : 0.0;
-                icnt[k] += ok ? 1u : 0u;
+                for (int u = 0; u < kFb; u++) {
+                    const T *pu = p + (yb0 + u < yb ? (long)u : yb - 1 - yb0) * ws;   // (clamped: re-reads the last row)
+                    raw[u][0] = hb_ldg_stream16(pu);
+                    raw[u][1] = hb_ldg_stream16(pu + 4);
+                }
+                p += (long)kFb * ws;
+#pragma unroll
+                for (int u = 0; u < kFb; u++) {
+                    if (yb0 + u >= yb) break;
+                    const float v[8] = {__uint_as_float(raw[u][0].x), __uint_as_float(raw[u][0].y),
+                                        __uint_as_float(raw[u][0].z), __uint_as_float(raw[u][0].w),
+                                        __uint_as_float(raw[u][1].x), __uint_as_float(raw[u][1].y),
+                                        __uint_as_float(raw[u][1].z), __uint_as_float(raw[u][1].w)};
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const bool ok = hb_valid(v[k], ndk);
+                        colsum[k] += ok ? (double)v[k] : 0.0;
+                        icnt[k] += ok ? 1u : 0u;
+                    }
+                }
+            }
+        } else {
+#pragma unroll 4
+            for (long y = ya; y < yb; y++) {
+                T v[8]; uint32_t inb;
+                ds_fetch<T, ALIGNED>(src + y * ws, c, ws, v, inb);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const bool ok = ((inb >> k) & 1u) && ds_valid<T>(v[k], ndk);
+                    colsum[k] += ok ? (double)v[k] : 0.0;
+                    icnt[k] += ok ? 1u : 0u;
+                }
             }
         }
 #pragma unroll
