@@ -439,11 +439,18 @@ def main():
     for k, d in per_kernel.items():
         if k in alg_bytes:
             d['gbs'] = round(alg_bytes[k] / (d['ms_avg'] * 1e-3) / 1e9, 1)
+    step_bytes_per_px = (2 * b_in + 4) if cfg['proc_crs'] == 'ref' else 12      # DESIGN.md section 4 / SURVEY.md 8d
     roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': round(achieved, 1), 'peak': peak_gbs,
                 'peak_source': peak_src, 'unit': 'GB/s', 'frac': round(achieved / peak_gbs, 4),
+                'frac_of_nominal_8000_gbs': round(achieved / 8000.0, 4),
                 'traffic': _ncu_traffic(args.workload, dominant),
                 'algorithmic_bytes_per_launch': int(alg_bytes[dominant]),
                 'share_of_step': round(sum(kernel_ms[dominant]) / serial_ms, 3),
+                'whole_step': {'algorithmic_bytes_per_pixel': step_bytes_per_px,
+                               'achieved_gbs': round(value * 1e6 * step_bytes_per_px / 1e9 / world, 1),
+                               'frac': round(value * 1e6 * step_bytes_per_px / 1e9 / world / peak_gbs, 4),
+                               'note': 'per GPU: value x algorithmic bytes per source band-pixel of the whole fit + '
+                                       'apply step, against the same peak'},
                 'timing': 'CUDA events around every launch, K steps with the bands serialised on one stream '
                           f'({round(serial_ms / args.steps, 4)} ms/step); `value` runs the bands on concurrent streams',
                 'kernels': per_kernel}
