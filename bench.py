@@ -52,6 +52,9 @@ WORKLOADS = {
                kernel_shape=(31, 31), r2_inpaint_thresh=None, proc_crs='src',
                desc='C3: synthetic 4-band float32 20000x20000, proc_crs=src (fit at source resolution), gain-offset '
                     '31x31, no in-painting'),
+    'tiny': dict(hp=40, wp=36, ratio=8, bands=2, dtype='uint16', mu=3000.0, src_nodata=0.0, model='gain-blk-offset',
+                 kernel_shape=(5, 5), r2_inpaint_thresh=0.25, proc_crs='ref',
+                 desc='tiny: synthetic 2-band uint16 320x288 (contract / smoke tests of this script, not a benchmark)'),
     'c4': dict(hp=400, wp=400, ratio=20, bands=4, dtype='uint16', mu=3000.0, src_nodata=0.0, model='gain-blk-offset',
                kernel_shape=(5, 5), r2_inpaint_thresh=0.25, proc_crs='ref',
                desc='C4: batch mosaic, synthetic 4-band uint16 8000x8000 sources vs a 10 m reference, one source per '

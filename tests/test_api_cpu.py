@@ -166,3 +166,26 @@ def test_product_does_not_import_oracle():
         if path.suffix in ('.py', '.cu', '.cuh', '.h'):
             text = path.read_text()
             assert 'import oracle' not in text and 'from oracle' not in text, path
+
+
+def test_bench_reference_arm_contract():
+    """ `bench.py --impl reference` (the CPU arm the driver runs beside ours) prints ONE JSON line with the contract's
+    keys; run here on the tiny workload. """
+    import json
+    import pathlib
+    import subprocess
+    import sys
+    repo = pathlib.Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(repo / 'bench.py'), '--impl', 'reference', '--workload', 'tiny', '--steps',
+                          '2', '--warmup', '1'], capture_output=True, text=True, timeout=600, cwd=str(repo))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better',
+                'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert key in line, key
+    assert line['impl'] == 'reference' and line['unit'] == 'Mpix/s' and line['value'] > 0
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
+    assert 'workload' in line['config'] and 'model' not in line['config']
