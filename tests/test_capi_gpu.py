@@ -439,3 +439,30 @@ def test_process_out_profile_dtype():
     a = f32.array.cpu().numpy()
     exp = np.where(np.isnan(a), 0, np.clip(np.round(np.nan_to_num(a)), 0, 65535)).astype('uint16')
     assert np.array_equal(u16.array.cpu().numpy().view('uint16'), exp)
+
+
+def test_bench_contract_on_gpu():
+    """ `python bench.py` prints ONE JSON line with the driver's contract (value, e2e, roofline, cpu_baseline, clocks,
+    gpu_launches ...); run on the tiny workload. """
+    import json
+    import pathlib
+    import subprocess
+    import sys
+    repo = pathlib.Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(repo / 'bench.py'), '--workload', 'tiny', '--steps', '3', '--warmup', '3'],
+                         capture_output=True, text=True, timeout=900, cwd=str(repo))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'clocks', 'e2e', 'gpu_launches', 'roofline', 'cpu_baseline'):
+        assert key in line, key
+    assert line['value'] > 0 and line['gpu_launches'] > 0 and line['n_gpus'] == 1 and line['steps'] == 3
+    assert line['e2e']['value'] > 0 and line['e2e']['h2d_bytes_per_step'] > 0 and line['e2e']['d2h_bytes_per_step'] > 0
+    roof = line['roofline']
+    for key in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'):
+        assert key in roof, key
+    assert roof['bound'] == 'hbm' and roof['achieved'] > 0
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['value'] > 0
+    assert 'workload' in line['config'] and 'model' not in line['config']
