@@ -141,6 +141,21 @@ def source_band_for_proc_rows(src_ra_shape: Tuple[int, int], src_transform: Affi
     return r0, max(r1, r0)
 
 
+def fit_row_window(bands: RowBands, rank: int, halo: int) -> Tuple[int, int, int, int]:
+    """
+    Proc-grid rows of the sharded proc_crs = ref path for ``rank``: ``(lo, hi, plo, phi)``.  ``[lo, hi)`` are the rows the
+    rank fits (its band extended by ``halo`` rows, clipped to the raster); ``[plo, phi)`` are the rows of that fit it keeps
+    and hands to the up-sampler (its band plus the 2 rows of cubic-spline support on either side, clipped).  Every kept
+    row is at least ``halo - 2`` rows away from a cut edge of the fitted window -- the distance over which window sums
+    (and the in-painting search) are affected by the cut -- unless that edge is the raster's own.
+    """
+    a, b = bands.band(rank)
+    hp = bands.starts[-1]
+    lo, hi = max(a - halo, 0), min(b + halo, hp)
+    plo, phi = max(a - 2, 0), min(b + 2, hp)
+    return lo, hi, plo, phi
+
+
 def fuse_refspace_sharded(model, src_local: RasterArray, ref_ra: RasterArray, bands: RowBands, group=None, out=None
                           ) -> Tuple[RasterArray, RasterArray]:
     """
@@ -161,7 +176,6 @@ def fuse_refspace_sharded(model, src_local: RasterArray, ref_ra: RasterArray, ba
     from homonim_b200.enums import Model
     rank = dist.get_rank(group)
     a, b = bands.band(rank)
-    hp = bands.starts[-1]
     nan = float('nan')
     src_t = km._to_device(src_local.array)
     # 1. down-sample my source rows onto my proc rows
@@ -177,9 +191,8 @@ def fuse_refspace_sharded(model, src_local: RasterArray, ref_ra: RasterArray, ba
     # 4. fit my proc rows + halo; keep the rows my source rows' spline taps touch
     inpaint = model.model == Model.gain_offset and model._r2_inpaint_thresh is not None
     halo = halo_rows(model.kernel_shape, proc_crs_ref=True, inpaint=inpaint)
-    lo, hi = max(a - halo, 0), min(b + halo, hp)
+    lo, hi, plo, phi = fit_row_window(bands, rank, halo)
     params_ext = model._fit_planes(src_ds[lo:hi], nan, ref_t[lo:hi], ref_ra.nodata, norm=norm)
-    plo, phi = max(a - 2, 0), min(b + 2, hp)
     params = params_ext[:, plo - lo:phi - lo].contiguous()
     param_ra = RasterArray(params, ref_ra.crs, ref_ra.transform * Affine.translation(0, plo), nodata=nan)
     # 5. apply to my source rows

@@ -86,3 +86,30 @@ def test_halo_exchange_world_size_3_deep_halo(tmp_path):
     world = 3
     mp.spawn(_worker, args=(world, _free_port(), 7, 4, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f'ok{r}').exists() for r in range(world))
+
+
+def test_fit_row_window_margins():
+    """ Row windows of the sharded proc_crs = ref path: the rows a rank keeps lie inside the rows it fits, far enough
+    from every cut edge that the cut cannot influence them, and together the kept bands cover every rank's taps. """
+    import random
+    from homonim_b200.dist import RowBands, fit_row_window, halo_rows
+    rnd = random.Random(3)
+    for _ in range(300):
+        hp = rnd.randint(1, 400)
+        world = rnd.randint(1, 9)
+        kh = rnd.choice([1, 3, 5, 15, 31])
+        inpaint = rnd.random() < 0.3
+        halo = halo_rows((kh, kh), proc_crs_ref=True, inpaint=inpaint)
+        bands = RowBands.split(hp, world)
+        for rank in range(world):
+            a, b = bands.band(rank)
+            lo, hi, plo, phi = fit_row_window(bands, rank, halo)
+            assert 0 <= lo <= plo <= phi <= hi <= hp
+            if b > a:
+                # the up-sampler's taps for source rows under proc rows [a, b) are proc rows [a - 2, b + 2)
+                assert plo == max(a - 2, 0) and phi == min(b + 2, hp)
+                # distance from the kept rows to a CUT edge (an edge that is not the raster's own)
+                if lo > 0:
+                    assert plo - lo >= halo - 2
+                if hi < hp:
+                    assert hi - phi >= halo - 2
