@@ -219,6 +219,27 @@ def apply_same_grid(src, params):
     return (params[0] * as_working(src)) + params[1]                         # :461
 
 
+def convert_dtype(corr, dtype, nodata=None):
+    """
+    RasterArray._convert_array_dtype, raster_array.py:353-387, for a float32 corrected plane with NaN nodata (what
+    to_rio_dataset converts before writing, :493-500): promote (:366), round half to even when going to an integer
+    type (:369-370), clip to its range (:373-377), cast (:380-381), nodata where the plane was NaN (:384-385).
+    """
+    corr = np.asarray(corr, dtype='float32')
+    mask = ~np.isnan(corr)
+    to_int = np.issubdtype(np.dtype(dtype), np.integer)
+    array = corr.astype(np.promote_types('float32', dtype), copy=True)       # :366
+    if to_int:
+        np.round(array, out=array)                                           # :370
+        info = np.iinfo(dtype)
+        np.clip(array, info.min, info.max, out=array)                        # :377
+    with np.errstate(invalid='ignore', over='ignore'):
+        array = array.astype(dtype, copy=False, casting='unsafe')            # :381
+    if nodata is not None:
+        array[~mask] = nodata                                                # :385
+    return array
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # grid-changing wrappers (kernel_model.py:375-409, 466-535)
 # ---------------------------------------------------------------------------------------------------------------------

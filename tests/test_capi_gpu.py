@@ -466,3 +466,26 @@ def test_bench_contract_on_gpu():
     assert roof['bound'] == 'hbm' and roof['achieved'] > 0
     assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['value'] > 0
     assert 'workload' in line['config'] and 'model' not in line['config']
+
+
+def test_convert_dtype_vs_reference_golden():
+    """ hb_convert_dtype against RasterArray._convert_array_dtype of the unmodified reference
+    (tests/golden/convert_dtype.npz). """
+    import pathlib
+    lib = _native.lib()
+    codes = {'uint8': _native.HB_U8, 'uint16': _native.HB_U16, 'int16': _native.HB_I16, 'float32': _native.HB_F32}
+    with np.load(pathlib.Path(__file__).resolve().parent / 'golden' / 'convert_dtype.npz') as data:
+        corr = torch.from_numpy(data['corr']).cuda().contiguous()
+        for key in data.files:
+            if key == 'corr':
+                continue
+            dtype, nodata = key.rsplit('_', 1)
+            out = torch.empty(corr.shape, dtype=getattr(torch, dtype), device='cuda')
+            _native.check(lib.hb_convert_dtype(corr.data_ptr(), corr.numel(), codes[dtype], 1, float(nodata),
+                                               out.data_ptr(), _stream()))
+            got = out.cpu().numpy()
+            exp = data[key]
+            if dtype == 'float32':
+                assert np.array_equal(got, exp), key
+            else:
+                assert np.array_equal(got.astype('int64'), exp.astype('int64')), key

@@ -51,3 +51,19 @@ def test_golden_fixture_inventory():
     for token in ('gain_k', 'gain-blk-offset', 'gain-offset', '_r2', '_inp', 'uint8', 'uint16', 'float32', 'partial',
                   'refspace', 'srcspace', 'conftest'):
         assert any(token in n for n in names), token
+
+
+def test_oracle_convert_dtype_matches_reference():
+    """ oracle.kernel_model_np.convert_dtype against RasterArray._convert_array_dtype of the unmodified reference
+    (tests/golden/convert_dtype.npz, oracle/make_golden_convert.py). """
+    import pathlib
+    from oracle import kernel_model_np as kmnp
+    with np.load(pathlib.Path(__file__).resolve().parent / 'golden' / 'convert_dtype.npz') as data:
+        corr = data['corr']
+        for key in data.files:
+            if key == 'corr':
+                continue
+            dtype, nodata = key.rsplit('_', 1)
+            got = kmnp.convert_dtype(corr, dtype, float(nodata))
+            assert got.dtype == data[key].dtype
+            assert np.array_equal(got, data[key]), key
