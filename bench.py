@@ -66,7 +66,41 @@ WORKLOADS = {
 }
 
 
-def _clock_sampler(stop, samples, gpu_index):
+def _clock_sampler(stop, samples, gpu_index, uuid=None):
+    """
+    SM clock / throttle-reason samples of one GPU while `stop` is unset.  NVML in-process (a query costs ~50 us, so the
+    few-millisecond timed region gets several samples); falls back to polling nvidia-smi (~100 ms per query).
+    Every sample: [sm_mhz, sm_max_mhz, power_w, hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap,
+    perf_counter timestamp].
+    """
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = None
+        if uuid:
+            try:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(uuid if str(uuid).startswith('GPU-') else f'GPU-{uuid}')
+            except Exception:
+                handle = None
+        if handle is None:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        smax = pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)
+        get_reasons = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [0x8, 0x40, 0x20, 0x4]        # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        while not stop.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+            try:
+                power = pynvml.nvmlDeviceGetPowerUsage(handle) / 1000.0
+            except Exception:
+                power = 0.0
+            reasons = int(get_reasons(handle))
+            samples.append([str(sm), str(smax), f'{power:.1f}'] +
+                           ['Active' if reasons & b else 'Not Active' for b in bits] + [time.perf_counter()])
+            stop.wait(0.002)
+        return
+    except Exception:
+        pass
     query = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
@@ -76,19 +110,25 @@ def _clock_sampler(stop, samples, gpu_index):
                                   '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
             parts = [p.strip() for p in out.strip().split(',')]
             if len(parts) >= 7:
-                samples.append(parts)
+                samples.append(parts[:7] + [time.perf_counter()])
         except Exception:
             pass
         stop.wait(0.2)
 
 
-def _clocks_summary(samples):
+def _clocks_summary(samples, window=None):
+    """ Median SM clock and the throttle reasons seen, over the samples inside `window` = (t0, t1) (the timed region;
+    all samples when none fell inside it). """
+    if window is not None:
+        inside = [s for s in samples if window[0] <= s[-1] <= window[1]]
+        if inside:
+            samples = inside
     if not samples:
         return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unsampled'])
     sm = [float(s[0]) for s in samples if s[0].replace('.', '', 1).isdigit()]
     smax = [float(s[1]) for s in samples if s[1].replace('.', '', 1).isdigit()]
     names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith('active') for s in samples)]
+    reasons = [n for i, n in enumerate(names) if any(str(s[3 + i]).lower().startswith('active') for s in samples)]
     return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(smax) if smax else None,
                 reasons=reasons, samples=len(samples))
 
@@ -151,6 +191,14 @@ def run_reference(args, cfg, rank):
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def _gpu_uuid(torch, index):
+    """ UUID of CUDA device `index` (NVML enumerates physical devices; CUDA_VISIBLE_DEVICES may renumber them). """
+    try:
+        return str(torch.cuda.get_device_properties(index).uuid)
+    except Exception:
+        return None
 
 
 def _peak():
@@ -244,12 +292,14 @@ def run_sharded(args, cfg, rank, world, local_rank):
         step()
     barrier()
     stop, samples = threading.Event(), []
-    sampler = threading.Thread(target=_clock_sampler, args=(stop, samples, local_rank), daemon=True)
+    sampler = threading.Thread(target=_clock_sampler, args=(stop, samples, local_rank, _gpu_uuid(torch, local_rank)),
+                               daemon=True)
     if rank == 0:
         sampler.start()
     lib.hb_reset_launch_count()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_region0 = time.perf_counter()
     start.record()
     for _ in range(args.steps):
         step()
@@ -260,6 +310,7 @@ def run_sharded(args, cfg, rank, world, local_rank):
     with KernelTimer() as timer:
         step()
         kernel_ms = timer.results()
+    t_region1 = time.perf_counter()
     stop.set()
     if rank == 0:
         sampler.join(timeout=2)
@@ -288,7 +339,7 @@ def run_sharded(args, cfg, rank, world, local_rank):
                        'sharding': f'row bands of {cfg["hp"]} proc rows over {world} rank(s); per band one all-gather '
                                    f'of the {cfg["hp"]}x{cfg["wp"]} float32 proc-grid plane',
                        'l2': 'inputs larger than L2 (no flush needed)'},
-            'clocks': _clocks_summary(samples), 'e2e': None, 'gpu_launches': int(launches),
+            'clocks': _clocks_summary(samples, (t_region0, t_region1)), 'e2e': None, 'gpu_launches': int(launches),
             'roofline': {'bound': 'hbm', 'kernel': dominant, 'achieved': round(achieved, 1), 'peak': peak_gbs,
                          'peak_source': peak_src, 'unit': 'GB/s', 'frac': round(achieved / peak_gbs, 4),
                          'traffic': None, 'algorithmic_bytes_per_launch': int(alg[dominant]), 'kernels': per_kernel},
@@ -364,12 +415,14 @@ def main():
     # ---- timed region: device-resident inputs -----------------------------------------------------------------------
     # clocks are sampled on rank 0 only (nvidia-smi is not free: 8 ranks polling it would compete with the timed loop)
     stop, samples = threading.Event(), []
-    sampler = threading.Thread(target=_clock_sampler, args=(stop, samples, local_rank), daemon=True)
+    sampler = threading.Thread(target=_clock_sampler, args=(stop, samples, local_rank, _gpu_uuid(torch, local_rank)),
+                               daemon=True)
     if rank == 0:
         sampler.start()
     lib.hb_reset_launch_count()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_region0 = time.perf_counter()
     start.record()
     for _ in range(args.steps):
         step()
@@ -387,6 +440,7 @@ def main():
         s1.record()
         kernel_ms = timer.results()
     serial_ms = s0.elapsed_time(s1)
+    t_region1 = time.perf_counter()          # (clock window: the timed steps and the same steps serialised for the roofline)
     stop.set()
     if rank == 0:
         sampler.join(timeout=2)
@@ -500,7 +554,8 @@ def main():
                        'proc_crs': cfg['proc_crs'], 'bands': cfg['bands'], 'src_dtype': cfg['dtype'],
                        'pixels_per_step_per_gpu': int(npix), 'sharding': 'one source image per GPU, no collective',
                        'l2': 'inputs larger than L2 (no flush needed)'},
-            'clocks': _clocks_summary(samples), 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
+            'clocks': _clocks_summary(samples, (t_region0, t_region1)), 'e2e': e2e, 'gpu_launches': int(launches),
+            'roofline': roofline,
             'cpu_baseline': cpu_baseline,
         }
         print(json.dumps(line), flush=True)
