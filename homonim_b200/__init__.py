@@ -14,9 +14,10 @@ from homonim_b200.geometry import Affine, CRS
 from homonim_b200.raster_array import RasterArray
 from homonim_b200.kernel_model import KernelModel, RefSpaceModel, SrcSpaceModel
 from homonim_b200.fuse import RasterFuse
+from homonim_b200.compare import RasterCompare
 
 __version__ = '0.1.0'
 logging.getLogger(__name__).addHandler(logging.NullHandler())
 
 __all__ = ['Model', 'ProcCrs', 'Resampling', 'Affine', 'CRS', 'RasterArray', 'KernelModel', 'RefSpaceModel',
-           'SrcSpaceModel', 'RasterFuse', 'NativeLibraryError']
+           'SrcSpaceModel', 'RasterFuse', 'RasterCompare', 'NativeLibraryError']

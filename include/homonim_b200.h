@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 4
+#define HB_ABI_VERSION 5
 
 /* storage dtype of a source raster plane */
 enum { HB_U8 = 0, HB_U16 = 1, HB_F32 = 2, HB_I16 = 3 };   /* HB_I16: output of hb_convert_dtype only */
@@ -153,6 +153,20 @@ int hb_convert_dtype(const float *src_dev, long n, int out_dtype, int has_nodata
 /* validity mask of a raster plane as uint8 (RasterArray.mask / mask_ra, raster_array.py:298-327) */
 int hb_valid_mask(const void *src_dev, int src_dtype, long n, int has_nodata, double nodata, uint8_t *mask_dev,
                   void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Accuracy sums of RasterCompare: `get_block_sums` of RasterCompare.process (homonim/compare.py:232-256) for two
+ * float32 planes of n pixels on one grid (the source and the reference after one of them was re-projected onto the
+ * other's grid).  mask = valid(src) & valid(ref); pixels outside it count as zero in both planes.
+ *   sums_dev   7 doubles on the device, in the reference's order:
+ *              sum(src), sum(ref), sum(src^2), sum(ref^2), sum(src*ref), sum((ref-src)^2), sum(mask)
+ * The per-pixel terms are rounded to float32 as numpy rounds them and accumulated in double in a fixed order.
+ * workspace_dev: hb_compare_sums_workspace_bytes() bytes of 16-byte aligned device scratch.  8 bytes read per pixel.
+ * --------------------------------------------------------------------------------------------------------------- */
+size_t hb_compare_sums_workspace_bytes(void);
+int hb_compare_sums(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
+                    int ref_has_nodata, double ref_nodata, long n, double *sums_dev, void *workspace_dev,
+                    size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * One (band, block) of RasterFuse._process_block (homonim/fuse.py:304-307: model.fit + model.apply) for proc_crs = ref

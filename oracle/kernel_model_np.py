@@ -241,6 +241,54 @@ def convert_dtype(corr, dtype, nodata=None):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# RasterCompare accuracy sums and statistics (compare.py:142-187, 232-256) -- SURVEY.md 8f-3
+# ---------------------------------------------------------------------------------------------------------------------
+COMPARE_SUM_KEYS = ('src_sum', 'ref_sum', 'src2_sum', 'ref2_sum', 'src_ref_sum', 'res2_sum', 'mask_sum')
+
+
+def compare_sums(src, src_nodata, ref, ref_nodata, dtype='float32') -> dict:
+    """
+    get_block_sums, compare.py:241-254, for two planes on one grid.  ``dtype='float32'`` is what the reference does
+    (float32 terms, numpy's pairwise float32 summation); ``dtype='float64'`` sums the SAME float32 terms in double --
+    the sums the CUDA path produces.
+    """
+    src, ref = as_working(np.array(src, copy=True)), as_working(np.array(ref, copy=True))
+    mask = valid_mask(ref, ref_nodata) & valid_mask(src, src_nodata)         # :245
+    src[~mask] = 0                                                           # :246
+    ref[~mask] = 0                                                           # :247
+    terms = dict(src_sum=src, ref_sum=ref, src2_sum=src ** 2, ref2_sum=ref ** 2, src_ref_sum=src * ref,
+                 res2_sum=(ref - src) ** 2)                                  # :249-253 (float32 terms)
+    sums = {k: v.sum(dtype=dtype) for k, v in terms.items()}
+    sums['mask_sum'] = mask.sum()
+    return sums
+
+
+def compare_band_stats(src_sum=0, ref_sum=0, src2_sum=0, ref2_sum=0, src_ref_sum=0, res2_sum=0, mask_sum=0) -> dict:
+    """ get_band_stats, compare.py:145-163: Pearson's r squared, RMSE and RMSE relative to the reference mean. """
+    src_mean = src_sum / mask_sum                                            # :152
+    ref_mean = ref_sum / mask_sum                                            # :153
+    pcc_num = src_ref_sum - (mask_sum * src_mean * ref_mean)                 # :154
+    pcc_den = (np.sqrt(src2_sum - (mask_sum * (src_mean ** 2))) *
+               np.sqrt(ref2_sum - (mask_sum * (ref_mean ** 2))))             # :155-157
+    pcc = pcc_num / pcc_den                                                  # :158
+    rmse = np.sqrt(res2_sum / mask_sum)                                      # :161
+    rrmse = rmse / ref_mean                                                  # :162
+    return dict(r2=pcc ** 2, rmse=rmse, rrmse=rrmse, n=int(mask_sum))        # :163
+
+
+def compare_image_stats(image_sums, band_names) -> dict:
+    """ _get_image_stats, compare.py:165-187: per-band statistics keyed by band name, plus their 'Mean' over bands. """
+    image_stats, sum_over_bands = {}, {}
+    for name, band_sums in zip(band_names, image_sums):
+        band_stats = compare_band_stats(**band_sums)
+        image_stats[name] = band_stats                                       # :176
+        sum_over_bands = {k: sum_over_bands.get(k, 0) + v for k, v in band_stats.items()}       # :177
+    image_stats['Mean'] = {k: int(v / len(image_sums)) if isinstance(v, int) else (v / len(image_sums))
+                           for k, v in sum_over_bands.items()}               # :180-185
+    return image_stats
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # grid-changing wrappers (kernel_model.py:375-409, 466-535)
 # ---------------------------------------------------------------------------------------------------------------------
 def _set_mask(array, mask, nodata=NODATA):
@@ -327,6 +375,26 @@ def fuse_band(src, src_transform, src_nodata, ref, ref_transform, ref_nodata, mo
 # ---------------------------------------------------------------------------------------------------------------------
 # block windows of RasterFuse / RasterPairReader for a single block per band
 # ---------------------------------------------------------------------------------------------------------------------
+def compare_band(src, src_transform, src_nodata, ref, ref_transform, ref_nodata, proc_crs='ref',
+                 downsampling='average', upsampling='cubic_spline', dtype='float32') -> dict:
+    """ get_block_sums, compare.py:232-254, for one band read as a single block (`block_windows`: the reader's
+    boundless source window on whole reference pixels): re-project onto the processing grid (:236-241), then the
+    masked sums. """
+    src_w, src_transform, ref_w, ref_transform, _ = block_windows(src, src_transform, src_nodata, as_working(ref),
+                                                                  ref_transform)      # :234 (self.read)
+    if proc_crs == 'ref':
+        resampling = pick_resampling(res_of(src_transform), res_of(ref_transform), downsampling, upsampling)   # :237
+        src_w = gdal_restate.reproject_array(src_w, src_transform, src_nodata, ref_w.shape, ref_transform, NODATA,
+                                             resampling)                     # :238
+        src_nodata = NODATA
+    else:
+        resampling = pick_resampling(res_of(ref_transform), res_of(src_transform), downsampling, upsampling)   # :240
+        ref_w = gdal_restate.reproject_array(ref_w, ref_transform, ref_nodata, src_w.shape, src_transform, NODATA,
+                                             resampling)                     # :241
+        ref_nodata = NODATA
+    return compare_sums(src_w, src_nodata, ref_w, ref_nodata, dtype=dtype)
+
+
 def _affine_mul(t, u):
     """ 6-coefficient affine product t * u. """
     ta, tb, tc, td, te, tf = [float(v) for v in t[:6]]

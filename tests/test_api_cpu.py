@@ -189,3 +189,39 @@ def test_bench_reference_arm_contract():
     assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
     assert 'workload' in line['config'] and 'model' not in line['config']
+
+
+def test_raster_compare_host_logic():
+    """ RasterCompare's host side (no GPU): configuration defaults, the closed-pair error, the statistics formed from
+    the sums (same expressions as compare.py:145-187, checked against the oracle restatement) and the table. """
+    import numpy as np
+    from homonim_b200 import Affine, CRS, ProcCrs, RasterArray, RasterCompare, Resampling
+    from oracle import kernel_model_np as knp
+    config = RasterCompare.create_config()
+    assert config['max_block_mem'] == 512 and config['downsampling'] == Resampling.average
+    assert config['upsampling'] == Resampling.cubic_spline and config['threads'] >= 1
+    crs = CRS.from_epsg(3857)
+    src = RasterArray(np.ones((2, 40, 40), 'float32'), crs, Affine(5, 0, 0, 0, -5, 0))
+    ref = RasterArray(np.ones((3, 20, 20), 'float32'), crs, Affine(10, 0, 0, 0, -10, 0))
+    cmp = RasterCompare(src, ref)
+    assert cmp.proc_crs == ProcCrs.ref and tuple(cmp.src_bands) == (1, 2) and tuple(cmp.ref_bands) == (1, 2)
+    assert cmp._get_resampling(src.res, ref.res) == Resampling.average
+    assert cmp._get_resampling(ref.res, src.res, upsampling='nearest') == Resampling.nearest
+    with pytest.raises(OSError):
+        cmp.process()
+    rng = np.random.default_rng(3)
+    image_sums = []
+    for _ in range(2):
+        a, b = rng.normal(5, 1, 500), rng.normal(6, 1, 500)
+        image_sums.append(dict(src_sum=a.sum(), ref_sum=b.sum(), src2_sum=(a * a).sum(), ref2_sum=(b * b).sum(),
+                               src_ref_sum=(a * b).sum(), res2_sum=((b - a) ** 2).sum(), mask_sum=500))
+    stats = cmp._get_image_stats(image_sums)
+    exp = knp.compare_image_stats(image_sums, ['Ref. band 1', 'Ref. band 2'])
+    assert list(stats.keys()) == list(exp.keys()) == ['Ref. band 1', 'Ref. band 2', 'Mean']
+    for band in exp:
+        assert stats[band]['n'] == exp[band]['n'] == 500 and isinstance(stats[band]['n'], int)
+        for key in ('r2', 'rmse', 'rrmse'):
+            assert stats[band][key] == pytest.approx(exp[band][key], rel=1e-14)
+    table = RasterCompare.stats_table(stats)
+    assert 'RMSE' in table and 'Mean' in table and 'Ref. band 2' in table
+    assert 'rRMSE' in RasterCompare.schema_table()

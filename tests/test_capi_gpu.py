@@ -489,3 +489,44 @@ def test_convert_dtype_vs_reference_golden():
                 assert np.array_equal(got, exp), key
             else:
                 assert np.array_equal(got.astype('int64'), exp.astype('int64')), key
+
+
+@pytest.mark.parametrize('n, offset, src_nodata, ref_nodata', [
+    (1, 0, NAN, NAN),
+    (1000003, 0, NAN, NAN),                 # vector path with a scalar tail
+    (262144, 1, NAN, -9999.0),              # planes not 16-byte aligned -> scalar path; a value nodata
+    (5000000, 0, None, NAN),                # every source pixel valid; more pixels than one trip of the grid
+    (4097, 0, NAN, NAN),
+])
+def test_compare_sums(n, offset, src_nodata, ref_nodata):
+    """ hb_compare_sums against get_block_sums (compare.py:243-253) restated with numpy: the same float32 terms summed
+    in double (tolerance 1e-12: the two double summation orders); deterministic from call to call. """
+    _, knp = _oracle()
+    from homonim_b200.compare import SUM_KEYS, compare_sums_device
+    rng = np.random.default_rng(n)
+    ref = rng.normal(900.0, 300.0, n + offset).astype('float32')
+    src = (0.7 * ref + 40 + rng.normal(0.0, 50.0, n + offset)).astype('float32')
+    if src_nodata is not None:
+        src[rng.integers(0, n + offset, n // 10)] = src_nodata
+    ref[rng.integers(0, n + offset, n // 17)] = ref_nodata
+    if n == 1:
+        src[:], ref[:] = 3.0, 5.0
+    exp = knp.compare_sums(src[offset:], src_nodata, ref[offset:], ref_nodata, dtype='float64')
+    src_t, ref_t = torch.from_numpy(src).cuda()[offset:], torch.from_numpy(ref).cuda()[offset:]
+    got = compare_sums_device(src_t, src_nodata, ref_t, ref_nodata).cpu().numpy()
+    again = compare_sums_device(src_t, src_nodata, ref_t, ref_nodata).cpu().numpy()
+    assert np.array_equal(got, again)
+    for key, value in zip(SUM_KEYS, got):
+        assert abs(value - float(exp[key])) <= 1e-12 * max(abs(float(exp[key])), 1.0), key
+    assert got[-1] == int(exp['mask_sum'])
+
+
+def test_compare_sums_all_invalid():
+    """ An empty mask gives seven zeros (the statistics are then NaN, as in the reference). """
+    from homonim_b200.compare import RasterCompare, compare_sums_device
+    src = torch.full((37, 41), NAN, device='cuda')
+    ref = torch.ones((37, 41), device='cuda')
+    got = compare_sums_device(src, NAN, ref, NAN).cpu().numpy()
+    assert np.array_equal(got, np.zeros(7))
+    stats = RasterCompare._band_stats(*got)
+    assert stats['n'] == 0 and np.isnan(stats['r2']) and np.isnan(stats['rmse'])

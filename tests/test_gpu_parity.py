@@ -382,3 +382,47 @@ def test_srcspace_fused_equals_fit_then_apply(model, kernel_shape, thresh):
         two_step, params = fuse.process(param_filename='p', **kw)
     assert none is None and params is not None
     assert torch.equal(got.array.nan_to_num(-1.0), two_step.array.nan_to_num(-1.0))
+
+
+def test_raster_compare_vs_reference_golden():
+    """
+    RasterCompare.process against the unmodified reference's RasterCompare.process (tests/golden/compare_stats.*,
+    oracle/make_golden_compare.py) and against the oracle's sums.  Tolerances: statistics 1e-4 relative (the reference
+    sums float32 terms in float32, the CUDA path in double); sums 1e-5 relative to the oracle's double sums of the same
+    float32 terms (the re-projected planes agree to float32 rounding); identical pixel counts.
+    """
+    import json
+    import pathlib
+    from homonim_b200 import Affine, RasterCompare
+    from oracle import kernel_model_np as knp
+    NAN = float('nan')
+    golden = pathlib.Path(__file__).resolve().parent / 'golden'
+    meta = json.loads((golden / 'compare_stats.json').read_text())
+    names = ['B4', 'B3', 'B2']
+    crs = CRS0
+    with np.load(golden / 'compare_stats.npz') as data:
+        for ci in range(len(meta)):
+            case = meta[f'case{ci}']
+            src, ref = data[f'src{ci}'], data[f'ref{ci}']
+            src_tf, ref_tf = Affine(*case['src_transform'][:6]), Affine(*case['ref_transform'][:6])
+            for on_device in (True, False):
+                to = (lambda a: torch.from_numpy(a).cuda()) if on_device else (lambda a: a)
+                cmp = RasterCompare(RasterArray(to(src), crs, src_tf, nodata=NAN),
+                                    RasterArray(to(ref), crs, ref_tf, nodata=NAN), proc_crs=case['proc_crs'],
+                                    band_names=names)
+                with pytest.raises(OSError):
+                    cmp.process()
+                with cmp:
+                    stats = cmp.process()
+                    sums = [cmp._band_sums_device(b).cpu().numpy() for b in range(3)]
+                assert list(stats.keys()) == names + ['Mean']
+                for band, band_stats in case['stats'].items():
+                    assert stats[band]['n'] == int(band_stats['n']), (ci, band)
+                    for key in ('r2', 'rmse', 'rrmse'):
+                        assert abs(stats[band][key] - band_stats[key]) <= 1e-4 * abs(band_stats[key]), (ci, band, key)
+                for b in range(3):
+                    exp = knp.compare_band(src[b], tuple(src_tf), NAN, ref[b], tuple(ref_tf), NAN, case['proc_crs'],
+                                           dtype='float64')
+                    for key, value in zip(knp.COMPARE_SUM_KEYS, sums[b]):
+                        assert abs(value - float(exp[key])) <= 1e-5 * abs(float(exp[key])), (ci, b, key)
+            assert isinstance(RasterCompare.stats_table(stats), str)

@@ -67,3 +67,31 @@ def test_oracle_convert_dtype_matches_reference():
             got = kmnp.convert_dtype(corr, dtype, float(nodata))
             assert got.dtype == data[key].dtype
             assert np.array_equal(got, data[key]), key
+
+
+def test_oracle_compare_matches_reference():
+    """ The oracle's RasterCompare restatement (compare.py:142-187, 232-256) against the unmodified reference's
+    RasterCompare.process (tests/golden/compare_stats.*): bit-exact with float32 summation (what the reference does);
+    within 1e-5 when the same float32 terms are summed in double (what the CUDA path does). """
+    import json
+    import pathlib
+    GOLDEN_DIR = pathlib.Path(__file__).resolve().parent / 'golden'
+    meta = json.loads((GOLDEN_DIR / 'compare_stats.json').read_text())
+    names = ['B4', 'B3', 'B2']
+    with np.load(GOLDEN_DIR / 'compare_stats.npz') as data:
+        for ci in range(len(meta)):
+            case = meta[f'case{ci}']
+            src, ref = data[f'src{ci}'], data[f'ref{ci}']
+            args = (tuple(case['src_transform']), float('nan'))
+            for dtype, tol in (('float32', 0.0), ('float64', 1e-5)):
+                sums = [kmnp.compare_band(src[b], args[0], args[1], ref[b], tuple(case['ref_transform']), float('nan'),
+                                         case['proc_crs'], dtype=dtype) for b in range(3)]
+                stats = kmnp.compare_image_stats(sums, names)
+                assert list(stats.keys()) == names + ['Mean']
+                for band, band_stats in case['stats'].items():
+                    for key, value in band_stats.items():
+                        assert abs(stats[band][key] - value) <= tol * abs(value), (ci, dtype, band, key)
+                if dtype == 'float32':
+                    for b in range(3):
+                        for key, value in case['image_sums'][b].items():
+                            assert float(sums[b][key]) == value, (ci, b, key)
