@@ -13,9 +13,12 @@
  *
  * Dependency: rasterio>=1.1 (pyproject.toml:7, unpinned) which bundles GDAL (3.x in current wheels).  GDAL is not
  * installed in this image, so these functions restate the published algorithm (alg/gdalwarpkernel.cpp,
- * alg/rasterfill.cpp) for axis-aligned, same-CRS, north-up grids.  PARITY UNPINNED: nothing executable here can
- * check them against GDAL itself; they are anchored on the reference's own loose known-answer tests
- * (tests/test_kernel_model.py:41-117, 166-273).
+ * alg/rasterfill.cpp) for axis-aligned, same-CRS, north-up grids.  Nothing executable here can check them against
+ * GDAL bit for bit.  PINNING: GRA_Average and GRA_CubicSpline are pinned at the known-answer level to real GDAL
+ * output -- the fuse + compare table the reference publishes for its own test images (docs/cli.rst:58-72, 32
+ * numbers) is reproduced to every printed digit through these functions (oracle/make_golden_docs.py,
+ * tests/test_oracle_golden.py).  GDALFillNodata and nearest are anchored only on the reference's loose known-answer
+ * tests (tests/test_kernel_model.py:41-117, 166-273): for those, PARITY UNPINNED.
  *
  * Grid mapping convention used by every resampler: destination pixel-EDGE coordinate u (column) maps to source
  * pixel-edge coordinate  sx*u + ox  (rows: sy*v + oy), sx, sy > 0.  Destination pixel j covers [j, j+1), its centre is

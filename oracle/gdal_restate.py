@@ -4,7 +4,8 @@ oracle/gdal_restate.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 ctypes front-end for ``oracle/gdal_restate.c``: the CPU restatement of the GDAL calls the reference's hot path makes
 through rasterio (``rasterio.warp.reproject`` -- /root/reference/homonim/raster_array.py:573-577 -- and
 ``rasterio.fill.fillnodata`` -- /root/reference/homonim/kernel_model.py:366).  GDAL / rasterio are not installed in
-this image; see the C file's header for what is restated and why parity of these pieces is UNPINNED.
+this image; see the C file's header for what is restated and how far each piece is pinned (average and cubic spline:
+the reference's published known answers; fillnodata and nearest: PARITY UNPINNED).
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this module.
 """

@@ -426,3 +426,42 @@ def test_raster_compare_vs_reference_golden():
                     for key, value in zip(knp.COMPARE_SUM_KEYS, sums[b]):
                         assert abs(value - float(exp[key])) <= 1e-5 * abs(float(exp[key])), (ci, b, key)
             assert isinstance(RasterCompare.stats_table(stats), str)
+
+
+def test_reference_published_table_gpu():
+    """
+    The CUDA path against known answers PUBLISHED by the reference (docs/cli.rst:58-72, real rasterio + GDAL pipeline):
+    RasterFuse.process(gain-blk-offset, 5x5) of ngi_rgb_byte_1.tif with the Sentinel-2 reference, then RasterCompare of
+    the source and of the corrected image with the Landsat-8 reference (tests/golden/docs_cli_ngi1.*,
+    oracle/make_golden_docs.py).  Pixel counts must be identical; r2 / RMSE / rRMSE must agree with the three printed
+    decimals to within half a unit of the last digit plus the 1e-4 relative float32 tolerance of the path.
+    """
+    import json
+    import pathlib
+    from homonim_b200 import Affine, RasterCompare
+    golden = pathlib.Path(__file__).resolve().parent / 'golden'
+    meta = json.loads((golden / 'docs_cli_ngi1.json').read_text())
+    with np.load(golden / 'docs_cli_ngi1.npz') as data:
+        src, s2, l8 = data['src'], data['s2'], data['l8']
+    src_tf, s2_tf, l8_tf = (Affine(*meta[k][:6]) for k in ('src_transform', 's2_transform', 'l8_transform'))
+    for on_device in (False, True):
+        to = (lambda a: torch.from_numpy(a).cuda()) if on_device else (lambda a: a)
+        src_ra = RasterArray(to(src), CRS0, src_tf, nodata=0)
+        s2_ra = RasterArray(to(s2), CRS0, s2_tf, nodata=float('nan'))     # no nodata tag: the reference's reader uses NaN
+        l8_ra = RasterArray(to(l8), CRS0, l8_tf, nodata=0)
+        with RasterFuse(src_ra, s2_ra) as fuse:
+            corr_ra, _ = fuse.process(model=Model.gain_blk_offset, kernel_shape=(5, 5))
+        rows = {}
+        for key, ra in (('source', src_ra), ('corrected', corr_ra)):
+            with RasterCompare(ra, l8_ra, band_names=meta['band_names']) as cmp:
+                rows[key] = cmp.process()['Mean']
+        for key in ('source', 'corrected'):
+            r2, rmse, rrmse, n = meta['published'][key]
+            got = rows[key]
+            assert got['n'] == n, (on_device, key, got)
+            for name, exp in (('r2', r2), ('rmse', rmse), ('rrmse', rrmse)):
+                assert abs(got[name] - exp) <= 0.5e-3 + 1e-4 * abs(exp), (on_device, key, name, got[name], exp)
+            # and against the oracle's unrounded values of the same table: 1e-4 relative
+            o_r2, o_rmse, o_rrmse, _ = meta['oracle'][key]
+            for name, exp in (('r2', o_r2), ('rmse', o_rmse), ('rrmse', o_rrmse)):
+                assert abs(got[name] - exp) <= 1e-4 * abs(exp), (on_device, key, name, got[name], exp)

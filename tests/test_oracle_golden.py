@@ -2,6 +2,8 @@
 CPU tier: the oracle port (oracle/kernel_model_np.py) is pinned BIT-FOR-BIT against the golden vectors that
 oracle/make_golden.py generated from the unmodified reference (/root/reference/homonim/kernel_model.py).
 """
+import pathlib
+
 import numpy as np
 import pytest
 
@@ -95,3 +97,50 @@ def test_oracle_compare_matches_reference():
                     for b in range(3):
                         for key, value in case['image_sums'][b].items():
                             assert float(sums[b][key]) == value, (ci, b, key)
+
+
+def _docs_rows(kmnp_mod, src, src_tf, s2, s2_tf, l8, l8_tf, names):
+    """ (source, corrected) rows of the docs/cli.rst table for one image, computed with the oracle. """
+    nan = float('nan')
+    src_sums, corr_sums = [], []
+    for b in range(3):
+        src_sums.append(kmnp_mod.compare_band(src[b], src_tf, 0.0, l8[b], l8_tf, 0.0, 'ref'))
+        _, _, corr = kmnp_mod.fuse_band_blocks(src[b], src_tf, 0.0, s2[b], s2_tf, nan, 'gain-blk-offset', (5, 5))
+        corr_sums.append(kmnp_mod.compare_band(corr, src_tf, nan, l8[b], l8_tf, 0.0, 'ref'))
+    return {key: kmnp_mod.compare_image_stats(sums, names)['Mean']
+            for key, sums in (('source', src_sums), ('corrected', corr_sums))}
+
+
+def test_oracle_reproduces_reference_published_table():
+    """
+    Known answers published by the reference (docs/cli.rst:58-72): `homonim fuse -m gain-blk-offset -k 5 5` of
+    ngi_rgb_byte_1.tif with the Sentinel-2 reference, then `homonim compare` of the source and the corrected image with
+    the Landsat-8 reference -- numbers from the real rasterio + GDAL pipeline.  The oracle chain (GRA_Average
+    restatement -> fit -> GRA_CubicSpline restatement -> apply -> compare sums) must reproduce every printed digit and
+    the pixel count exactly.  This is what pins oracle/gdal_restate.c to real GDAL output.
+    """
+    import json
+    import pathlib
+    golden = pathlib.Path(__file__).resolve().parent / 'golden'
+    meta = json.loads((golden / 'docs_cli_ngi1.json').read_text())
+    with np.load(golden / 'docs_cli_ngi1.npz') as data:
+        rows = _docs_rows(kmnp, data['src'], tuple(meta['src_transform']), data['s2'], tuple(meta['s2_transform']),
+                          data['l8'], tuple(meta['l8_transform']), meta['band_names'])
+    for key in ('source', 'corrected'):
+        r2, rmse, rrmse, n = meta['published'][key]
+        got = rows[key]
+        assert int(got['n']) == n, key
+        assert (round(float(got['r2']), 3), round(float(got['rmse']), 3), round(float(got['rrmse']), 3)) == \
+            (r2, rmse, rrmse), (key, got)
+
+
+@pytest.mark.skipif(not pathlib.Path('/root/reference/tests/data/source/ngi_rgb_byte_4.tif').exists(),
+                    reason='container-only: reads the reference test images from /root/reference')
+def test_oracle_reproduces_reference_published_table_all_images():
+    """ The same for all four source images of docs/cli.rst:63-72, read from the reference checkout (32 published
+    numbers). """
+    from oracle import make_golden_docs as mgd
+    (s2, s2_tf), (l8, l8_tf) = mgd.matched_references()
+    for name, published in mgd.PUBLISHED.items():
+        src = mgd.read_geotiff(mgd.DATA / 'source' / name)
+        mgd.check_rows(mgd.docs_rows(src['array'], src['transform'], s2, s2_tf, l8, l8_tf), published, name)
