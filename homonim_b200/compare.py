@@ -10,6 +10,7 @@ import numpy as np
 
 from homonim_b200 import _native
 from homonim_b200.enums import ProcCrs, Resampling
+from homonim_b200.errors import IoError
 from homonim_b200.fuse import RasterFuse, _band, _validate_threads
 from homonim_b200.kernel_model import (NAN, _as_f32_plane, _call, _nodata_args, _require_torch, _resample_plane,
                                         _stream, _to_device)
@@ -98,7 +99,7 @@ class RasterCompare:
 
     def _assert_open(self):
         if self._closed:
-            raise OSError('The raster pair has not been opened: use it in a `with` block, or call `open()`.')
+            raise IoError('The raster pair has not been opened: use it in a `with` block, or call `open()`.')
 
     # ---- configuration and tables (reference compare.py:90-131, 189-211) --------------------------------------------
     @staticmethod

@@ -1,52 +1,39 @@
 """
-Exception and warning classes of the reference API (mirrors /root/reference/homonim/errors.py), plus the errors the
-B200 path adds for its native library.
+Exceptions and warnings raised on the kernel-model path.  The class names are the ones the reference raises in the same
+situations (/root/reference/homonim/errors.py), so that ``except`` clauses written against homonim keep working; the
+reference's file-format, block-size and band-matching errors belong to components outside this path and are not
+defined here.
 """
 
 
 class HomonimError(Exception):
-    """ Root exception class. """
-
-
-class UnsupportedImageError(HomonimError):
-    """ Raised when an image cannot be handled. """
-
-
-class ImageContentError(HomonimError):
-    """ Raised when an image has insufficient coverage or bands. """
-
-
-class BlockSizeError(HomonimError):
-    """ Raised when the image block size is invalid. """
-
-
-class ImageProfileError(HomonimError):
-    """ Raised when an image profile is invalid. """
-
-
-class ImageFormatError(HomonimError):
-    """ Raised when an image format is invalid. """
-
-
-class IoError(HomonimError):
-    """ Raised when accessing unopened file(s). """
+    """ Base class of every exception this package raises itself. """
 
 
 class NativeLibraryError(HomonimError):
-    """ Raised when the sm_100a CUDA library is missing, fails to load, or a CUDA call fails (no CPU fallback). """
+    """ The sm_100a CUDA library is missing or failed to load, no CUDA device is present, or a native call returned an
+    error.  There is no CPU fallback, so this is always fatal for the call. """
+
+
+class IoError(HomonimError):
+    """ A raster pair (``RasterFuse`` / ``RasterCompare``) was used before ``open()`` / outside its ``with`` block
+    (reference raster_pair.py:271-278). """
+
+
+class ImageContentError(HomonimError):
+    """ The rasters cannot be fused: the reference does not cover the source, or has fewer bands than the source
+    (reference raster_pair.py:160-192). """
+
+
+class ImageProfileError(HomonimError):
+    """ A ``RasterArray`` was given an incomplete or inconsistent georeferencing profile
+    (reference raster_array.py:83-98). """
 
 
 class HomonimWarning(RuntimeWarning):
-    """ Homonim runtime warning. """
-
-
-class BandMatchWarning(HomonimWarning):
-    """ Warn about band matching issues. """
-
-
-class ImageFormatWarning(HomonimWarning):
-    """ Warn about image format issues. """
+    """ Base class of the warnings below; filter on it to silence the package. """
 
 
 class ConfigWarning(HomonimWarning):
-    """ Warn about configuration issues. """
+    """ A configuration value is allowed but not recommended, e.g. ``proc_crs`` set against the pixel-size ordering
+    of source and reference (reference raster_pair.py:194-225). """

@@ -207,7 +207,7 @@ def test_raster_compare_host_logic():
     assert cmp.proc_crs == ProcCrs.ref and tuple(cmp.src_bands) == (1, 2) and tuple(cmp.ref_bands) == (1, 2)
     assert cmp._get_resampling(src.res, ref.res) == Resampling.average
     assert cmp._get_resampling(ref.res, src.res, upsampling='nearest') == Resampling.nearest
-    with pytest.raises(OSError):
+    with pytest.raises(IoError):
         cmp.process()
     rng = np.random.default_rng(3)
     image_sums = []

@@ -394,6 +394,7 @@ def test_raster_compare_vs_reference_golden():
     import json
     import pathlib
     from homonim_b200 import Affine, RasterCompare
+    from homonim_b200.errors import IoError
     from oracle import kernel_model_np as knp
     NAN = float('nan')
     golden = pathlib.Path(__file__).resolve().parent / 'golden'
@@ -410,7 +411,7 @@ def test_raster_compare_vs_reference_golden():
                 cmp = RasterCompare(RasterArray(to(src), crs, src_tf, nodata=NAN),
                                     RasterArray(to(ref), crs, ref_tf, nodata=NAN), proc_crs=case['proc_crs'],
                                     band_names=names)
-                with pytest.raises(OSError):
+                with pytest.raises(IoError):
                     cmp.process()
                 with cmp:
                     stats = cmp.process()
