@@ -15,9 +15,10 @@ from homonim_b200.raster_array import RasterArray
 from homonim_b200.kernel_model import KernelModel, RefSpaceModel, SrcSpaceModel
 from homonim_b200.fuse import RasterFuse
 from homonim_b200.compare import RasterCompare
+from homonim_b200.geotiff import GeoTiffReader, write_geotiff
 
 __version__ = '0.1.0'
 logging.getLogger(__name__).addHandler(logging.NullHandler())
 
 __all__ = ['Model', 'ProcCrs', 'Resampling', 'Affine', 'CRS', 'RasterArray', 'KernelModel', 'RefSpaceModel',
-           'SrcSpaceModel', 'RasterFuse', 'RasterCompare', 'NativeLibraryError']
+           'SrcSpaceModel', 'RasterFuse', 'RasterCompare', 'GeoTiffReader', 'write_geotiff', 'NativeLibraryError']

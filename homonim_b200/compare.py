@@ -58,8 +58,8 @@ class RasterCompare:
                  band_names: Optional[List[str]] = None):
         """
         Compare a source raster with a reference (reference compare.py:38-81).  Arguments as for
-        :class:`~homonim_b200.fuse.RasterFuse`; ``band_names`` stands in for the band descriptions the reference
-        reads from the files (compare.py:171-175; default ``'Ref. band N'``).
+        :class:`~homonim_b200.fuse.RasterFuse` (GeoTIFF file names or RasterArrays); ``band_names`` overrides the band
+        descriptions read from the files (compare.py:171-175; default for RasterArrays: ``'Ref. band N'``).
         """
         self._pair = RasterFuse(src, ref, proc_crs=proc_crs, src_bands=src_bands, ref_bands=ref_bands, force=force)
         if band_names is not None and len(band_names) < len(self._pair.src_bands):
@@ -151,6 +151,11 @@ class RasterCompare:
     def _band_name(self, band_i: int) -> str:
         if self._band_names is not None:
             return self._band_names[band_i]
+        files = self._pair._files
+        if files is not None:            # the reference band's description, else the source band's (compare.py:171-173)
+            name = files.ref_descriptions[band_i] or files.src_descriptions[band_i]
+            if name:
+                return name
         return f'Ref. band {self.ref_bands[band_i]}'                        # compare.py:174
 
     def _get_image_stats(self, image_sums: List[Dict]) -> Dict[str, Dict]:
@@ -167,7 +172,7 @@ class RasterCompare:
     def _band_sums_device(self, band_i: int, **kwargs):
         """ `get_block_sums` of reference compare.py:232-256 for one band (read as a single block): re-project onto
         the processing grid, then the masked sums -- returns the 7 sums as a float64 device tensor. """
-        src_ra = _band(self._pair._src, self.src_bands[band_i])
+        src_ra = _band(self._pair._src, self._pair._src_bands[band_i])
         ref_ra = self._pair._ref_block(band_i)
         src_t, ref_t = _to_device(src_ra.array), _to_device(ref_ra.array)
         src_nodata, ref_nodata = src_ra.nodata, ref_ra.nodata

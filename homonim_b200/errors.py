@@ -1,8 +1,7 @@
 """
 Exceptions and warnings raised on the kernel-model path.  The class names are the ones the reference raises in the same
 situations (/root/reference/homonim/errors.py), so that ``except`` clauses written against homonim keep working; the
-reference's file-format, block-size and band-matching errors belong to components outside this path and are not
-defined here.
+reference's file-format and block-size errors belong to components outside this path and are not defined here.
 """
 
 
@@ -37,3 +36,8 @@ class HomonimWarning(RuntimeWarning):
 class ConfigWarning(HomonimWarning):
     """ A configuration value is allowed but not recommended, e.g. ``proc_crs`` set against the pixel-size ordering
     of source and reference (reference raster_pair.py:194-225). """
+
+
+class BandMatchWarning(HomonimWarning):
+    """ Something about the band selection / matching of two files was assumed rather than known, e.g. a three-band
+    image without wavelength metadata taken to be RGB (reference matched_pair.py:118-176). """

@@ -13,6 +13,7 @@ and ``process`` RETURNS the corrected (and optionally parameter) rasters instead
 block grid exists to bound host memory (raster_pair.py:227-269); on a 180 GB B200 a whole band is one block, which is
 also the reference's own result for ``max_block_mem`` large enough.
 """
+import pathlib
 import threading
 import warnings
 from multiprocessing import cpu_count
@@ -22,6 +23,7 @@ import numpy as np
 
 from homonim_b200.enums import Model, ProcCrs
 from homonim_b200.errors import ConfigWarning, ImageContentError, IoError
+from homonim_b200.files import FilePair, is_path
 from homonim_b200.geometry import Affine
 from homonim_b200.kernel_model import KernelModel, RefSpaceModel, SrcSpaceModel, overlap_for_kernel
 from homonim_b200.raster_array import RasterArray, is_tensor
@@ -90,11 +92,14 @@ class RasterFuse:
         matched_pair.py:38-83).  ``src`` / ``ref`` are RasterArrays on north-up grids of the same CRS; ``src_bands`` /
         ``ref_bands`` are 1-based band indexes (default: all bands, matched in order).
         """
+        self._files = None
+        if is_path(src) and is_path(ref):
+            # GeoTIFF file names, as the reference takes them: open, match the bands by wavelength (matched_pair.py),
+            # and stage the matched bands (in matched order) for the GPU path
+            self._files = FilePair(src, ref, src_bands=src_bands, ref_bands=ref_bands, force=force)
+            src, ref, src_bands, ref_bands = self._files.src_ra, self._files.ref_ra, None, None
         if not isinstance(src, RasterArray) or not isinstance(ref, RasterArray):
-            raise NotImplementedError(
-                'homonim_b200.RasterFuse takes in-memory RasterArray objects; GeoTIFF file I/O is outside the B200 '
-                'kernel-model path (read the files with rasterio and wrap the arrays in RasterArray)'
-            )
+            raise TypeError('`src` and `ref` must both be GeoTIFF file names, or both be RasterArray objects')
         if src.crs != ref.crs:
             raise NotImplementedError('source and reference must share a CRS (CRS re-projection is out of scope)')
         self._src, self._ref = src, ref
@@ -133,11 +138,13 @@ class RasterFuse:
 
     @property
     def src_bands(self) -> Tuple[int, ...]:
-        return tuple(self._src_bands)
+        """ 1-based source bands taking part (band numbers in the file, for a pair opened from files). """
+        return tuple(self._files.src_bands) if self._files is not None else tuple(self._src_bands)
 
     @property
     def ref_bands(self) -> Tuple[int, ...]:
-        return tuple(self._ref_bands)
+        """ The reference band matched to each source band. """
+        return tuple(self._files.ref_bands) if self._files is not None else tuple(self._ref_bands)
 
     @property
     def closed(self) -> bool:
@@ -263,6 +270,11 @@ class RasterFuse:
         band-major as the reference's parameter file does (index = param_i * n_bands + band_i, fuse.py:315).
         """
         self._assert_open()
+        if self._files is not None and not overwrite:  # fuse.py:275-282: refuse before any work is done
+            for name, what in ((corr_filename, 'Corrected'), (param_filename, 'Parameter')):
+                if is_path(name) and pathlib.Path(name).exists():
+                    raise FileExistsError(
+                        f"{what} image file exists and won't be overwritten without the `overwrite` option: {name}")
         model_type = Model(model)
         _ = overlap_for_kernel(kernel_shape)           # fuse.py:371 (single block per band: no overlap is needed)
         model_config = RasterFuse.create_model_config(**(model_config or {}))
@@ -340,6 +352,14 @@ class RasterFuse:
             planes = [param_planes[b].array[p] for p in range(n_params) for b in range(n_bands)]
             stack = torch.stack if is_tensor(planes[0]) else np.stack
             params = RasterArray(stack(planes), param_planes[0].crs, param_planes[0].transform, nodata=float('nan'))
+        if self._files is not None and is_path(corr_filename):
+            # a pair opened from files: write the outputs with the reference's metadata (fuse.py:264-293)
+            meta = dict(model=model_type, kernel_shape=tuple(kernel_shape), **model_config, **block_config)
+            self._files.write_corrected(corr.to_host(), corr_filename, self.proc_crs, out_profile,
+                                        overwrite=overwrite, **meta)
+            if params is not None and is_path(param_filename):
+                self._files.write_params(params.to_host(), param_filename, self.proc_crs, out_profile,
+                                         overwrite=overwrite, **meta)
         return corr, params
 
 

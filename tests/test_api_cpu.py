@@ -117,8 +117,10 @@ def test_raster_fuse_host_logic():
         RasterFuse(src, ref, proc_crs='src')
     with pytest.raises(IoError):
         fuse.process()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(FileNotFoundError):          # file names are opened as GeoTIFFs (tests/test_files_cpu.py)
         RasterFuse('src.tif', 'ref.tif')
+    with pytest.raises(TypeError):
+        RasterFuse(src, 'ref.tif')
     assert RasterFuse.create_block_config(threads=1) == dict(threads=1, max_block_mem=100)
     assert RasterFuse.create_out_profile()['dtype'] == 'float32'
     assert RasterFuse.create_model_config() == KernelModel.create_config()
