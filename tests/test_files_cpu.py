@@ -295,3 +295,37 @@ def test_band_matching_of_the_reference_images():
         assert match_bands(ngi, l8) == ((1, 2, 3), (4, 3, 2))
         assert match_bands(l8, modis, src_bands=[4, 3, 2]) == ((4, 3, 2), (1, 4, 3))
         assert ngi.crs == s2.crs == l8.crs == modis.crs
+
+
+def test_geotiff_georeferencing_variants(tmp_path):
+    """ ModelTransformation instead of scale + tie point; RasterPixelIsPoint (the tie point is a pixel centre); a tie
+    point that is not at the raster origin. """
+    import struct
+    array = np.arange(16 * 16, dtype='uint8').reshape(1, 16, 16)
+    path = write_geotiff(tmp_path / 'a.tif', array, TF, geokeys=GEOKEYS, compress=None)
+    blob = bytearray(path.read_bytes())
+    ifd, = struct.unpack('<I', blob[4:8])
+    n, = struct.unpack('<H', blob[ifd:ifd + 2])
+    pos = {struct.unpack('<H', blob[ifd + 2 + 12 * i:ifd + 4 + 12 * i])[0]: ifd + 2 + 12 * i for i in range(n)}
+    # tie point (i, j) = (2, 3) <-> the same world point
+    tie_off, = struct.unpack('<I', blob[pos[33922] + 8:pos[33922] + 12])
+    x, y = TF * (2, 3)
+    blob[tie_off:tie_off + 48] = struct.pack('<6d', 2.0, 3.0, 0.0, x, y, 0.0)
+    (tmp_path / 'tie.tif').write_bytes(bytes(blob))
+    with GeoTiffReader(tmp_path / 'tie.tif') as im:
+        assert im.transform == TF
+    # RasterPixelIsPoint: GTRasterTypeGeoKey (1025) = 2 -> the grid origin is half a pixel up and left of the tie point
+    keys = (1, 1, 0, 3, 1024, 0, 1, 1, 1025, 0, 1, 2, 3072, 0, 1, 3857)
+    point = write_geotiff(tmp_path / 'point.tif', array, TF, geokeys=(keys, (), ''), compress=None)
+    with GeoTiffReader(point) as im:
+        assert im.transform == TF * Affine.translation(-0.5, -0.5)
+    # ModelTransformation (34264): re-tag the pixel-scale entry as a 16-double matrix and drop the tie point
+    blob = bytearray(path.read_bytes())
+    matrix = struct.pack('<16d', TF.a, 0, 0, TF.c, 0, TF.e, 0, TF.f, 0, 0, 0, 0, 0, 0, 0, 1)
+    blob[pos[33550]:pos[33550] + 12] = struct.pack('<HHII', 34264, 12, 16, len(blob))
+    blob[pos[33922]:pos[33922] + 2] = struct.pack('<H', 65000)            # an unknown private tag: ignored
+    blob += matrix
+    # (the directory is no longer sorted by tag; readers must not rely on the order)
+    (tmp_path / 'matrix.tif').write_bytes(bytes(blob))
+    with GeoTiffReader(tmp_path / 'matrix.tif') as im:
+        assert im.transform == TF and np.array_equal(im.read(), array)
