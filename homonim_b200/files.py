@@ -118,6 +118,7 @@ class FilePair:
         compress = out_profile.get('compress', 'deflate')
         compress = None if compress in (None, 'none', 'NONE') else str(compress).lower()
         return dict(compress=compress, blocksize=int(out_profile.get('blockxsize', 512) or 512),
+                    level=int(out_profile.get('zlevel', 6)),          # GDAL's ZLEVEL creation option (default 6)
                     interleave=str(out_profile.get('interleave', 'band')).lower(),
                     photometric=(str(out_profile['photometric']).lower() if out_profile.get('photometric') else
                                  'minisblack'))
