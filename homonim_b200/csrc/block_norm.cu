@@ -361,12 +361,16 @@ extern "C" int hb_block_norm(const float *src_dev, int src_has_nodata, double sr
     const long cap = (long)hb_sm_count() * 2;
     if (blocks > cap) blocks = cap;
     const size_t smem01 = 4 * kBins * sizeof(unsigned int), smem2 = 4 * 256 * sizeof(unsigned int);
-    static std::atomic<unsigned long long> attr_set{0ull};
-    if (hb_first_on_device(attr_set)) {
-        HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
-        HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
-        HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
-        HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
+    static HbOncePerDevice attr_once;
+    {
+        const int rc = hb_once_per_device(attr_once, [&]() -> int {
+            HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
+            HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
+            HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
+            HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
+            return 0;
+        });
+        if (rc) return rc;
     }
     norm_init_kernel<<<1, 256, 0, st>>>(state);
     HB_LAUNCH_OK("norm_init_kernel");

@@ -129,15 +129,24 @@ static inline cudaError_t hb_pool_keep_memory()
     return err;
 }
 
-// True exactly once per (call site, device): for per-device one-time set-up such as cudaFuncSetAttribute (function
-// attributes belong to the device that is current when they are set).  `mask` is a call-site static.
-#include <atomic>
-static inline bool hb_first_on_device(std::atomic<unsigned long long> &mask)
+// Per-device one-time set-up such as cudaFuncSetAttribute (function attributes belong to the device that is current
+// when they are set).  `once` is a call-site static; the set-up runs under its mutex and the device's bit is only set
+// AFTER it succeeded, so a second thread can never launch before the attribute is in place.
+#include <mutex>
+struct HbOncePerDevice {
+    std::mutex mu;
+    unsigned long long done = 0ull;
+};
+template <class F> static inline int hb_once_per_device(HbOncePerDevice &once, F &&setup)
 {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return setup();
     const unsigned long long bit = 1ull << dev;
-    return (mask.fetch_or(bit) & bit) == 0ull;
+    std::lock_guard<std::mutex> lock(once.mu);
+    if (once.done & bit) return 0;
+    const int rc = setup();
+    if (rc == 0) once.done |= bit;
+    return rc;
 }
 
 static inline int hb_sm_count()

@@ -1251,9 +1251,12 @@ int hb_up_poly_resample(const float *coarse, int nb, const UpPolyGeom &g, float 
     }
     {
         const size_t smem = kMaxRows * (sizeof(RowEntryD) + sizeof(int)) + (size_t)kWarps * kYfCols * 2 * 32 * sizeof(double2);
-        static std::atomic<unsigned long long> attr_done{0ull};
-        if (hb_first_on_device(attr_done))
+        static HbOncePerDevice attr_once;
+        const int arc = hb_once_per_device(attr_once, [&]() -> int {
             HB_CUDA_OK(cudaFuncSetAttribute(upsample_yfirst_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            return 0;
+        });
+        if (arc) return arc;
         const long cta_w = (long)kWarpW * kWarps;
         const long gx = (g.ws + cta_w - 1) / cta_w;
         const long slots = (long)hb_sm_count() * 2;

@@ -58,8 +58,10 @@ class FilePair:
                 raise ImageContentError('No source / reference bands could be matched.')
             for im in (src_im, ref_im):
                 if im.nodata is None and 'alpha' in im.colorinterp:
-                    warnings.warn(f'{pathlib.Path(im.name).name}: alpha / internal masks are not read; pixels are '
-                                  f'only masked by a nodata value.')
+                    # the reference masks with the alpha band then (dataset_mask, raster_array.py:170-197); reading the
+                    # file as fully valid would let the masked pixels into the fit
+                    raise NotImplementedError(f'{pathlib.Path(im.name).name}: alpha-band masks are not supported (give '
+                                              f'the image a nodata value instead)')
             # the reference window that covers the source (whole reference pixels, 2 pixels to spare), clipped
             left, bottom, right, top = src_im.bounds
             rt = ref_im.transform

@@ -38,6 +38,28 @@ _SAMPLE_DTYPES = {(1, 8): 'u1', (1, 16): 'u2', (1, 32): 'u4', (2, 8): 'i1', (2, 
 _DEFLATE = (8, 32946)
 # GeoKeys that only carry citations / names: ignored when two CRSs are compared
 _CITATION_KEYS = (1026, 2049, 3073)
+_RASTER_TYPE_KEY = 1025          # GTRasterTypeGeoKey: 1 = RasterPixelIsArea, 2 = RasterPixelIsPoint (not part of the CRS)
+
+
+def _raster_type(directory: Sequence[int]) -> int:
+    """ GTRasterTypeGeoKey of a GeoKeyDirectory (1 = PixelIsArea when absent). """
+    if directory and len(directory) >= 4:
+        for i in range(directory[3]):
+            key, loc, _, value = directory[4 + 4 * i:8 + 4 * i]
+            if key == _RASTER_TYPE_KEY and loc == 0:
+                return int(value)
+    return 1
+
+
+def _geokeys_pixel_is_area(geokeys):
+    """ The GeoKeys with GTRasterTypeGeoKey rewritten to RasterPixelIsArea: `write_geotiff` always writes its tie point
+    at the pixel CORNER, so keys passed through from a PixelIsPoint source must not keep saying "point". """
+    directory = list(geokeys[0])
+    if len(directory) >= 4:
+        for i in range(directory[3]):
+            if directory[4 + 4 * i] == _RASTER_TYPE_KEY and directory[5 + 4 * i] == 0:
+                directory[7 + 4 * i] = 1
+    return (tuple(directory),) + tuple(geokeys[1:])
 
 _pool = None
 
@@ -57,7 +79,7 @@ def _crs_from_geokeys(directory: Sequence[int], doubles: Sequence[float], ascii_
     keys = []
     for i in range(directory[3]):
         key, loc, count, value = directory[4 + 4 * i:8 + 4 * i]
-        if key in _CITATION_KEYS:
+        if key in _CITATION_KEYS or key == _RASTER_TYPE_KEY:
             continue
         if loc == 0:
             keys.append((key, value))
@@ -100,6 +122,21 @@ class GeoTiffReader:
         self._bo = bo
         tags = self._read_ifd(ifd_off)
         self._raw_tags = tags
+        # GDAL per-dataset masks live in a LATER IFD (NewSubfileType bit 2) or in a `.msk` side-car; the reference honours
+        # them through dataset_mask (raster_array.py:170-197).  They are not decoded here, and reading such a file as
+        # "fully valid" would let invalid pixels into the fit, so refuse it.
+        self.has_internal_mask = False
+        next_off, seen = self._next_ifd, 0
+        while next_off and seen < 64:
+            sub = self._read_ifd(next_off)
+            next_off, seen = self._next_ifd, seen + 1
+            if 254 in sub and (int(sub[254][0]) & 4):
+                self.has_internal_mask = True
+        if os.path.exists(self.name + '.msk'):
+            self.has_internal_mask = True
+        if self.has_internal_mask:
+            raise NotImplementedError(f'{self.name}: internal / side-car mask bands are not supported (give the image '
+                                      f'a nodata value instead)')
         self.width, self.height = int(tags[256][0]), int(tags[257][0])
         self.count = int(tags.get(277, (1,))[0])
         bits = tags.get(258, (1,))
@@ -144,7 +181,7 @@ class GeoTiffReader:
         self.crs = _crs_from_geokeys(*self._geo)
         if self.crs is not None:
             self.crs.raw_geokeys = self._geo
-            if dict(self.crs.definition[1]).get(1025) == 2:     # RasterPixelIsPoint: the tie point is a pixel centre
+            if _raster_type(self._geo[0]) == 2:                 # RasterPixelIsPoint: the tie point is a pixel centre
                 self.transform = self.transform * Affine.translation(-0.5, -0.5)
         nodata = tags.get(42113)
         self.nodata = None
@@ -215,6 +252,9 @@ class GeoTiffReader:
                 tags[tag] = tuple(vals[2 * k] / vals[2 * k + 1] if vals[2 * k + 1] else 0.0 for k in range(cnt))
             else:
                 tags[tag] = struct.unpack(bo + fmt * cnt, data)
+        fh.seek(offset + (8 if self._big else 2) + esize * n)
+        nxt = fh.read(8 if self._big else 4)
+        self._next_ifd = struct.unpack(bo + ('Q' if self._big else 'I'), nxt)[0] if len(nxt) in (4, 8) else 0
         return tags
 
     # ---- dataset-style attributes -------------------------------------------------------------------------------------
@@ -476,6 +516,7 @@ def write_geotiff(filename, array, transform, crs=None, nodata=None, description
         if geokeys is None:
             geokeys = getattr(crs, 'raw_geokeys', None)         # a CRS read by GeoTiffReader carries its raw keys
         if geokeys and geokeys[0]:
+            geokeys = _geokeys_pixel_is_area(geokeys)           # the tie point below is a pixel corner
             add(34735, 3, geokeys[0])
             if geokeys[1]:
                 add(34736, 12, geokeys[1])

@@ -315,10 +315,27 @@ def test_geotiff_georeferencing_variants(tmp_path):
     with GeoTiffReader(tmp_path / 'tie.tif') as im:
         assert im.transform == TF
     # RasterPixelIsPoint: GTRasterTypeGeoKey (1025) = 2 -> the grid origin is half a pixel up and left of the tie point
-    keys = (1, 1, 0, 3, 1024, 0, 1, 1, 1025, 0, 1, 2, 3072, 0, 1, 3857)
-    point = write_geotiff(tmp_path / 'point.tif', array, TF, geokeys=(keys, (), ''), compress=None)
-    with GeoTiffReader(point) as im:
+    # (the writer itself always writes PixelIsArea -- see test_pixel_is_point_round_trip -- so patch the key in place)
+    blob = bytearray(path.read_bytes())
+    key_off, = struct.unpack('<I', blob[pos[34735] + 8:pos[34735] + 12])
+    keys = list(struct.unpack('<16H', blob[key_off:key_off + 32]))
+    assert keys[8:12] == [1025, 0, 1, 1]
+    keys[11] = 2
+    blob[key_off:key_off + 32] = struct.pack('<16H', *keys)
+    (tmp_path / 'point.tif').write_bytes(bytes(blob))
+    with GeoTiffReader(tmp_path / 'point.tif') as im:
         assert im.transform == TF * Affine.translation(-0.5, -0.5)
+        point_crs, point_keys = im.crs, im.geokeys
+    with GeoTiffReader(path) as im:
+        assert im.crs == point_crs          # PixelIsPoint / PixelIsArea describe the raster space, not the CRS
+    # writing with keys passed through from a PixelIsPoint file must not shift the grid: write -> read -> write -> read
+    t0 = TF * Affine.translation(-0.5, -0.5)
+    again = write_geotiff(tmp_path / 'again.tif', array, t0, geokeys=point_keys, compress=None)
+    with GeoTiffReader(again) as im:
+        assert im.transform == t0
+        again2 = write_geotiff(tmp_path / 'again2.tif', array, im.transform, crs=im.crs, compress=None)
+    with GeoTiffReader(again2) as im:
+        assert im.transform == t0
     # ModelTransformation (34264): re-tag the pixel-scale entry as a 16-double matrix and drop the tie point
     blob = bytearray(path.read_bytes())
     matrix = struct.pack('<16d', TF.a, 0, 0, TF.c, 0, TF.e, 0, TF.f, 0, 0, 0, 0, 0, 0, 0, 1)
@@ -329,3 +346,34 @@ def test_geotiff_georeferencing_variants(tmp_path):
     (tmp_path / 'matrix.tif').write_bytes(bytes(blob))
     with GeoTiffReader(tmp_path / 'matrix.tif') as im:
         assert im.transform == TF and np.array_equal(im.read(), array)
+
+
+def test_internal_mask_ifd_is_refused(tmp_path):
+    """ A GDAL per-dataset mask sits in a second IFD (NewSubfileType bit 2); the reference honours it through
+    dataset_mask (raster_array.py:170-197).  It is not decoded here, so the file must be refused, not read as valid. """
+    import struct
+    array = np.arange(16 * 16, dtype='uint8').reshape(1, 16, 16)
+    path = write_geotiff(tmp_path / 'a.tif', array, TF, geokeys=GEOKEYS, compress=None)
+    with GeoTiffReader(path) as im:
+        assert not im.has_internal_mask
+    blob = bytearray(path.read_bytes())
+    ifd, = struct.unpack('<I', blob[4:8])
+    n, = struct.unpack('<H', blob[ifd:ifd + 2])
+    next_pos = ifd + 2 + 12 * n
+    assert struct.unpack('<I', blob[next_pos:next_pos + 4])[0] == 0
+    # append a second IFD: NewSubfileType = 4 (mask), 16 x 16, 1 bit per sample
+    second = len(blob) + (len(blob) & 1)
+    blob += b'\0' * (second - len(blob))
+    entries = [(254, 4, 1, 4), (256, 3, 1, 16), (257, 3, 1, 16), (258, 3, 1, 1)]
+    blob += struct.pack('<H', len(entries))
+    for tag, typ, cnt, val in entries:
+        blob += struct.pack('<HHII', tag, typ, cnt, val)
+    blob += struct.pack('<I', 0)
+    blob[next_pos:next_pos + 4] = struct.pack('<I', second)
+    (tmp_path / 'masked.tif').write_bytes(bytes(blob))
+    with pytest.raises(NotImplementedError, match='mask'):
+        GeoTiffReader(tmp_path / 'masked.tif')
+    # a .msk side-car is the other form of the same thing
+    (tmp_path / 'a.tif.msk').write_bytes(b'')
+    with pytest.raises(NotImplementedError, match='mask'):
+        GeoTiffReader(path)
