@@ -17,16 +17,21 @@ namespace {
 constexpr int kBins = 4096;
 constexpr int kNormThreads = 512;
 
-struct NormState {
+// What one pass over (a shard of) the planes accumulates.  It sits at the start of the workspace, so that the ranks of a
+// row-band sharded raster can exchange it (hb_block_norm_accum_bytes / hb_block_norm_partial / hb_block_norm_merge).
+struct NormAccum {
     unsigned long long n;          // number of valid pixels
     double sum[2];                 // sum src, sum ref
     double ssd[2];                 // sum (x - mean)^2
+    unsigned long long hist[4][kBins];
+};
+
+struct NormState : NormAccum {
     double mean[2];
     unsigned long long rank[4];    // remaining rank inside the current prefix; queries: src k, src k+1, ref k, ref k+1
     unsigned int prefix[4];        // key prefix found so far
     float gamma;                   // numpy's interpolation weight
     unsigned int ticket;           // CTAs that have finished the current level (the last one resolves it)
-    unsigned long long hist[4][kBins];
 };
 
 __device__ __forceinline__ unsigned int float_key(float v)
@@ -127,6 +132,8 @@ __device__ __forceinline__ void norm_pixel(float s, float r, bool valid, unsigne
 // LEVEL 1: histogram of (key >> 8) & 0xfff for keys matching each query's 12-bit prefix; squared deviations
 // LEVEL 2: histogram of key & 0xff for keys matching each query's 24-bit prefix
 // The last CTA to finish a level resolves it (norm_resolve) -- no separate one-CTA launches between the passes.
+// `norm` == nullptr: accumulate only (row-band shards: the level is resolved by norm_merge_kernel once every rank's
+// accumulators are known).
 template <int LEVEL, bool VEC>
 __global__ void __launch_bounds__(kNormThreads)
 norm_level_kernel(const float *__restrict__ src, NoData nd_s, const float *__restrict__ ref, NoData nd_r, long n,
@@ -199,6 +206,7 @@ norm_level_kernel(const float *__restrict__ src, NoData nd_s, const float *__res
             if (threadIdx.x == 0) atomicAdd(&st->n, (unsigned long long)(tc + 0.5));
         }
     }
+    if (norm == nullptr) return;
     // ---- the last CTA to arrive resolves the level -------------------------------------------------------------------
     __threadfence();
     __syncthreads();
@@ -326,6 +334,39 @@ __device__ void norm_resolve(NormState *__restrict__ st, double *__restrict__ no
     }
 }
 
+// Row-band shards: sum the accumulators of all ranks (`gathered`: world x NormAccum, in rank order -- a fixed order, so
+// every rank gets bit-identical statistics) into this rank's state and resolve the level.  One CTA.
+template <int LEVEL>
+__global__ void __launch_bounds__(kNormThreads)
+norm_merge_kernel(NormState *__restrict__ st, const NormAccum *__restrict__ gathered, int world, double *__restrict__ norm)
+{
+    constexpr int bins = (LEVEL == 2) ? 256 : kBins;
+    constexpr int nq = (LEVEL == 0) ? 3 : 4;                 // level 0 fills hist[0] and hist[2] only
+    for (int i = threadIdx.x; i < nq * bins; i += blockDim.x) {
+        const int q = i / bins, b = i % bins;
+        if (LEVEL == 0 && q == 1) continue;
+        unsigned long long c = 0;
+        for (int r = 0; r < world; r++) c += gathered[r].hist[q][b];
+        st->hist[q][b] = c;
+    }
+    if (threadIdx.x == 0) {
+        if (LEVEL == 0) {
+            unsigned long long n = 0;
+            double s0 = 0.0, s1 = 0.0;
+            for (int r = 0; r < world; r++) { n += gathered[r].n; s0 += gathered[r].sum[0]; s1 += gathered[r].sum[1]; }
+            st->n = n; st->sum[0] = s0; st->sum[1] = s1;
+        }
+        if (LEVEL == 1) {
+            double d0 = 0.0, d1 = 0.0;
+            for (int r = 0; r < world; r++) { d0 += gathered[r].ssd[0]; d1 += gathered[r].ssd[1]; }
+            st->ssd[0] = d0; st->ssd[1] = d1;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    norm_resolve<LEVEL>(st, norm);
+}
+
 __global__ void norm_init_kernel(NormState *st)
 {
     for (int i = threadIdx.x; i < 4 * kBins; i += blockDim.x) st->hist[i / kBins][i % kBins] = 0ull;
@@ -345,6 +386,47 @@ extern "C" size_t hb_block_norm_workspace_bytes(long n)
     return sizeof(NormState);
 }
 
+namespace {
+
+int norm_setup_once(size_t smem01)
+{
+    static HbOncePerDevice attr_once;
+    return hb_once_per_device(attr_once, [&]() -> int {
+        HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
+        HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
+        HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
+        HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
+        return 0;
+    });
+}
+
+// one streaming pass (level 0, 1 or 2) over n pixels of both planes; `norm_dev` == nullptr: accumulate only
+int norm_launch_level(int level, const float *src_dev, const NoData &nd_s, const float *ref_dev, const NoData &nd_r, long n,
+                      NormState *state, double *norm_dev, cudaStream_t st)
+{
+    long blocks = (n / 4 + kNormThreads - 1) / kNormThreads;
+    if (blocks < 1) blocks = 1;
+    const long cap = (long)hb_sm_count() * 2;
+    if (blocks > cap) blocks = cap;
+    const size_t smem01 = 4 * kBins * sizeof(unsigned int), smem2 = 4 * 256 * sizeof(unsigned int);
+    const int rc = norm_setup_once(smem01);
+    if (rc) return rc;
+    const bool vec = (((uintptr_t)src_dev) % 16 == 0) && (((uintptr_t)ref_dev) % 16 == 0);
+#define HB_NORM_LEVEL(L_, SMEM_)                                                                                      \
+    do {                                                                                                              \
+        if (vec) norm_level_kernel<L_, true><<<(unsigned)blocks, kNormThreads, SMEM_, st>>>(src_dev, nd_s, ref_dev, nd_r, n, state, norm_dev); \
+        else norm_level_kernel<L_, false><<<(unsigned)blocks, kNormThreads, SMEM_, st>>>(src_dev, nd_s, ref_dev, nd_r, n, state, norm_dev);    \
+        HB_LAUNCH_OK("norm_level_kernel");                                                                            \
+    } while (0)
+    if (level == 0) HB_NORM_LEVEL(0, smem01);
+    else if (level == 1) HB_NORM_LEVEL(1, smem01);
+    else HB_NORM_LEVEL(2, smem2);
+#undef HB_NORM_LEVEL
+    return 0;
+}
+
+}  // namespace
+
 extern "C" int hb_block_norm(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
                              int ref_has_nodata, double ref_nodata, long n, double *norm_dev, void *workspace_dev,
                              size_t workspace_bytes, void *stream)
@@ -356,34 +438,51 @@ extern "C" int hb_block_norm(const float *src_dev, int src_has_nodata, double sr
     const NoData nd_s = hb_make_nodata(src_has_nodata, src_nodata), nd_r = hb_make_nodata(ref_has_nodata, ref_nodata);
     cudaStream_t st = (cudaStream_t)stream;
     NormState *state = (NormState *)workspace_dev;
-    long blocks = (n / 4 + kNormThreads - 1) / kNormThreads;
-    if (blocks < 1) blocks = 1;
-    const long cap = (long)hb_sm_count() * 2;
-    if (blocks > cap) blocks = cap;
-    const size_t smem01 = 4 * kBins * sizeof(unsigned int), smem2 = 4 * 256 * sizeof(unsigned int);
-    static HbOncePerDevice attr_once;
-    {
-        const int rc = hb_once_per_device(attr_once, [&]() -> int {
-            HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
-            HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
-            HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
-            HB_CUDA_OK(cudaFuncSetAttribute(norm_level_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem01));
-            return 0;
-        });
-        if (rc) return rc;
-    }
     norm_init_kernel<<<1, 256, 0, st>>>(state);
     HB_LAUNCH_OK("norm_init_kernel");
-    const bool vec = (((uintptr_t)src_dev) % 16 == 0) && (((uintptr_t)ref_dev) % 16 == 0);
-#define HB_NORM_LEVEL(L_, SMEM_)                                                                                      \
-    do {                                                                                                              \
-        if (vec) norm_level_kernel<L_, true><<<(unsigned)blocks, kNormThreads, SMEM_, st>>>(src_dev, nd_s, ref_dev, nd_r, n, state, norm_dev); \
-        else norm_level_kernel<L_, false><<<(unsigned)blocks, kNormThreads, SMEM_, st>>>(src_dev, nd_s, ref_dev, nd_r, n, state, norm_dev);    \
-        HB_LAUNCH_OK("norm_level_kernel");                                                                            \
-    } while (0)
-    HB_NORM_LEVEL(0, smem01);
-    HB_NORM_LEVEL(1, smem01);
-    HB_NORM_LEVEL(2, smem2);
-#undef HB_NORM_LEVEL
+    for (int level = 0; level < 3; level++) {
+        const int rc = norm_launch_level(level, src_dev, nd_s, ref_dev, nd_r, n, state, norm_dev, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ---- row-band shards: the same three passes with the per-level resolve replaced by an exchange between the ranks ------
+extern "C" size_t hb_block_norm_accum_bytes(void) { return sizeof(NormAccum); }
+
+extern "C" int hb_block_norm_partial(int level, const float *src_dev, int src_has_nodata, double src_nodata,
+                                     const float *ref_dev, int ref_has_nodata, double ref_nodata, long n,
+                                     void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    HB_REQUIRE(level >= 0 && level <= 2, "hb_block_norm_partial: level must be 0, 1 or 2");
+    HB_REQUIRE(workspace_dev && n >= 0 && (n == 0 || (src_dev && ref_dev)), "hb_block_norm_partial: bad arguments");
+    HB_REQUIRE(workspace_bytes >= sizeof(NormState), "hb_block_norm_partial: workspace too small (%zu < %zu)",
+               workspace_bytes, sizeof(NormState));
+    HB_REQUIRE(((uintptr_t)workspace_dev) % 8 == 0, "hb_block_norm_partial: workspace must be 8-byte aligned");
+    const NoData nd_s = hb_make_nodata(src_has_nodata, src_nodata), nd_r = hb_make_nodata(ref_has_nodata, ref_nodata);
+    cudaStream_t st = (cudaStream_t)stream;
+    NormState *state = (NormState *)workspace_dev;
+    if (level == 0) {
+        norm_init_kernel<<<1, 256, 0, st>>>(state);
+        HB_LAUNCH_OK("norm_init_kernel");
+    }
+    if (n == 0) return 0;                                    // (a rank without rows contributes empty accumulators)
+    return norm_launch_level(level, src_dev, nd_s, ref_dev, nd_r, n, state, nullptr, st);
+}
+
+extern "C" int hb_block_norm_merge(int level, const void *gathered_dev, int world, void *workspace_dev,
+                                   size_t workspace_bytes, double *norm_dev, void *stream)
+{
+    HB_REQUIRE(level >= 0 && level <= 2, "hb_block_norm_merge: level must be 0, 1 or 2");
+    HB_REQUIRE(gathered_dev && world >= 1 && workspace_dev && norm_dev, "hb_block_norm_merge: bad arguments");
+    HB_REQUIRE(workspace_bytes >= sizeof(NormState), "hb_block_norm_merge: workspace too small");
+    HB_REQUIRE(((uintptr_t)gathered_dev) % 8 == 0, "hb_block_norm_merge: gathered buffer must be 8-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    NormState *state = (NormState *)workspace_dev;
+    const NormAccum *g = (const NormAccum *)gathered_dev;
+    if (level == 0) norm_merge_kernel<0><<<1, kNormThreads, 0, st>>>(state, g, world, norm_dev);
+    else if (level == 1) norm_merge_kernel<1><<<1, kNormThreads, 0, st>>>(state, g, world, norm_dev);
+    else norm_merge_kernel<2><<<1, kNormThreads, 0, st>>>(state, g, world, norm_dev);
+    HB_LAUNCH_OK("norm_merge_kernel");
     return 0;
 }

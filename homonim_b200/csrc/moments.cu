@@ -9,11 +9,13 @@
 //     in registers (double): add the entering row, subtract the row that left the kh-row window;
 //   * per output row the kw-column window sum is a prefix difference: thread-local prefix over its C columns, warp
 //     shuffle scan of the per-thread totals, per-column prefixes published once in shared memory, then
-//     W(x) = Q(x+hw) - Q(x-hw-1) (+ totals of the warps in between);
+//     W(x) = Q(x+hw) - Q(x-hw-1) (+ the total of the warp the window starts in, when it ends in the next one);
 //   * the epilogue evaluates the reference's formulas with the reference's precision class and rounding order for
 //     every intermediate (SURVEY.md 8a numerics note): sums rounded to float32 where cv.boxFilter returns float32,
 //     kept double where cv.sqrBoxFilter returns float64, float32 numerator, double denominator, no FMA contraction.
 //   Zero padding beyond the raster (cv BORDER_CONSTANT) falls out of skipping out-of-range rows / columns.
+#include <type_traits>
+
 #include "hb_common.cuh"
 
 namespace {
@@ -23,7 +25,7 @@ namespace {
 #endif
 constexpr int kFitThreads = 128;
 constexpr int kFitWarps = kFitThreads / 32;
-constexpr int kMaxHalfW = 64;                    // kw <= 129
+constexpr int kMaxHalfW = 63;                    // kw <= 127: a window spans at most two 128-column warps
 
 enum { Q_S = 0, Q_R = 1, Q_P = 2, Q_S2 = 3, Q_R2 = 4 };
 
@@ -33,7 +35,39 @@ struct FitGeom {
     int hw_al;         // half kernel width rounded up to a multiple of C
     int tw_out;        // output columns per CTA
     int rows_per_band;
+    long row0, nrows;  // output rows [row0, row0 + nrows) of the plane; output arrays hold just these rows
+    int aligned;       // planes are 16-byte aligned and w % 4 == 0: 16-byte loads / stores
 };
+
+// L2 residency hints.  Every input row is read twice by a CTA: when it enters the kh-row window and, kh rows later, when
+// it leaves it.  In between the resident CTAs of the whole GPU stream ~(CTAs x kh rows x 512 columns x 8 bytes) -- tens
+// of MB -- through L2, so with plain loads the second read mostly misses (measured: 2.2x the compulsory DRAM reads).
+// Entering rows are therefore loaded "evict last", leaving rows (their last use) "evict first", and the output is
+// written with streaming stores, which leaves L2 to the windows.
+__device__ __forceinline__ unsigned long long hb_policy_evict_last()
+{
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long hb_policy_evict_first()
+{
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 hb_ldg16_hint(const float *p, unsigned long long policy)
+{
+    float4 r;
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ void hb_stg16_stream(float *p, float4 v)
+{
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 // a / b in double with a quotient that is correctly rounded in all but a vanishing fraction of cases (approximate
 // reciprocal + 2 Newton steps + one residual correction: ~9 instructions instead of the ~35 of the IEEE routine).
@@ -53,19 +87,6 @@ __device__ __forceinline__ double hb_ddiv(double a, double b)
     double q = a * r;
     const double rem = fma(-b, q, a);
     return fma(rem, r, q);
-}
-
-// one step of an inclusive warp scan of doubles: v += (value of lane - d), for lanes >= d.  The shuffle's own
-// "source lane in range" predicate guards the add (one predicated DADD instead of an add and two selects).
-__device__ __forceinline__ double scan_step(double v, int d)
-{
-    int lo = __double2loint(v), hi = __double2hiint(v), ulo, uhi, p;
-    asm volatile("{\n\t.reg .pred q;\n\tshfl.sync.up.b32 %0|q, %3, %5, 0, 0xffffffff;\n\t"
-                 "shfl.sync.up.b32 %1, %4, %5, 0, 0xffffffff;\n\tselp.s32 %2, 1, 0, q;\n\t}"
-                 : "=r"(ulo), "=r"(uhi), "=r"(p) : "r"(lo), "r"(hi), "r"(d));
-    const double up = __hiloint2double(uhi, ulo);
-    if (p) v += up;
-    return v;
 }
 
 // contribution of one pixel to the running sums
@@ -100,8 +121,21 @@ __device__ __forceinline__ void pixel_terms(float s, float r, bool valid, double
     cnt = valid ? 1 : 0;
 }
 
-// MODEL: HB_MODEL_*; WANT_R2: third band; NQ: number of double sums carried (2, 4 or 5); C: columns per thread
-template <int MODEL, bool WANT_R2, int NQ, int C, bool ALIGNED>
+// MODEL: HB_MODEL_*; WANT_R2: third band; NQ: number of double sums carried (2, 4 or 5); C: columns per thread;
+// FUSED: write corr = gain * src + offset instead of the parameters.
+//
+// Shared-memory exchange of one output row (double-buffered, one barrier per row).  Per sum k a row of SLOTS doubles:
+//   slots [0, TW)      warp-local inclusive prefixes of the column sums; column c lives at (c % C) * threads + c / C,
+//                      conflict-free for the stores (thread t, its column i) and for the window look-ups
+//   slot  TW           a permanent 0.0
+//   slots TW + 1 + w   total of warp w
+// The window sum of column c is  Q(c + hw) - Q(c - hw - 1) + (total of the warp the window starts in, if it ends in the
+// next one), and every term's slot is a per-thread constant: where a term does not apply (no warp boundary inside the
+// window, window starting at the CTA's first column) its slot is the permanent zero, so the row loop has no selects,
+// no index arithmetic and no divergent branches -- the byte offsets are computed once per thread, the sum's offset is
+// an immediate and the buffer's offset a warp-uniform register.  (The launcher guarantees kw <= columns per warp, so a
+// window never spans more than two warps.)
+template <int MODEL, bool WANT_R2, int NQ, int C, bool FUSED>
 __global__ void __launch_bounds__(kFitThreads, (NQ >= 5 && C == 4) ? HB_FIT_MIN_CTAS - 1 : HB_FIT_MIN_CTAS)
 fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__restrict__ ref, NoData nd_r,
                      FitGeom g, const double *__restrict__ norm, float *__restrict__ params,
@@ -111,35 +145,69 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
     constexpr bool HAS_N = (NQ > 2);
     constexpr int TW = kFitThreads * C;                       // columns per CTA including both halos
     constexpr int WCOLS = 32 * C;                             // columns per warp
-    __shared__ double s_q[2][NQ][TW];                         // per-column warp-local inclusive prefixes
-    __shared__ int s_n[2][HAS_N ? TW : 1];
-    __shared__ double s_tot[2][NQ][kFitWarps];                // per-warp totals
-    __shared__ int s_ntot[2][kFitWarps];
+    constexpr int SLOTS = TW + 8;
+    constexpr int ZERO = TW;
+    // (the valid count rides along as one more row of 4-byte slots, addressed with half the byte offset)
+    constexpr int ROW_BYTES = SLOTS * 8, BUF_BYTES = NQ * ROW_BYTES + (HAS_N ? ROW_BYTES / 2 : 0);
+    __shared__ double s_x[2 * BUF_BYTES / 8];
+    char *const s_base = reinterpret_cast<char *>(s_x);
+    auto q_at = [&](int bufoff, int k, unsigned off) -> double & {
+        return *reinterpret_cast<double *>(s_base + bufoff + k * ROW_BYTES + off);
+    };
+    auto n_at = [&](int bufoff, unsigned off) -> int & {
+        return *reinterpret_cast<int *>(s_base + bufoff + NQ * ROW_BYTES + (off >> 1));
+    };
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int hh = g.kh / 2, hw = g.kw / 2;
-    const long tile_start = (long)blockIdx.x * g.tw_out - g.hw_al;   // global column of this CTA's column 0
-    const long cx = tile_start + (long)t * C;                        // first global column of this thread
-    const long y0 = (long)blockIdx.y * g.rows_per_band;
-    const long y1 = min(y0 + (long)g.rows_per_band, g.h);
-    const long plane = g.h * g.w;
+    const int w = (int)g.w;
+    const int cx = (int)blockIdx.x * g.tw_out - g.hw_al + t * C;     // first global column of this thread (may be < 0)
+    const long y0 = g.row0 + (long)blockIdx.y * g.rows_per_band;     // output rows [y0, y1) of the plane's rows [0, h)
+    const long y1 = min(y0 + (long)g.rows_per_band, g.row0 + g.nrows);
+    const long plane = g.nrows * g.w;                                // output planes hold rows [row0, row0 + nrows)
     const float qnan = __int_as_float(0x7fc00000);
     double n0 = 1.0, n1 = 0.0;
     if (NORM) { n0 = norm[0]; n1 = norm[1]; }
 
+    if (t < 2 * NQ) q_at((t / NQ) * BUF_BYTES, t % NQ, ZERO * 8) = 0.0;
+    if (HAS_N && t < 2) n_at(t * BUF_BYTES, ZERO * 8) = 0;
+
     // validity of a pixel without per-pixel branching on the nodata kind: "equals the nodata value" compares with nan
-    // (never true) when there is no value nodata, and the nan test is switched by a kernel-uniform flag
+    // (never true) when there is no value nodata, and the nan test is OR-ed with a kernel-uniform "nan is data" flag:
+    // four compare-and-combine instructions per pixel, result AND-ed with `gate` (column / row inside the raster)
     const float ndv_s = (nd_s.has && !nd_s.is_nan) ? nd_s.value : qnan, ndv_r = (nd_r.has && !nd_r.is_nan) ? nd_r.value : qnan;
-    const bool nan_s = nd_s.has && nd_s.is_nan, nan_r = nd_r.has && nd_r.is_nan;
-    auto valid2 = [&](float sv, float rv) {
-        return !(sv == ndv_s) && !(rv == ndv_r) && !(nan_s && (sv != sv)) && !(nan_r && (rv != rv));
+    const unsigned keep_nan_s = !(nd_s.has && nd_s.is_nan), keep_nan_r = !(nd_r.has && nd_r.is_nan);
+    auto valid2 = [&](float sv, float rv, unsigned gate) -> bool {
+        unsigned ok;
+        asm("{\n\t.reg .pred p, q, ks, kr;\n\t"
+            "setp.ne.u32 ks, %3, 0;\n\tsetp.ne.u32 kr, %4, 0;\n\t"
+            "setp.num.or.f32 p, %1, %1, ks;\n\tsetp.neu.and.f32 p, %1, %5, p;\n\t"
+            "setp.num.or.f32 q, %2, %2, kr;\n\tsetp.neu.and.f32 q, %2, %6, q;\n\t"
+            "and.pred p, p, q;\n\tselp.u32 %0, %7, 0, p;\n\t}"
+            : "=r"(ok)
+            : "f"(sv), "f"(rv), "r"(keep_nan_s), "r"(keep_nan_r), "f"(ndv_s), "f"(ndv_r), "r"(gate));
+        return ok != 0u;
     };
-    bool col_in[C];
+    // bit i: this thread's column i lies inside the raster
+    unsigned cmask = 0;
 #pragma unroll
-    for (int i = 0; i < C; i++) col_in[i] = (cx + i >= 0) && (cx + i < g.w);
-    const bool vec_ok = ALIGNED && (C == 4) && (cx >= 0) && (cx + C <= g.w);
+    for (int i = 0; i < C; i++) cmask |= ((cx + i >= 0) && (cx + i < w)) ? (1u << i) : 0u;
+    const bool vec_ok = g.aligned && (C == 4) && (cmask == 0xfu);
     // this thread's columns are output columns iff they sit between the two halos (whole-thread granularity)
     const bool out_thread = (t * C >= g.hw_al) && (t * C + C <= g.hw_al + g.tw_out);
+
+    // per-thread constant slots of the window look-ups (see above), as byte offsets inside a row of slots
+    unsigned sl_a[C], sl_b[C], sl_t0[C];
+#pragma unroll
+    for (int i = 0; i < C; i++) {
+        const int ci = t * C + i;
+        const int a = min(ci + hw, TW - 1), b = ci - hw - 1;         // (a is only clamped for halo threads: unused)
+        const int wa = a / WCOLS, wb = (b >= 0) ? b / WCOLS : 0;
+        sl_a[i] = 8u * ((a % C) * kFitThreads + a / C);
+        sl_b[i] = 8u * ((b >= 0) ? (b % C) * kFitThreads + b / C : ZERO);
+        sl_t0[i] = 8u * ((wa != wb) ? TW + 1 + wb : ZERO);
+    }
+    const unsigned sl_own = 8u * t, sl_tot = 8u * (TW + 1 + warp);   // this thread's store slots (column i: + i * threads)
 
     double V[C][NQ];
     int VN[C];
@@ -152,11 +220,13 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
         vring[i] = 0ull;
     }
 
-    auto load_row = [&](long y, float (&s)[C], float (&r)[C]) {
-        const float *srow = src + y * g.w, *rrow = ref + y * g.w;
+    const unsigned long long pol_keep = hb_policy_evict_last(), pol_drop = hb_policy_evict_first();
+    // `last_use`: the row is leaving the window (its final read) -- see the L2 note above
+    auto load_row = [&](long y, float (&s)[C], float (&r)[C], bool last_use) {
+        const float *srow = src + y * g.w + cx, *rrow = ref + y * g.w + cx;
         if (vec_ok) {
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(srow + cx));
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(rrow + cx));
+            const float4 a = hb_ldg16_hint(srow, last_use ? pol_drop : pol_keep);
+            const float4 b = hb_ldg16_hint(rrow, last_use ? pol_drop : pol_keep);
             s[0] = a.x; r[0] = b.x;
             if (C > 1) { s[1] = a.y; r[1] = b.y; }
             if (C > 2) { s[2] = a.z; r[2] = b.z; }
@@ -164,23 +234,47 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
         } else {
 #pragma unroll
             for (int i = 0; i < C; i++) {
-                s[i] = col_in[i] ? __ldg(srow + cx + i) : 0.f;
-                r[i] = col_in[i] ? __ldg(rrow + cx + i) : 0.f;
+                const bool in = (cmask >> i) & 1u;
+                s[i] = in ? __ldg(srow + i) : 0.f;
+                r[i] = in ? __ldg(rrow + i) : 0.f;
             }
         }
     };
 
     const bool single_row = (g.kh == 1), single_col = (g.kw == 1);
     const long e_first = y0 - hh, e_last = y1 - 1 + hh;
-    // the rows of step e + 1 are fetched (into registers) before step e is computed: their latency hides behind a
-    // whole row step instead of heading every step's dependency chain
-    float se[C], re[C], sl[C], rl[C], nse[C], nre[C], nsl[C], nrl[C];
+    float se[C], re[C], sl[C], rl[C];
 #pragma unroll
-    for (int i = 0; i < C; i++) { se[i] = re[i] = sl[i] = rl[i] = nse[i] = nre[i] = nsl[i] = nrl[i] = 0.f; }
-    auto fetch = [&](long e, float (&a)[C], float (&b)[C], float (&c)[C], float (&d)[C]) {
+    for (int i = 0; i < C; i++) { se[i] = re[i] = sl[i] = rl[i] = 0.f; }
+    auto fetch = [&](long e) {
         const long l = e - g.kh;
-        if ((e >= 0) && (e < g.h)) load_row(e, a, b);
-        if (!single_row && (l >= e_first) && (l >= 0) && (l < g.h)) load_row(l, c, d);
+        if ((e >= 0) && (e < g.h)) load_row(e, se, re, false);
+        if (!single_row && (l >= e_first) && (l >= 0) && (l < g.h)) load_row(l, sl, rl, true);
+    };
+    // Vertical update with one row's pixels; `rowmask` = cmask if the row exists, else 0 (rows outside the raster / before
+    // the band's first window contribute as invalid pixels: all-zero terms, so the update is free of branches; their
+    // registers hold stale values that the mask hides).  A LEAVING pixel's validity is the bit it shifted into the ring
+    // when it entered kh rows ago -- no second test -- as long as the ring (64 rows) reaches that far.
+    const bool ring_has_leaver = g.kh <= 63;
+    auto accumulate = [&](const float (&s)[C], const float (&r)[C], unsigned rowmask, bool entering) {
+#pragma unroll
+        for (int i = 0; i < C; i++) {
+            double q[NQ]; int cnt;
+            bool v;
+            if (entering || !ring_has_leaver) v = valid2(s[i], r[i], (rowmask >> i) & 1u);
+            else v = (((unsigned)(vring[i] >> g.kh)) & (rowmask >> i) & 1u) != 0u;
+            pixel_terms<NQ, NORM>(s[i], r[i], v, n0, n1, q, cnt);
+            if (entering) {
+#pragma unroll
+                for (int k = 0; k < NQ; k++) V[i][k] = __dadd_rn(V[i][k], q[k]);
+                VN[i] += cnt;
+                vring[i] = vring[i] + vring[i] + (unsigned long long)cnt;      // (ring << 1) | valid
+            } else {
+#pragma unroll
+                for (int k = 0; k < NQ; k++) V[i][k] = __dsub_rn(V[i][k], q[k]);
+                VN[i] -= cnt;
+            }
+        }
     };
     // ---- warm-up: the rows above the first output row's centre only ENTER the window (nothing leaves, no output row is
     //      completed).  Fetch them 4 at a time -- all loads in flight together -- and accumulate in row order (the same
@@ -195,134 +289,92 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
                 const long e = e_begin + u;
 #pragma unroll
                 for (int i = 0; i < C; i++) { ws[u][i] = 0.f; wr[u][i] = 0.f; }
-                if (e < e_warm_end && e >= 0 && e < g.h) load_row(e, ws[u], wr[u]);
+                if (e < e_warm_end && e >= 0 && e < g.h) load_row(e, ws[u], wr[u], false);
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const long e = e_begin + u;
                 if (e >= e_warm_end) break;
-                const bool has_e = (e >= 0) && (e < g.h);
-#pragma unroll
-                for (int i = 0; i < C; i++) {
-                    bool ve = false;
-                    if (has_e) {
-                        double q[NQ]; int cnt;
-                        ve = col_in[i] && valid2(ws[u][i], wr[u][i]);
-                        pixel_terms<NQ, NORM>(ws[u][i], wr[u][i], ve, n0, n1, q, cnt);
-                        ve = cnt != 0;
-#pragma unroll
-                        for (int k = 0; k < NQ; k++) V[i][k] = __dadd_rn(V[i][k], q[k]);
-                        VN[i] += cnt;
-                    }
-                    vring[i] = (vring[i] << 1) | (ve ? 1ull : 0ull);
-                }
+                accumulate(ws[u], wr[u], ((e >= 0) && (e < g.h)) ? cmask : 0u, true);
             }
         }
         e_begin = e_warm_end;
     }
-    fetch(e_begin, se, re, sl, rl);
+    fetch(e_begin);
+
+    // ---- row loop: vertical update with rows e (entering) and e - kh (leaving), which were fetched one step ago; the
+    //      rows of step e + 1 are requested as soon as those registers are free, so their latency hides behind the scan
+    //      and the solve
     for (long e = e_begin; e <= e_last; e++) {
-        // ---- vertical running sums: entering row e, leaving row e - kh ---------------------------------------------
+        const int bufoff = (int)(e & 1) * BUF_BYTES;                 // exchange buffer of this step (warp-uniform)
         const long l = e - g.kh;
         const bool has_e = (e >= 0) && (e < g.h);
         const bool has_l = !single_row && (l >= e_first) && (l >= 0) && (l < g.h);
-        if (e < e_last) fetch(e + 1, nse, nre, nsl, nrl);
+        if (single_row) {                                            // kh == 1: the window IS this row (exact)
 #pragma unroll
-        for (int i = 0; i < C; i++) {
-            bool ve = false;
-            if (has_e) {
-                double q[NQ]; int cnt;
-                ve = col_in[i] && valid2(se[i], re[i]);
-                pixel_terms<NQ, NORM>(se[i], re[i], ve, n0, n1, q, cnt);
-                ve = cnt != 0;
-                if (single_row) {                                    // kh == 1: the window IS this row (exact)
-#pragma unroll
-                    for (int k = 0; k < NQ; k++) V[i][k] = q[k];
-                    VN[i] = cnt;
-                } else {
-#pragma unroll
-                    for (int k = 0; k < NQ; k++) V[i][k] = __dadd_rn(V[i][k], q[k]);
-                    VN[i] += cnt;
-                }
-            } else if (single_row) {
+            for (int i = 0; i < C; i++) {
 #pragma unroll
                 for (int k = 0; k < NQ; k++) V[i][k] = 0.0;
                 VN[i] = 0;
             }
-            vring[i] = (vring[i] << 1) | (ve ? 1ull : 0ull);
-            if (has_l) {
-                double q[NQ]; int cnt;
-                const bool vl = col_in[i] && valid2(sl[i], rl[i]);
-                pixel_terms<NQ, NORM>(sl[i], rl[i], vl, n0, n1, q, cnt);
-#pragma unroll
-                for (int k = 0; k < NQ; k++) V[i][k] = __dsub_rn(V[i][k], q[k]);
-                VN[i] -= cnt;
-            }
         }
-#pragma unroll
-        for (int i = 0; i < C; i++) { se[i] = nse[i]; re[i] = nre[i]; sl[i] = nsl[i]; rl[i] = nrl[i]; }   // rotate
+        accumulate(se, re, has_e ? cmask : 0u, true);
+        accumulate(sl, rl, has_l ? cmask : 0u, false);
+        if (e < e_last) fetch(e + 1);
         const long y = e - hh;                                       // output row completed by this step
-        if (y < y0) continue;                                        // still filling the first window (uniform)
-        const int buf = (int)(y & 1);
 
         // ---- horizontal window sums: prefix over this thread's columns, warp scan of thread totals ----------------
         // (kw == 1: the window sum is the column sum itself -- exact, and no exchange is needed)
         if (!single_col) {
-        double pre[C][NQ];
-        int pren[C];
+            double pre[C][NQ], incl[NQ];
+            int pren[C], incl_n = 0;
 #pragma unroll
-        for (int k = 0; k < NQ; k++) {
-            double acc = 0.0;
+            for (int k = 0; k < NQ; k++) {
+                double acc = 0.0;
 #pragma unroll
-            for (int i = 0; i < C; i++) { acc += V[i][k]; pre[i][k] = acc; }
-        }
-        {
-            int acc = 0;
+                for (int i = 0; i < C; i++) { acc += V[i][k]; pre[i][k] = acc; }
+                incl[k] = acc;
+            }
+            if (HAS_N) {
+                int acc = 0;
 #pragma unroll
-            for (int i = 0; i < C; i++) { acc += VN[i]; pren[i] = acc; }
-        }
-        double excl[NQ];
-        int excl_n = 0;
-#pragma unroll
-        for (int k = 0; k < NQ; k++) {
-            double incl = pre[C - 1][k];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) incl = scan_step(incl, d);
-            excl[k] = incl - pre[C - 1][k];
-            if (lane == 31) s_tot[buf][k][warp] = incl;
-        }
-        if (HAS_N) {
-            int incl = pren[C - 1];
+                for (int i = 0; i < C; i++) { acc += VN[i]; pren[i] = acc; }
+                incl_n = acc;
+            }
+            // the scans of all sums advance together: NQ + 1 independent shuffle / add chains per step
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const int up = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += up;
+                double up[NQ];
+                int up_n = 0;
+#pragma unroll
+                for (int k = 0; k < NQ; k++) up[k] = __shfl_up_sync(0xffffffffu, incl[k], d);
+                if (HAS_N) up_n = __shfl_up_sync(0xffffffffu, incl_n, d);
+                if (lane >= d) {
+#pragma unroll
+                    for (int k = 0; k < NQ; k++) incl[k] += up[k];
+                    if (HAS_N) incl_n += up_n;
+                }
             }
-            excl_n = incl - pren[C - 1];
-            if (lane == 31) s_ntot[buf][warp] = incl;
-        }
 #pragma unroll
-        for (int i = 0; i < C; i++) {
+            for (int k = 0; k < NQ; k++) {
+                const double excl = incl[k] - pre[C - 1][k];
+                if (lane == 31) q_at(bufoff, k, sl_tot) = incl[k];
 #pragma unroll
-            for (int k = 0; k < NQ; k++) s_q[buf][k][i * kFitThreads + t] = excl[k] + pre[i][k];
-            if (HAS_N) s_n[buf][i * kFitThreads + t] = excl_n + pren[i];
-        }
-        __syncthreads();        // (double-buffered: the next row writes the other buffer, so one barrier per row)
+                for (int i = 0; i < C; i++) q_at(bufoff, k, sl_own + i * (kFitThreads * 8)) = excl + pre[i][k];
+            }
+            if (HAS_N) {
+                const int excl_n = incl_n - pren[C - 1];
+                if (lane == 31) n_at(bufoff, sl_tot) = incl_n;
+#pragma unroll
+                for (int i = 0; i < C; i++) n_at(bufoff, sl_own + i * (kFitThreads * 8)) = excl_n + pren[i];
+            }
+            __syncthreads();        // (double-buffered: the next row writes the other buffer, so one barrier per row)
         }
 
         if (!out_thread) continue;
         float o_gain[C], o_off[C], o_r2[C], o_rs[C], o_ss[C], o_n[C];
 #pragma unroll
         for (int i = 0; i < C; i++) {
-            const int ci = t * C + i;
-            const int a = ci + hw, b = ci - hw - 1;
-            // column c is stored at slot (c % C) * threads + c / C (conflict-free for both the stores and these loads);
-            // the window spans at most two warps (kw <= 129 <= columns per warp + 1): one conditional total
-            const int wa = a / WCOLS, wb = (b >= 0) ? b / WCOLS : 0;
-            const int sa = (a % C) * kFitThreads + a / C;
-            const int sb = (b >= 0) ? (b % C) * kFitThreads + b / C : 0;
-            const bool cross = (wa != wb);
-            const bool cross2 = (wa - wb) > 1;                        // only when kw > columns per warp
             double W[NQ];
             int N = 0;
             if (single_col) {
@@ -331,21 +383,9 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
                 N = VN[i];
             } else {
 #pragma unroll
-                // (all loads unconditional, corrections selected: no divergent branches in the row loop)
-                const int wb1 = min(wb + 1, kFitWarps - 1);
-                for (int k = 0; k < NQ; k++) {
-                    const double qa = s_q[buf][k][sa], qb = s_q[buf][k][sb];
-                    const double t0 = s_tot[buf][k][wb], t1 = s_tot[buf][k][wb1];
-                    double v = qa + (cross ? t0 : -0.0);     // (x + -0.0 == x and x - 0.0 == x for every x, signed zeros too)
-                    v += cross2 ? t1 : -0.0;
-                    v -= (b >= 0) ? qb : 0.0;
-                    W[k] = v;
-                }
-                if (HAS_N) {
-                    int v = s_n[buf][sa] + (cross ? s_ntot[buf][wb] : 0) + (cross2 ? s_ntot[buf][wb1] : 0);
-                    v -= (b >= 0) ? s_n[buf][sb] : 0;
-                    N = v;
-                }
+                for (int k = 0; k < NQ; k++)
+                    W[k] = (q_at(bufoff, k, sl_a[i]) + q_at(bufoff, k, sl_t0[i])) - q_at(bufoff, k, sl_b[i]);
+                if (HAS_N) N = (n_at(bufoff, sl_a[i]) + n_at(bufoff, sl_t0[i])) - n_at(bufoff, sl_b[i]);
             }
             const bool mask = ((vring[i] >> hh) & 1ull) != 0ull;     // centre pixel valid in both images
 
@@ -405,57 +445,60 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
             o_rs[i] = fR; o_ss[i] = fS; o_n[i] = mask ? fN : -1.f;   // count plane: -1 marks "outside the mask"
         }
         // ---- store -------------------------------------------------------------------------------------------------
-        if (corr_out != nullptr) {
+        const long yo = y - g.row0;                                  // row of the output planes
+        if (FUSED) {
             // fused apply (KernelModel.apply, kernel_model.py:461): corr = gain * src + offset with the centre row's
             // ORIGINAL source pixels (re-read: they entered the window kh/2 rows ago, an L2 hit), two float32
             // roundings as numpy; the parameters are not materialised
-            float sc[C], rdummy[C];
-            load_row(y, sc, rdummy);
+            float sc[C];
+            const float *srow = src + y * g.w + cx;
+            if (vec_ok) {
+                const float4 a = hb_ldg16_hint(srow, pol_keep);
+                sc[0] = a.x;
+                if (C > 1) sc[1] = a.y;
+                if (C > 2) sc[2] = a.z;
+                if (C > 3) sc[3] = a.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < C; i++) sc[i] = ((cmask >> i) & 1u) ? __ldg(srow + i) : 0.f;
+            }
             float oc[C];
 #pragma unroll
             for (int i = 0; i < C; i++) oc[i] = __fadd_rn(__fmul_rn(o_gain[i], sc[i]), o_off[i]);
-            float *crow = corr_out + y * g.w;
-            if (vec_ok && C == 4) {
-                *reinterpret_cast<float4 *>(crow + cx) = make_float4(oc[0], oc[C > 1 ? 1 : 0], oc[C > 2 ? 2 : 0], oc[C > 3 ? 3 : 0]);
+            float *crow = corr_out + yo * g.w + cx;
+            if (vec_ok) {
+                hb_stg16_stream(crow, make_float4(oc[0], oc[C > 1 ? 1 : 0], oc[C > 2 ? 2 : 0], oc[C > 3 ? 3 : 0]));
             } else {
 #pragma unroll
                 for (int i = 0; i < C; i++)
-                    if (col_in[i]) crow[cx + i] = oc[i];
-            }
-            continue;
-        }
-        float *prow = params + y * g.w;
-        if (vec_ok) {
-            if (C == 4) {
-                *reinterpret_cast<float4 *>(prow + cx) = make_float4(o_gain[0], o_gain[C > 1 ? 1 : 0],
-                                                                     o_gain[C > 2 ? 2 : 0], o_gain[C > 3 ? 3 : 0]);
-                *reinterpret_cast<float4 *>(prow + plane + cx) = make_float4(o_off[0], o_off[C > 1 ? 1 : 0],
-                                                                             o_off[C > 2 ? 2 : 0], o_off[C > 3 ? 3 : 0]);
-                if (WANT_R2)
-                    *reinterpret_cast<float4 *>(prow + 2 * plane + cx) =
-                        make_float4(o_r2[0], o_r2[C > 1 ? 1 : 0], o_r2[C > 2 ? 2 : 0], o_r2[C > 3 ? 3 : 0]);
-                if (sums_out != nullptr) {
-                    float *srow = sums_out + y * g.w;
-                    *reinterpret_cast<float4 *>(srow + cx) =
-                        make_float4(o_rs[0], o_rs[C > 1 ? 1 : 0], o_rs[C > 2 ? 2 : 0], o_rs[C > 3 ? 3 : 0]);
-                    *reinterpret_cast<float4 *>(srow + plane + cx) =
-                        make_float4(o_ss[0], o_ss[C > 1 ? 1 : 0], o_ss[C > 2 ? 2 : 0], o_ss[C > 3 ? 3 : 0]);
-                    *reinterpret_cast<float4 *>(srow + 2 * plane + cx) =
-                        make_float4(o_n[0], o_n[C > 1 ? 1 : 0], o_n[C > 2 ? 2 : 0], o_n[C > 3 ? 3 : 0]);
-                }
+                    if ((cmask >> i) & 1u) crow[i] = oc[i];
             }
         } else {
-#pragma unroll
-            for (int i = 0; i < C; i++) {
-                if (!col_in[i]) continue;
-                prow[cx + i] = o_gain[i];
-                prow[plane + cx + i] = o_off[i];
-                if (WANT_R2) prow[2 * plane + cx + i] = o_r2[i];
+            float *prow = params + yo * g.w + cx;
+            if (vec_ok) {
+                hb_stg16_stream(prow, make_float4(o_gain[0], o_gain[C > 1 ? 1 : 0], o_gain[C > 2 ? 2 : 0], o_gain[C > 3 ? 3 : 0]));
+                hb_stg16_stream(prow + plane, make_float4(o_off[0], o_off[C > 1 ? 1 : 0], o_off[C > 2 ? 2 : 0], o_off[C > 3 ? 3 : 0]));
+                if (WANT_R2)
+                    hb_stg16_stream(prow + 2 * plane, make_float4(o_r2[0], o_r2[C > 1 ? 1 : 0], o_r2[C > 2 ? 2 : 0], o_r2[C > 3 ? 3 : 0]));
                 if (sums_out != nullptr) {
-                    float *srow = sums_out + y * g.w;
-                    srow[cx + i] = o_rs[i];
-                    srow[plane + cx + i] = o_ss[i];
-                    srow[2 * plane + cx + i] = o_n[i];
+                    float *srow = sums_out + yo * g.w + cx;
+                    hb_stg16_stream(srow, make_float4(o_rs[0], o_rs[C > 1 ? 1 : 0], o_rs[C > 2 ? 2 : 0], o_rs[C > 3 ? 3 : 0]));
+                    hb_stg16_stream(srow + plane, make_float4(o_ss[0], o_ss[C > 1 ? 1 : 0], o_ss[C > 2 ? 2 : 0], o_ss[C > 3 ? 3 : 0]));
+                    hb_stg16_stream(srow + 2 * plane, make_float4(o_n[0], o_n[C > 1 ? 1 : 0], o_n[C > 2 ? 2 : 0], o_n[C > 3 ? 3 : 0]));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < C; i++) {
+                    if (!((cmask >> i) & 1u)) continue;
+                    prow[i] = o_gain[i];
+                    prow[plane + i] = o_off[i];
+                    if (WANT_R2) prow[2 * plane + i] = o_r2[i];
+                    if (sums_out != nullptr) {
+                        float *srow = sums_out + yo * g.w + cx;
+                        srow[i] = o_rs[i];
+                        srow[plane + i] = o_ss[i];
+                        srow[2 * plane + i] = o_n[i];
+                    }
                 }
             }
         }
@@ -463,14 +506,16 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
 }
 
 template <int MODEL, bool WANT_R2, int NQ, int C>
-int launch_fit(const float *src, NoData nd_s, const float *ref, NoData nd_r, long h, long w, int kh, int kw,
-               const double *norm, float *params, float *sums, float *corr, cudaStream_t stream)
+int launch_fit(const float *src, NoData nd_s, const float *ref, NoData nd_r, long h, long w, long row0, long nrows,
+               int kh, int kw, const double *norm, float *params, float *sums, float *corr, cudaStream_t stream)
 {
     FitGeom g;
-    g.h = h; g.w = w; g.kh = kh; g.kw = kw;
+    g.h = h; g.w = w; g.kh = kh; g.kw = kw; g.row0 = row0; g.nrows = nrows;
     const int hw = kw / 2;
     g.hw_al = ((hw + C - 1) / C) * C;
     g.tw_out = kFitThreads * C - 2 * g.hw_al;
+    HB_REQUIRE(g.tw_out > 0 && kw <= 32 * C, "hb_fit_same_grid: kernel width %d is too wide for this variant", kw);
+    HB_REQUIRE(w < (1L << 30), "hb_fit_same_grid: rasters wider than 2^30 pixels are not supported");
     const long xtiles = (w + g.tw_out - 1) / g.tw_out;
     // rows per band: every band re-reads (kh - 1) warm-up rows, so bands should be tall -- ~8 window heights -- unless
     // that leaves SMs idle (mid-size rasters: go down to 2 window heights to get one CTA per resident slot).  Small
@@ -479,7 +524,7 @@ int launch_fit(const float *src, NoData nd_s, const float *ref, NoData nd_r, lon
     long rpb;
     if (C == 1) {
         const long bands_t = ((long)hb_sm_count() * 8 + xtiles - 1) / xtiles;
-        rpb = (h + bands_t - 1) / bands_t;
+        rpb = (nrows + bands_t - 1) / bands_t;
         if (rpb < 4) rpb = 4;
     } else {
         // score = (fraction of the last wave of resident CTAs that is filled) x (fraction of row fetches that are not
@@ -487,78 +532,89 @@ int launch_fit(const float *src, NoData nd_s, const float *ref, NoData nd_r, lon
         double best = -1.0;
         rpb = 8L * kh;
         for (long cand = 16L * kh; cand >= 2L * kh; cand -= (kh + 1) / 2) {
-            const long c = cand > h ? h : cand;
-            const long ctas = xtiles * ((h + c - 1) / c);
+            const long c = cand > nrows ? nrows : cand;
+            const long ctas = xtiles * ((nrows + c - 1) / c);
             const long waves = (ctas + slots - 1) / slots;
             const double score = ((double)ctas / (double)(waves * slots)) * ((double)c / (double)(c + kh - 1));
             if (score > best) { best = score; rpb = c; }
         }
     }
-    if (rpb > h) rpb = h;
+    if (rpb > nrows) rpb = nrows;
     long bands;
     g.rows_per_band = (int)rpb;
-    bands = (h + rpb - 1) / rpb;
+    bands = (nrows + rpb - 1) / rpb;
     HB_REQUIRE(bands <= 65535, "hb_fit_same_grid: too many row bands");
     dim3 grid((unsigned)xtiles, (unsigned)bands);
-    const bool aligned = (C == 4) && (w % 4 == 0) && (((uintptr_t)src) % 16 == 0) && (((uintptr_t)ref) % 16 == 0) &&
-                         (((uintptr_t)params) % 16 == 0) && (sums == nullptr || ((uintptr_t)sums) % 16 == 0) &&
-                         (corr == nullptr || ((uintptr_t)corr) % 16 == 0);
-    if (aligned)
-        fit_same_grid_kernel<MODEL, WANT_R2, NQ, C, true><<<grid, kFitThreads, 0, stream>>>(src, nd_s, ref, nd_r, g,
-                                                                                           norm, params, sums, corr);
-    else
+    g.aligned = ((C == 4) && (w % 4 == 0) && (((uintptr_t)src) % 16 == 0) && (((uintptr_t)ref) % 16 == 0) &&
+                 (params == nullptr || ((uintptr_t)params) % 16 == 0) &&
+                 (sums == nullptr || ((uintptr_t)sums) % 16 == 0) &&
+                 (corr == nullptr || ((uintptr_t)corr) % 16 == 0)) ? 1 : 0;
+    if (corr != nullptr) {
+        if constexpr (!WANT_R2)
+            fit_same_grid_kernel<MODEL, false, NQ, C, true><<<grid, kFitThreads, 0, stream>>>(src, nd_s, ref, nd_r, g, norm,
+                                                                                             nullptr, nullptr, corr);
+        else
+            HB_REQUIRE(false, "hb_fit_apply_same_grid: the fused apply does not produce an R2 band");
+    } else {
         fit_same_grid_kernel<MODEL, WANT_R2, NQ, C, false><<<grid, kFitThreads, 0, stream>>>(src, nd_s, ref, nd_r, g,
-                                                                                            norm, params, sums, corr);
+                                                                                            norm, params, sums, nullptr);
+    }
     HB_LAUNCH_OK("fit_same_grid_kernel");
     return 0;
 }
 
 template <int MODEL, bool WANT_R2, int NQ>
-int launch_fit_c(const float *src, NoData nd_s, const float *ref, NoData nd_r, long h, long w, int kh, int kw,
-                 const double *norm, float *params, float *sums, float *corr, cudaStream_t stream)
+int launch_fit_c(const float *src, NoData nd_s, const float *ref, NoData nd_r, long h, long w, long row0, long nrows,
+                 int kh, int kw, const double *norm, float *params, float *sums, float *corr, cudaStream_t stream)
 {
-    // small rasters: 1 column per thread (128-column strips) so that the grid still spreads over the SMs
-    if (h * w < (long)4 << 20)
-        return launch_fit<MODEL, WANT_R2, NQ, 1>(src, nd_s, ref, nd_r, h, w, kh, kw, norm, params, sums, corr, stream);
-    return launch_fit<MODEL, WANT_R2, NQ, 4>(src, nd_s, ref, nd_r, h, w, kh, kw, norm, params, sums, corr, stream);
+    // small rasters: 1 column per thread (128-column strips) so that the grid still spreads over the SMs.  A window
+    // may span at most two warps (one warp total in the look-up): 32-column warps carry kernels up to 31 wide,
+    // 128-column warps up to 127.
+    if (nrows * w < ((long)4 << 20) && kw <= 31)
+        return launch_fit<MODEL, WANT_R2, NQ, 1>(src, nd_s, ref, nd_r, h, w, row0, nrows, kh, kw, norm, params, sums,
+                                                 corr, stream);
+    return launch_fit<MODEL, WANT_R2, NQ, 4>(src, nd_s, ref, nd_r, h, w, row0, nrows, kh, kw, norm, params, sums, corr,
+                                             stream);
 }
 
 }  // namespace
 
 static int fit_dispatch(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
-                        int ref_has_nodata, double ref_nodata, long h, long w, int model, int kh, int kw, int want_r2,
-                        const double *norm_dev, float *params_dev, float *sums_dev, float *corr_dev, void *stream,
-                        const char *who)
+                        int ref_has_nodata, double ref_nodata, long h, long w, long row0, long nrows, int model, int kh,
+                        int kw, int want_r2, const double *norm_dev, float *params_dev, float *sums_dev, float *corr_dev,
+                        void *stream, const char *who)
 {
     HB_REQUIRE(src_dev && ref_dev && (params_dev || corr_dev) && h > 0 && w > 0, "%s: bad arguments", who);
+    HB_REQUIRE(row0 >= 0 && nrows > 0 && row0 + nrows <= h, "%s: output rows [%ld, %ld) outside the %ld-row plane", who,
+               row0, row0 + nrows, h);
     HB_REQUIRE(kh >= 1 && kw >= 1 && (kh & 1) && (kw & 1), "%s: kernel shape must be odd and >= 1", who);
     HB_REQUIRE(kw / 2 <= kMaxHalfW, "%s: kernel width %d > %d is not supported", who, kw, 2 * kMaxHalfW + 1);
     HB_REQUIRE(kh / 2 <= 63, "%s: kernel height %d > 127 is not supported", who, kh);
     const NoData nd_s = hb_make_nodata(src_has_nodata, src_nodata), nd_r = hb_make_nodata(ref_has_nodata, ref_nodata);
     cudaStream_t st = (cudaStream_t)stream;
+#define HB_FIT_ARGS src_dev, nd_s, ref_dev, nd_r, h, w, row0, nrows, kh, kw
     switch (model) {
         case HB_MODEL_GAIN:
             HB_REQUIRE(sums_dev == nullptr, "%s: sums are only produced for the gain-offset model", who);
             if (want_r2)
-                return launch_fit_c<HB_MODEL_GAIN, true, 5>(src_dev, nd_s, ref_dev, nd_r, h, w, kh, kw, nullptr,
-                                                            params_dev, nullptr, corr_dev, st);
-            return launch_fit_c<HB_MODEL_GAIN, false, 2>(src_dev, nd_s, ref_dev, nd_r, h, w, kh, kw, nullptr,
-                                                         params_dev, nullptr, corr_dev, st);
+                return launch_fit_c<HB_MODEL_GAIN, true, 5>(HB_FIT_ARGS, nullptr, params_dev, nullptr, corr_dev, st);
+            return launch_fit_c<HB_MODEL_GAIN, false, 2>(HB_FIT_ARGS, nullptr, params_dev, nullptr, corr_dev, st);
         case HB_MODEL_GAIN_BLK_OFFSET:
             HB_REQUIRE(norm_dev != nullptr, "%s: gain-blk-offset needs the block normalisation", who);
             HB_REQUIRE(sums_dev == nullptr, "%s: sums are only produced for the gain-offset model", who);
             if (want_r2)
-                return launch_fit_c<HB_MODEL_GAIN_BLK_OFFSET, true, 5>(src_dev, nd_s, ref_dev, nd_r, h, w, kh, kw,
-                                                                       norm_dev, params_dev, nullptr, corr_dev, st);
-            return launch_fit_c<HB_MODEL_GAIN_BLK_OFFSET, false, 2>(src_dev, nd_s, ref_dev, nd_r, h, w, kh, kw,
-                                                                    norm_dev, params_dev, nullptr, corr_dev, st);
+                return launch_fit_c<HB_MODEL_GAIN_BLK_OFFSET, true, 5>(HB_FIT_ARGS, norm_dev, params_dev, nullptr,
+                                                                       corr_dev, st);
+            return launch_fit_c<HB_MODEL_GAIN_BLK_OFFSET, false, 2>(HB_FIT_ARGS, norm_dev, params_dev, nullptr,
+                                                                    corr_dev, st);
         case HB_MODEL_GAIN_OFFSET:
             if (want_r2)
-                return launch_fit_c<HB_MODEL_GAIN_OFFSET, true, 5>(src_dev, nd_s, ref_dev, nd_r, h, w, kh, kw, nullptr,
-                                                                   params_dev, sums_dev, corr_dev, st);
-            return launch_fit_c<HB_MODEL_GAIN_OFFSET, false, 4>(src_dev, nd_s, ref_dev, nd_r, h, w, kh, kw, nullptr,
-                                                                params_dev, sums_dev, corr_dev, st);
+                return launch_fit_c<HB_MODEL_GAIN_OFFSET, true, 5>(HB_FIT_ARGS, nullptr, params_dev, sums_dev, corr_dev,
+                                                                   st);
+            return launch_fit_c<HB_MODEL_GAIN_OFFSET, false, 4>(HB_FIT_ARGS, nullptr, params_dev, sums_dev, corr_dev,
+                                                                st);
     }
+#undef HB_FIT_ARGS
     HB_REQUIRE(false, "%s: unknown model %d", who, model);
 }
 
@@ -567,8 +623,19 @@ extern "C" int hb_fit_same_grid(const float *src_dev, int src_has_nodata, double
                                 int want_r2, const double *norm_dev, float *params_dev, float *sums_dev, void *stream)
 {
     HB_REQUIRE(params_dev != nullptr, "hb_fit_same_grid: bad arguments");
-    return fit_dispatch(src_dev, src_has_nodata, src_nodata, ref_dev, ref_has_nodata, ref_nodata, h, w, model, kh, kw,
-                        want_r2, norm_dev, params_dev, sums_dev, nullptr, stream, "hb_fit_same_grid");
+    return fit_dispatch(src_dev, src_has_nodata, src_nodata, ref_dev, ref_has_nodata, ref_nodata, h, w, 0, h, model, kh,
+                        kw, want_r2, norm_dev, params_dev, sums_dev, nullptr, stream, "hb_fit_same_grid");
+}
+
+extern "C" int hb_fit_same_grid_rows(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
+                                     int ref_has_nodata, double ref_nodata, long h, long w, long row0, long nrows,
+                                     int model, int kh, int kw, int want_r2, const double *norm_dev, float *params_dev,
+                                     float *sums_dev, void *stream)
+{
+    HB_REQUIRE(params_dev != nullptr, "hb_fit_same_grid_rows: bad arguments");
+    return fit_dispatch(src_dev, src_has_nodata, src_nodata, ref_dev, ref_has_nodata, ref_nodata, h, w, row0, nrows,
+                        model, kh, kw, want_r2, norm_dev, params_dev, sums_dev, nullptr, stream,
+                        "hb_fit_same_grid_rows");
 }
 
 extern "C" int hb_fit_apply_same_grid(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
@@ -576,6 +643,16 @@ extern "C" int hb_fit_apply_same_grid(const float *src_dev, int src_has_nodata, 
                                       const double *norm_dev, float *corr_dev, void *stream)
 {
     HB_REQUIRE(corr_dev != nullptr, "hb_fit_apply_same_grid: bad arguments");
-    return fit_dispatch(src_dev, src_has_nodata, src_nodata, ref_dev, ref_has_nodata, ref_nodata, h, w, model, kh, kw, 0,
-                        norm_dev, nullptr, nullptr, corr_dev, stream, "hb_fit_apply_same_grid");
+    return fit_dispatch(src_dev, src_has_nodata, src_nodata, ref_dev, ref_has_nodata, ref_nodata, h, w, 0, h, model, kh,
+                        kw, 0, norm_dev, nullptr, nullptr, corr_dev, stream, "hb_fit_apply_same_grid");
+}
+
+extern "C" int hb_fit_apply_same_grid_rows(const float *src_dev, int src_has_nodata, double src_nodata,
+                                           const float *ref_dev, int ref_has_nodata, double ref_nodata, long h, long w,
+                                           long row0, long nrows, int model, int kh, int kw, const double *norm_dev,
+                                           float *corr_dev, void *stream)
+{
+    HB_REQUIRE(corr_dev != nullptr, "hb_fit_apply_same_grid_rows: bad arguments");
+    return fit_dispatch(src_dev, src_has_nodata, src_nodata, ref_dev, ref_has_nodata, ref_nodata, h, w, row0, nrows,
+                        model, kh, kw, 0, norm_dev, nullptr, nullptr, corr_dev, stream, "hb_fit_apply_same_grid_rows");
 }

@@ -7,18 +7,24 @@ pixels (utils.py:136-153).  Two regimes follow:
 
 * **Batch / mosaic** (`shard_sources`): independent source images are dealt round-robin to the ranks; the reference
   image is replicated.  No data-path collective at all.
-* **One raster as row bands** (`RowBands`, `fuse_refspace_sharded`, `fit_same_grid_sharded`): rank g owns a band of
-  source rows whose edges coincide with proc-grid (reference) pixel rows.
+* **One raster as row bands** (`RowBands`, `fuse_refspace_sharded`, `fit_apply_same_grid_sharded`): rank g owns a band
+  of source rows whose edges coincide with proc-grid (reference) pixel rows.  Two things cross the interconnect:
 
-  - proc_crs = ref: every rank down-samples its own source rows, the proc-grid planes (3000 x 3000 float32 = 36 MB for
-    the 60k x 60k configuration -- 1/400 of the source) are **all-gathered** so that the block normalisation of
-    gain-blk-offset (a whole-block statistic, kernel_model.py:216-229) stays global; every rank then fits its own proc
-    rows plus a halo (`halo_rows`) and applies the parameters to its own source rows.  Results equal the single-GPU
-    results up to the summation order of the fit kernel's running sums (> 99.9 % of the parameters bit-identical).
-  - same grid (proc_crs = src): the window sums need ``kh // 2`` rows of source and reference from each neighbour:
-    `exchange_halos` does that with point-to-point send / recv between row-band neighbours (NCCL P2P over NVLink on
-    GPUs, gloo in the CPU tests); rows beyond the raster stay absent, which is the reference's zero padding
-    (cv BORDER_CONSTANT).  The fit then runs on the extended band and the halo rows of the result are dropped.
+  - **halo rows** (`exchange_halos`, `exchange_halos_inplace`): ``kh // 2`` proc-grid rows from each neighbour for the
+    window sums (+ 2 for the cubic-spline taps when proc_crs = ref, + 100 with R2 in-painting: `halo_rows`), sent point
+    to point between row-band neighbours (NCCL P2P over NVLink on GPUs, gloo in the CPU tests).  Rows beyond the
+    raster stay absent, which is the reference's zero padding (cv BORDER_CONSTANT).  proc_crs = ref exchanges rows of
+    the DOWN-SAMPLED source (9 x 3000 float32 = 108 KB per neighbour and band for the 60k x 60k configuration); the
+    same-grid path exchanges ``kh // 2`` rows of source and reference, received straight into the halo rows of
+    pre-allocated planes (no copy of the band itself).
+  - **block statistics** of gain-blk-offset (`block_norm_sharded`): ``_fit_block_norm`` (kernel_model.py:216-229) is a
+    statistic of the WHOLE block, so its three streaming passes (counts + sums + 12-bit key histograms; squared
+    deviations + next 12 bits; last 8 bits) run on each rank's own rows and every pass ends in one all-gather of the
+    131 KB of accumulators, summed in rank order by every rank (bit-identical statistics everywhere).  No rank ever
+    reads another rank's pixels.
+
+  Results equal the single-GPU results up to the summation order of the fit kernel's running sums and of the block
+  sums (> 99.9 % of the parameters bit-identical).
 
 All timing of multi-GPU runs is done by the caller on the device (bench.py: CUDA events, max over ranks).
 """
@@ -29,6 +35,33 @@ import torch.distributed as dist
 
 from homonim_b200.geometry import Affine
 from homonim_b200.raster_array import RasterArray
+
+
+def _host_staged(t: torch.Tensor, group=None) -> bool:
+    """ CUDA tensors over a back end without device support (gloo: several ranks sharing one GPU in the tests, or a box
+    without NVLink / NCCL): the payload is staged through host memory.  NCCL moves device memory directly. """
+    return t.is_cuda and dist.get_backend(group) != 'nccl'
+
+
+def _run_p2p(sends, recvs, group=None) -> None:
+    """ One batch of point-to-point transfers: ``sends`` / ``recvs`` are lists of ``(tensor view, peer)``; received rows
+    land in the views. """
+    if not sends and not recvs:
+        return
+    probe = (sends or recvs)[0][0]
+    staged = _host_staged(probe, group)
+    ops, landed = [], []
+    for t, peer in sends:
+        ops.append(dist.P2POp(dist.isend, t.cpu().contiguous() if staged else t, peer, group))
+    for t, peer in recvs:
+        buf = torch.empty(t.shape, dtype=t.dtype) if staged else t
+        landed.append((t, buf))
+        ops.append(dist.P2POp(dist.irecv, buf, peer, group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    if staged:
+        for t, buf in landed:
+            t.copy_(buf)
 
 
 def shard_sources(n_sources: int, rank: int, world_size: int) -> List[int]:
@@ -86,7 +119,7 @@ def exchange_halos(local: torch.Tensor, bands: RowBands, halo: int, group=None) 
     lo, hi = bands.with_halo(rank, halo)
     if world == 1 or halo == 0:
         return local, 0
-    ops, recv_bufs = [], []
+    sends, recvs, recv_bufs = [], [], []
     lead = local.shape[:-2]
     width = local.shape[-1]
     for peer in range(world):
@@ -97,17 +130,14 @@ def exchange_halos(local: torch.Tensor, bands: RowBands, halo: int, group=None) 
         # rows of mine that the peer needs
         s0, s1 = max(a, plo), min(b, phi)
         if s1 > s0:
-            chunk = local[..., s0 - a:s1 - a, :].contiguous()
-            ops.append(dist.P2POp(dist.isend, chunk, peer, group))
+            sends.append((local[..., s0 - a:s1 - a, :].contiguous(), peer))
         # rows of the peer that I need
         r0, r1 = max(pa, lo), min(pb, hi)
         if r1 > r0:
             buf = torch.empty(lead + (r1 - r0, width), dtype=local.dtype, device=local.device)
             recv_bufs.append((r0, buf))
-            ops.append(dist.P2POp(dist.irecv, buf, peer, group))
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
+            recvs.append((buf, peer))
+    _run_p2p(sends, recvs, group)
     pieces = sorted(recv_bufs + [(a, local)], key=lambda t: t[0])
     extended = torch.cat([p for _, p in pieces], dim=-2) if len(pieces) > 1 else local
     return extended, a - lo
@@ -122,8 +152,13 @@ def all_gather_rows(local: torch.Tensor, bands: RowBands, group=None) -> torch.T
     max_rows = max(bands.size(g) for g in range(world))
     padded = torch.zeros(lead + (max_rows, width), dtype=local.dtype, device=local.device)
     padded[..., :local.shape[-2], :] = local
-    gathered = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(gathered, padded, group=group)
+    if _host_staged(padded, group):
+        parts = [torch.empty(padded.shape, dtype=padded.dtype) for _ in range(world)]
+        dist.all_gather(parts, padded.cpu(), group=group)
+        gathered = [g.to(local.device) for g in parts]
+    else:
+        gathered = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(gathered, padded, group=group)
     return torch.cat([gathered[g][..., :bands.size(g), :] for g in range(world)], dim=-2)
 
 
@@ -144,10 +179,10 @@ def source_band_for_proc_rows(src_ra_shape: Tuple[int, int], src_transform: Affi
 def fit_row_window(bands: RowBands, rank: int, halo: int) -> Tuple[int, int, int, int]:
     """
     Proc-grid rows of the sharded proc_crs = ref path for ``rank``: ``(lo, hi, plo, phi)``.  ``[lo, hi)`` are the rows the
-    rank fits (its band extended by ``halo`` rows, clipped to the raster); ``[plo, phi)`` are the rows of that fit it keeps
-    and hands to the up-sampler (its band plus the 2 rows of cubic-spline support on either side, clipped).  Every kept
-    row is at least ``halo - 2`` rows away from a cut edge of the fitted window -- the distance over which window sums
-    (and the in-painting search) are affected by the cut -- unless that edge is the raster's own.
+    rank holds for the fit (its band extended by ``halo`` rows, clipped to the raster); ``[plo, phi)`` are the rows whose
+    parameters it needs for the up-sampler (its band plus the 2 rows of cubic-spline support on either side, clipped).
+    Every kept row is at least ``halo - 2`` rows away from a cut edge of the held window -- the distance over which
+    window sums (and the in-painting search) are affected by the cut -- unless that edge is the raster's own.
     """
     a, b = bands.band(rank)
     hp = bands.starts[-1]
@@ -156,21 +191,133 @@ def fit_row_window(bands: RowBands, rank: int, halo: int) -> Tuple[int, int, int
     return lo, hi, plo, phi
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# whole-block statistics of a sharded block
+# ---------------------------------------------------------------------------------------------------------------------
+def _all_gather_bytes(local: torch.Tensor, group=None) -> torch.Tensor:
+    """ ``[world * n]`` uint8 tensor holding every rank's ``[n]`` uint8 tensor, in rank order. """
+    world = dist.get_world_size(group)
+    if _host_staged(local, group):
+        parts = [torch.empty(local.shape, dtype=local.dtype) for _ in range(world)]
+        dist.all_gather(parts, local.cpu(), group=group)
+        return torch.cat(parts).to(local.device)
+    out = torch.empty(world * local.numel(), dtype=local.dtype, device=local.device)
+    try:
+        dist.all_gather_into_tensor(out, local, group=group)
+    except (RuntimeError, NotImplementedError):          # back ends without the flat variant
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local, group=group)
+        out = torch.cat(parts)
+    return out
+
+
+class NativeBlockNorm:
+    """ The three accumulate / merge passes of ``hb_block_norm_partial`` / ``hb_block_norm_merge`` on device planes. """
+
+    def __init__(self, src_local: torch.Tensor, src_nodata, ref_local: torch.Tensor, ref_nodata):
+        from homonim_b200 import _native
+        from homonim_b200 import kernel_model as km
+        self._km, self._lib = km, _native.lib()
+        if src_local.dtype != torch.float32 or ref_local.dtype != torch.float32:
+            raise ValueError('block statistics are taken on float32 planes')
+        if not (src_local.is_contiguous() and ref_local.is_contiguous()):
+            raise ValueError('block statistics need contiguous planes (row ranges of a plane are fine)')
+        self.src, self.ref = src_local, ref_local
+        self.n = int(src_local.numel())
+        self.s_nd, self.r_nd = km._nodata_args(src_nodata), km._nodata_args(ref_nodata)
+        self.ws_bytes = int(self._lib.hb_block_norm_workspace_bytes(max(self.n, 1)))
+        self.accum_bytes = int(self._lib.hb_block_norm_accum_bytes())
+        self.work = torch.empty(self.ws_bytes, dtype=torch.uint8, device=src_local.device)
+        self.norm = torch.empty(2, dtype=torch.float64, device=src_local.device)
+
+    def partial(self, level: int) -> torch.Tensor:
+        km = self._km
+        km._call('hb_block_norm_partial', level, self.src.data_ptr() if self.n else None, self.s_nd[0], self.s_nd[1],
+                 self.ref.data_ptr() if self.n else None, self.r_nd[0], self.r_nd[1], self.n, self.work.data_ptr(),
+                 self.ws_bytes, km._stream())
+        return self.work[:self.accum_bytes]
+
+    def merge(self, level: int, gathered: torch.Tensor, world: int):
+        km = self._km
+        km._call('hb_block_norm_merge', level, gathered.data_ptr(), world, self.work.data_ptr(), self.ws_bytes,
+                 self.norm.data_ptr(), km._stream())
+
+
+def block_norm_sharded(src_local: torch.Tensor, src_nodata, ref_local: torch.Tensor, ref_nodata, group=None,
+                       backend=NativeBlockNorm) -> torch.Tensor:
+    """
+    ``KernelModel._fit_block_norm`` (kernel_model.py:216-229) of a block whose rows are spread over the ranks: every rank
+    passes ITS rows of the two planes and gets the two float64 statistics of the whole block (identical on all ranks).
+    Three passes, each followed by one all-gather of the pass's accumulators (counts, sums, histograms; 131 KB per rank)
+    and a merge in rank order.  ``backend`` supplies the two native steps (the CPU tests substitute a numpy stand-in to
+    exercise this protocol over gloo).
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    state = backend(src_local, src_nodata, ref_local, ref_nodata)
+    for level in range(3):
+        acc = state.partial(level)
+        gathered = _all_gather_bytes(acc, group) if world > 1 else acc
+        state.merge(level, gathered, world)
+    return state.norm
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# halo rows received in place
+# ---------------------------------------------------------------------------------------------------------------------
+def alloc_with_halo(bands: RowBands, rank: int, halo: int, width: int, dtype, device) -> Tuple[torch.Tensor, int]:
+    """
+    An uninitialised ``[rows of bands.with_halo(rank, halo), width]`` plane and the number of halo rows on top: fill
+    rows ``[top, top + bands.size(rank))`` with the rank's own rows, then `exchange_halos_inplace` fills the rest.
+    """
+    a, _ = bands.band(rank)
+    lo, hi = bands.with_halo(rank, halo)
+    return torch.empty((hi - lo, width), dtype=dtype, device=device), a - lo
+
+
+def exchange_halos_inplace(ext: torch.Tensor, bands: RowBands, halo: int, group=None) -> None:
+    """
+    Fill the halo rows of ``ext`` (``[..., rows of bands.with_halo(rank, halo), width]``, own rows already in place) from
+    the row-band neighbours, point to point, receiving straight into ``ext``: nothing but the halo rows moves.
+    """
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1 or halo == 0:
+        return
+    a, b = bands.band(rank)
+    lo, hi = bands.with_halo(rank, halo)
+    if ext.shape[-2] != hi - lo:
+        raise ValueError(f'`ext` must hold the {hi - lo} rows of the band with its halo, not {ext.shape[-2]}')
+    sends, recvs = [], []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        pa, pb = bands.band(peer)
+        plo, phi = bands.with_halo(peer, halo)
+        s0, s1 = max(a, plo), min(b, phi)                # rows of mine that the peer needs
+        if s1 > s0:
+            sends.append((ext[..., s0 - lo:s1 - lo, :], peer))
+        r0, r1 = max(pa, lo), min(pb, hi)                # rows of the peer that I need
+        if r1 > r0:
+            recvs.append((ext[..., r0 - lo:r1 - lo, :], peer))
+    _run_p2p(sends, recvs, group)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the two sharded regimes
+# ---------------------------------------------------------------------------------------------------------------------
 def fuse_refspace_sharded(model, src_local: RasterArray, ref_ra: RasterArray, bands: RowBands, group=None, out=None
                           ) -> Tuple[RasterArray, RasterArray]:
     """
     proc_crs = ref fit + apply of ONE band of a raster that is sharded by rows (configuration C5a).
 
     ``src_local`` holds this rank's source rows (its transform already points at its first row); ``ref_ra`` is the
-    whole (replicated) reference band on the proc grid; ``bands`` partitions the proc-grid rows.  Returns
-    ``(corr_local, param_ra)``: the corrected rows of this rank and the parameters of the proc-grid rows they depend on
-    (this rank's band plus the 2 rows of cubic-spline support on either side; ``param_ra.transform`` points at them).
-    ``out`` (optional): float32 CUDA tensor to receive the corrected rows.
+    whole (replicated: it is 1 / ratio^2 of the source) reference band on the proc grid; ``bands`` partitions the
+    proc-grid rows.  Returns ``(corr_local, param_ra)``: the corrected rows of this rank and the parameters of the
+    proc-grid rows they depend on (this rank's band plus the 2 rows of cubic-spline support on either side;
+    ``param_ra.transform`` points at them).  ``out`` (optional): float32 CUDA tensor to receive the corrected rows.
 
-    Only the down-sampled proc-grid plane -- 1/ratio^2 of the source -- crosses the interconnect: it is all-gathered so
-    that the block normalisation of gain-blk-offset (a whole-block statistic, kernel_model.py:216-229) stays global;
-    every rank then fits just its own proc rows plus the halo that makes them equal the whole-raster fit
-    (`halo_rows`: window half-height + spline support + the in-painting search radius).
+    Per rank: down-sample own rows -> block statistics over own proc rows, merged by `block_norm_sharded`
+    (gain-blk-offset) -> halo rows of the down-sampled source from the neighbours -> fit of the rows the up-sampler
+    needs -> up-sample + apply on own source rows.  No rank reads pixels outside its band + halo.
     """
     from homonim_b200 import kernel_model as km
     from homonim_b200.enums import Model
@@ -178,22 +325,21 @@ def fuse_refspace_sharded(model, src_local: RasterArray, ref_ra: RasterArray, ba
     a, b = bands.band(rank)
     nan = float('nan')
     src_t = km._to_device(src_local.array)
+    ref_t = km._as_f32_plane(km._to_device(ref_ra.array), ref_ra.nodata).contiguous()
     # 1. down-sample my source rows onto my proc rows
     local_tf = ref_ra.transform * Affine.translation(0, a)
     src_ds_local = km._downsample_average(src_t, src_local.transform, src_local.nodata, (b - a, ref_ra.width), local_tf)
-    # 2. the proc-grid plane is tiny: gather it everywhere
-    src_ds = all_gather_rows(src_ds_local, bands, group)
-    ref_t = km._to_device(ref_ra.array)
-    # 3. whole-block statistics (redundant on every rank: three passes over the small proc-grid planes)
+    # 2. whole-block statistics from per-rank accumulators
     norm = None
     if model.model == Model.gain_blk_offset:
-        norm = model._block_norm(src_ds, nan, ref_t, ref_ra.nodata)
-    # 4. fit my proc rows + halo; keep the rows my source rows' spline taps touch
+        norm = block_norm_sharded(src_ds_local, nan, ref_t[a:b], ref_ra.nodata, group)
+    # 3. halo rows of the down-sampled plane, point to point
     inpaint = model.model == Model.gain_offset and model._r2_inpaint_thresh is not None
     halo = halo_rows(model.kernel_shape, proc_crs_ref=True, inpaint=inpaint)
     lo, hi, plo, phi = fit_row_window(bands, rank, halo)
-    params_ext = model._fit_planes(src_ds[lo:hi], nan, ref_t[lo:hi], ref_ra.nodata, norm=norm)
-    params = params_ext[:, plo - lo:phi - lo].contiguous()
+    src_ds, _ = exchange_halos(src_ds_local, bands, halo, group)
+    # 4. fit the rows my source rows' spline taps touch, inside the held window
+    params = model._fit_planes(src_ds, nan, ref_t[lo:hi], ref_ra.nodata, norm=norm, rows=(plo - lo, phi - plo))
     param_ra = RasterArray(params, ref_ra.crs, ref_ra.transform * Affine.translation(0, plo), nodata=nan)
     # 5. apply to my source rows
     corr_local = model.apply(RasterArray(src_t, src_local.crs, src_local.transform, nodata=src_local.nodata), param_ra,
@@ -204,17 +350,44 @@ def fuse_refspace_sharded(model, src_local: RasterArray, ref_ra: RasterArray, ba
 def fit_same_grid_sharded(model, src_local: torch.Tensor, src_nodata, ref_local: torch.Tensor, ref_nodata,
                           bands: RowBands, group=None) -> torch.Tensor:
     """
-    Same-grid fit of a raster sharded by rows (configuration C5b): halo exchange of ``kh // 2`` rows of both planes
-    with the row-band neighbours, fit on the extended band, halo rows dropped.  gain and gain-offset models only --
-    gain-blk-offset needs the block statistics of the whole raster (use `fuse_refspace_sharded`, or fit unsharded).
+    Same-grid fit of a raster sharded by rows: halo exchange of ``kh // 2`` rows of both planes with the row-band
+    neighbours (+ 100 with R2 in-painting), whole-block statistics merged over the ranks for gain-blk-offset, fit of the
+    rank's own rows inside the extended band.  Returns the ``[2|3, own rows, W]`` parameters.  (Copies the band into the
+    extended plane; callers that own their buffers use `alloc_with_halo` + `fit_apply_same_grid_sharded`.)
     """
     from homonim_b200.enums import Model
-    if model.model == Model.gain_blk_offset:
-        raise NotImplementedError('sharded same-grid fitting of gain-blk-offset needs whole-raster block statistics')
     halo = halo_rows(model.kernel_shape, proc_crs_ref=False,
                      inpaint=(model.model == Model.gain_offset and model._r2_inpaint_thresh is not None))
     rank = dist.get_rank(group)
+    norm = None
+    if model.model == Model.gain_blk_offset:
+        norm = block_norm_sharded(src_local.contiguous(), src_nodata, ref_local.contiguous(), ref_nodata, group)
     src_ext, top = exchange_halos(src_local, bands, halo, group)
     ref_ext, _ = exchange_halos(ref_local, bands, halo, group)
-    params = model._fit_planes(src_ext.contiguous(), src_nodata, ref_ext.contiguous(), ref_nodata)
-    return params[:, top:top + bands.size(rank), :].contiguous()
+    return model._fit_planes(src_ext.contiguous(), src_nodata, ref_ext.contiguous(), ref_nodata, norm=norm,
+                             rows=(top, bands.size(rank)))
+
+
+def fit_apply_same_grid_sharded(model, src_ext: torch.Tensor, src_nodata, ref_ext: torch.Tensor, ref_nodata,
+                                bands: RowBands, group=None, out=None) -> torch.Tensor:
+    """
+    Same-grid fit + apply of ONE band of a raster sharded by rows (configuration C5b: source and reference on one grid).
+
+    ``src_ext`` / ``ref_ext``: float32 planes from `alloc_with_halo` (halo = `halo_rows(kernel_shape, False, False)`) with
+    this rank's own rows in place.  The halo rows are received from the neighbours in place, the block statistics of
+    gain-blk-offset are merged over the ranks, and one kernel fits the rank's rows and writes the corrected pixels
+    (``hb_fit_apply_same_grid_rows``).  Returns the corrected ``[own rows, W]`` plane (``out`` when given).
+    """
+    from homonim_b200.enums import Model
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    halo = halo_rows(model.kernel_shape, proc_crs_ref=False, inpaint=False)
+    a, b = bands.band(rank)
+    lo, _ = bands.with_halo(rank, halo)
+    top, n_local = a - lo, b - a
+    norm = None
+    if model.model == Model.gain_blk_offset:
+        norm = block_norm_sharded(src_ext[top:top + n_local], src_nodata, ref_ext[top:top + n_local], ref_nodata, group)
+    if dist.is_initialized():
+        exchange_halos_inplace(src_ext, bands, halo, group)
+        exchange_halos_inplace(ref_ext, bands, halo, group)
+    return model._fit_apply_rows(src_ext, src_nodata, ref_ext, ref_nodata, top, n_local, norm=norm, out=out)

@@ -231,17 +231,21 @@ class KernelModel:
               work.data_ptr(), ws_bytes, _stream())
         return norm
 
-    def _fit_planes(self, src_t, src_nodata, ref_t, ref_nodata, norm=None):
+    def _fit_planes(self, src_t, src_nodata, ref_t, ref_nodata, norm=None, rows=None):
         """
         Same-grid fit of two float32 device planes -> float32 [2|3, H, W] parameter tensor.  ``norm``: block
-        normalisation computed elsewhere (row-band sharding: the statistics of the WHOLE block, dist.py).
+        normalisation computed elsewhere (row-band sharding: the statistics of the WHOLE block, dist.py).  ``rows`` =
+        ``(row0, nrows)``: fit only these rows of the planes (a row band inside its halo); the result then holds
+        ``nrows`` rows.  With R2 in-painting the whole plane is fitted and in-painted (its search reaches 100 pixels)
+        and the rows are cut out afterwards.
         """
         lib = _native.lib()
         h, w = int(src_t.shape[-2]), int(src_t.shape[-1])
         src_t, ref_t = _as_f32_plane(src_t, src_nodata).contiguous(), _as_f32_plane(ref_t, ref_nodata).contiguous()
         want_r2 = self._wants_r2()
         inpaint = self._model == Model.gain_offset and self._r2_inpaint_thresh is not None
-        params = torch.empty((3 if want_r2 else 2, h, w), dtype=torch.float32, device=src_t.device)
+        row0, nrows = (0, h) if (rows is None or inpaint) else (int(rows[0]), int(rows[1]))
+        params = torch.empty((3 if want_r2 else 2, nrows, w), dtype=torch.float32, device=src_t.device)
         s_has, s_nd = _nodata_args(src_nodata)
         r_has, r_nd = _nodata_args(ref_nodata)
         stream = _stream()
@@ -252,16 +256,41 @@ class KernelModel:
             norm_ptr = norm.data_ptr()
         sums = torch.empty((3, h, w), dtype=torch.float32, device=src_t.device) if inpaint else None
         kh, kw = self._kernel_shape
-        _call('hb_fit_same_grid', src_t.data_ptr(), s_has, s_nd, ref_t.data_ptr(), r_has, r_nd, h, w,
-                                           _MODEL_CODES[self._model], kh, kw, int(want_r2), norm_ptr,
-                                           params.data_ptr(), sums.data_ptr() if inpaint else None, stream)
+        _call('hb_fit_same_grid_rows', src_t.data_ptr(), s_has, s_nd, ref_t.data_ptr(), r_has, r_nd, h, w, row0, nrows,
+              _MODEL_CODES[self._model], kh, kw, int(want_r2), norm_ptr, params.data_ptr(),
+              sums.data_ptr() if inpaint else None, stream)
         if inpaint:
             ws_bytes = lib.hb_inpaint_workspace_bytes(h, w)
             work = torch.empty(ws_bytes, dtype=torch.uint8, device=src_t.device)
             _call('hb_inpaint_refit', params.data_ptr(), sums.data_ptr(), h, w,
                                                float(self._r2_inpaint_thresh), MAX_SEARCH_DISTANCE, work.data_ptr(),
                                                ws_bytes, stream)
+            if rows is not None:
+                params = params[:, int(rows[0]):int(rows[0]) + int(rows[1])].contiguous()
         return params
+
+    def _fit_apply_rows(self, src_t, src_nodata, ref_t, ref_nodata, row0, nrows, norm=None, out=None):
+        """
+        Fit fused with apply (``hb_fit_apply_same_grid_rows``) for the rows ``[row0, row0 + nrows)`` of two float32 device
+        planes on one grid -> corrected float32 ``[nrows, W]``.  The parameters are not materialised (models whose
+        parameters are final after the fit: everything but gain-offset with R2 in-painting).
+        """
+        if self._model == Model.gain_offset and self._r2_inpaint_thresh is not None:
+            raise ValueError('fit + apply in one kernel is not available with R2 in-painting')
+        h, w = int(src_t.shape[-2]), int(src_t.shape[-1])
+        if src_t.dtype != torch.float32 or ref_t.dtype != torch.float32 or not src_t.is_contiguous() \
+                or not ref_t.is_contiguous():
+            raise ValueError('fit + apply in one kernel needs contiguous float32 planes')
+        corr = self._check_out(out, int(nrows), w, src_t.device)
+        if self._model == Model.gain_blk_offset and norm is None:
+            norm = self._block_norm(src_t, src_nodata, ref_t, ref_nodata)
+        s_has, s_nd = _nodata_args(src_nodata)
+        r_has, r_nd = _nodata_args(ref_nodata)
+        kh, kw = self._kernel_shape
+        _call('hb_fit_apply_same_grid_rows', src_t.data_ptr(), s_has, s_nd, ref_t.data_ptr(), r_has, r_nd, h, w,
+              int(row0), int(nrows), _MODEL_CODES[self._model], kh, kw, norm.data_ptr() if norm is not None else None,
+              corr.data_ptr(), _stream())
+        return corr
 
     def _full_coverage_mask(self, in_mask_t, in_transform, params_t, param_transform):
         """ Reference kernel_model.py:375-409 on device: uint8 [hp, wp] mask on the parameter grid. """

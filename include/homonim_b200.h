@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 5
+#define HB_ABI_VERSION 6
 
 /* storage dtype of a source raster plane */
 enum { HB_U8 = 0, HB_U16 = 1, HB_F32 = 2, HB_I16 = 3 };   /* HB_I16: output of hb_convert_dtype only */
@@ -67,6 +67,23 @@ int hb_block_norm(const float *src_dev, int src_has_nodata, double src_nodata, c
                   int ref_has_nodata, double ref_nodata, long n, double *norm_dev, void *workspace_dev,
                   size_t workspace_bytes, void *stream);
 
+/* Row-band shards (one raster split by rows over several GPUs): _fit_block_norm is a statistic of the
+ * WHOLE block (kernel_model.py:216-229), so the three streaming passes of hb_block_norm are run per shard and resolved
+ * after an exchange.  Per level (0, 1, 2, in this order), every rank calls
+ *     hb_block_norm_partial(level, its rows of both planes, n_local, workspace)       -- accumulate only
+ * all-gathers the first hb_block_norm_accum_bytes() bytes of its workspace (counts, sums, histograms of the level)
+ * into `gathered_dev` = world x accum_bytes, in rank order, and calls
+ *     hb_block_norm_merge(level, gathered_dev, world, workspace, norm_dev)            -- sum over ranks + resolve
+ * The merge adds the ranks' accumulators in rank order, so every rank derives bit-identical statistics; after level 2
+ * norm_dev holds the same two doubles hb_block_norm gives for the unsharded planes (the double sums are associated
+ * per rank, so the float32 standard deviations can differ from the unsharded ones in the last bit).  n_local may be 0. */
+size_t hb_block_norm_accum_bytes(void);
+int hb_block_norm_partial(int level, const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
+                          int ref_has_nodata, double ref_nodata, long n_local, void *workspace_dev,
+                          size_t workspace_bytes, void *stream);
+int hb_block_norm_merge(int level, const void *gathered_dev, int world, void *workspace_dev, size_t workspace_bytes,
+                        double *norm_dev, void *stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Same-grid fit: KernelModel.fit -> _fit_gain / _fit_gain_blk_offset / _fit_gain_offset + _r2_array
  * (kernel_model.py:142-373, 411-440), without the in-painting step.
@@ -76,11 +93,19 @@ int hb_block_norm(const float *src_dev, int src_has_nodata, double src_nodata, c
  *   sums_dev   optional float32 [3][h][w] receiving the window sums (sum ref, sum src, count) that
  *              hb_inpaint_refit needs; NULL to skip.
  * Window sums are centred kh x kw box sums with zero padding (cv.boxFilter BORDER_CONSTANT), accumulated in
- * double and rounded exactly where OpenCV / numpy round them (SURVEY.md 8a numerics note).
+ * double and rounded exactly where OpenCV / numpy round them (SURVEY.md 8a numerics note).  kh, kw odd, <= 127.
  * --------------------------------------------------------------------------------------------------------------- */
 int hb_fit_same_grid(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
                      int ref_has_nodata, double ref_nodata, long h, long w, int model, int kh, int kw, int want_r2,
                      const double *norm_dev, float *params_dev, float *sums_dev, void *stream);
+
+/* hb_fit_same_grid for the output rows [row0, row0 + nrows) only: the planes still hold h rows (the windows of the
+ * first / last output rows reach into the rows around them), params_dev / sums_dev hold nrows rows per plane.  What a
+ * row band of a sharded raster calls on its rows + halo (the reference's block overlap, utils.py:136-153):
+ * rows outside [0, h) are the reference's zero padding, rows inside are real neighbours. */
+int hb_fit_same_grid_rows(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
+                          int ref_has_nodata, double ref_nodata, long h, long w, long row0, long nrows, int model, int kh,
+                          int kw, int want_r2, const double *norm_dev, float *params_dev, float *sums_dev, void *stream);
 
 /* Same-grid fit fused with the apply step: corr = gain * src + offset (KernelModel.apply, kernel_model.py:442-463) of the
  * parameters hb_fit_same_grid would produce, written straight from the fit kernel's epilogue -- the parameters never
@@ -90,6 +115,12 @@ int hb_fit_same_grid(const float *src_dev, int src_has_nodata, double src_nodata
 int hb_fit_apply_same_grid(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
                            int ref_has_nodata, double ref_nodata, long h, long w, int model, int kh, int kw,
                            const double *norm_dev, float *corr_dev, void *stream);
+
+/* hb_fit_apply_same_grid for the output rows [row0, row0 + nrows) only (see hb_fit_same_grid_rows); corr_dev holds
+ * nrows rows. */
+int hb_fit_apply_same_grid_rows(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
+                                int ref_has_nodata, double ref_nodata, long h, long w, long row0, long nrows, int model,
+                                int kh, int kw, const double *norm_dev, float *corr_dev, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Low-R2 in-painting and gain refit: kernel_model.py:361-371 (rasterio.fill.fillnodata == GDALFillNodata with

@@ -188,7 +188,8 @@ def test_bench_reference_arm_contract():
                 'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
         assert key in line, key
     assert line['impl'] == 'reference' and line['unit'] == 'Mpix/s' and line['value'] > 0
-    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['cpu_baseline']['kind'] in ('reference', 'port') and line['cpu_baseline']['cores'] >= 1
+    assert 'one_block' in line['cpu_baseline']['modes']
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
     assert 'workload' in line['config'] and 'model' not in line['config']
 

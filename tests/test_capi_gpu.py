@@ -456,7 +456,8 @@ def test_bench_contract_on_gpu():
     assert len(lines) == 1
     line = json.loads(lines[0])
     for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
-                'vs_baseline', 'dtype', 'data', 'config', 'clocks', 'e2e', 'gpu_launches', 'roofline', 'cpu_baseline'):
+                'vs_baseline', 'dtype', 'data', 'config', 'clocks', 'e2e', 'gpu_launches', 'roofline', 'cpu_baseline',
+                'parity', 'row_band'):
         assert key in line, key
     assert line['value'] > 0 and line['gpu_launches'] > 0 and line['n_gpus'] == 1 and line['steps'] == 3
     assert line['e2e']['value'] > 0 and line['e2e']['h2d_bytes_per_step'] > 0 and line['e2e']['d2h_bytes_per_step'] > 0
@@ -464,7 +465,14 @@ def test_bench_contract_on_gpu():
     for key in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'):
         assert key in roof, key
     assert roof['bound'] == 'hbm' and roof['achieved'] > 0
-    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['value'] > 0
+    assert line['cpu_baseline']['kind'] in ('reference', 'port') and line['cpu_baseline']['value'] > 0
+    # the GPU result of the sampled band against the reference's own result on the same inputs
+    par = line['parity']
+    assert par['masks_identical'] and par['within_tolerance'], par
+    assert par['max_rel_err_corr'] <= 1e-4 and par['max_rel_err_gain'] <= 1e-4 and par['max_rel_err_offset'] <= 1e-4
+    # the one-raster (row band) regime measured in the same invocation
+    rb = line['row_band']
+    assert rb['value'] > 0 and rb['scaling'] == 'strong' and rb['gpu_launches'] > 0
     assert 'workload' in line['config'] and 'model' not in line['config']
 
 

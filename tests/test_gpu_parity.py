@@ -3,6 +3,8 @@ GPU tier: parity of the sm_100a CUDA path against (i) the golden vectors generat
 (ii) the oracle port on larger seeded synthetic rasters.  Tolerance (BASELINE.json north_star): parameter and
 corrected-pixel max rel err <= 1e-4 (see conftest.check_params for the floors), nodata masks identical.
 """
+import warnings
+
 import numpy as np
 import pytest
 
@@ -110,6 +112,63 @@ def test_same_grid_1k_vs_oracle(model, kernel_shape, find_r2, thresh):
         got = param_ra.to_host().array[0]
         same = (got == exp_params[0]) | (np.isnan(got) & np.isnan(exp_params[0]))
         assert same.mean() > 0.99
+
+
+@pytest.mark.parametrize('shape', [(300, 700), (2100, 2300)])
+@pytest.mark.parametrize('model, kernel_shape, find_r2', [
+    (Model.gain, (1, 67), False),
+    (Model.gain_offset, (3, 65), True),
+    (Model.gain_offset, (1, 127), False),
+    (Model.gain_blk_offset, (67, 1), True),
+    (Model.gain, (127, 127), True),
+])
+def test_same_grid_wide_kernels_vs_oracle(shape, model, kernel_shape, find_r2):
+    """
+    Kernels wider than a 32-column warp: small rasters (one column per thread) are routed to the 4-column variant above
+    31 columns, whose 128-column warps carry kernels up to 127 wide (a window never spans more than two warps).  Small
+    and large rasters take different kernel instantiations; both must agree with the oracle.
+    """
+    kmnp = _oracle()
+    h, w = shape
+    src_ra, ref_ra = make_pair(h, w, 1, bands=1, dtype='float32', mu=0.3, seed=13, device='cuda',
+                               src_nodata=float('nan'), ref_pad=0)
+    src_ra = RasterArray(src_ra.array[0].contiguous(), src_ra.crs, src_ra.transform, nodata=src_ra.nodata)
+    ref_ra = RasterArray(ref_ra.array[0].contiguous(), ref_ra.crs, src_ra.transform, nodata=ref_ra.nodata)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        km = KernelModel(model, kernel_shape, find_r2=find_r2, r2_inpaint_thresh=None)
+    param_ra = km.fit(src_ra, ref_ra)
+    src, ref = src_ra.to_host().array, ref_ra.to_host().array
+    exp_params = kmnp.fit_same_grid(src, float('nan'), ref, float('nan'), model, kernel_shape, find_r2, None)
+    check_params(param_ra.to_host().array, exp_params, float(np.nanmean(src)), f'params {kernel_shape}',
+                 r2_robust=model == Model.gain_blk_offset)
+
+
+def test_same_grid_row_range_equals_full_fit():
+    """ hb_fit_same_grid_rows / hb_fit_apply_same_grid_rows: the rows of a band inside a larger plane get exactly the
+    full fit's values for those rows wherever the band sits (what the row-band shards rely on). """
+    src_ra, ref_ra = make_pair(700, 2052, 1, bands=1, dtype='float32', mu=0.3, seed=17, device='cuda',
+                               src_nodata=float('nan'), ref_pad=0)
+    s, r = src_ra.array[0].contiguous(), ref_ra.array[0].contiguous()
+    nan = float('nan')
+    for model, kshape, find_r2 in ((Model.gain_offset, (15, 15), True), (Model.gain_blk_offset, (5, 7), False),
+                                   (Model.gain, (1, 1), False)):
+        km = KernelModel(model, kshape, find_r2=find_r2, r2_inpaint_thresh=None)
+        norm = km._block_norm(s, nan, r, nan) if model == Model.gain_blk_offset else None
+        full = km._fit_planes(s, nan, r, nan, norm=norm)
+        full_corr = km._apply_planes(s, nan, full, mask_src=False)
+        for row0, nrows in ((0, 700), (0, 33), (123, 301), (650, 50), (699, 1)):
+            part = km._fit_planes(s, nan, r, nan, norm=norm, rows=(row0, nrows))
+            exp = full[:, row0:row0 + nrows]
+            assert torch.equal(torch.isnan(part), torch.isnan(exp))
+            same = ((part == exp) | (torch.isnan(part) & torch.isnan(exp))).float().mean().item()
+            assert same > 0.999, (model, row0, nrows, same)
+            corr = km._fit_apply_rows(s, nan, r, nan, row0, nrows, norm=norm)
+            expc = full_corr[row0:row0 + nrows]
+            assert torch.equal(torch.isnan(corr), torch.isnan(expc))
+            fin = torch.isfinite(expc)
+            rel = ((corr - expc).abs()[fin] / expc.abs()[fin].clamp_min(1e-3 * expc[fin].abs().mean())).max().item()
+            assert rel <= 1e-4, (model, row0, nrows, rel)
 
 
 @pytest.mark.parametrize('dtype, nodata, ratio, model, kernel_shape, thresh', [
