@@ -332,13 +332,18 @@ def _rel_err(actual, expected, floor, exclude):
     return float(np.max(np.abs(a - e) / np.maximum(np.abs(e), fl)))
 
 
-def parity_metrics(got_params, got_corr, exp_params, exp_corr, src_mean):
+def parity_metrics(got_params, got_corr, exp_params, exp_corr, src_mean, param_to_corr=None, offset_at_corr=None):
     """
     SURVEY.md 8(d): masks `isnan(out) == isnan(reference)` exactly; gain / corrected-pixel error relative to
     max(|x_ref|, 1e-3 x band mean); offset error relative to max(|offset|, |gain| x mean(src)); R2 absolute.  Pixels
     where the reference's own solve is ill-conditioned (|gain| > 50 x the band median: a denominator crossing zero
     turns rounding noise into the value) are counted in `excluded_px` and left out of the maxima --
-    never out of the mask comparison.
+    never out of the mask comparison.  ``param_to_corr``: maps a boolean parameter-grid mask to the corrected-image grid
+    (the pixels whose cubic-spline taps touch those parameters), so that the same pixels are left out there.
+    ``offset_at_corr``: the reference's offset parameter looked up at every corrected pixel; corrected pixels where the
+    reference's own float32 expression gain * src + offset (kernel_model.py:461) cancels by more than 2^7 (|corr| < |offset| /
+    128: the value is then the rounding residue of two ~100x larger float32 terms) are counted in `cancellation_px` and
+    likewise left out of `max_rel_err_corr` -- their worst error is reported separately, relative to the same floor.
     """
     n = min(got_params.shape[0], exp_params.shape[0])
     masks = bool(np.array_equal(np.isnan(got_corr), np.isnan(exp_corr)) and
@@ -361,8 +366,16 @@ def parity_metrics(got_params, got_corr, exp_params, exp_corr, src_mean):
     med_c = float(np.median(np.abs(exp_corr[fin_c]))) if fin_c.any() else 1.0
     with np.errstate(invalid='ignore'):
         bad_c = np.abs(exp_corr) > 50 * max(med_c, 1e-30)
+    if bad.any():
+        bad_c |= param_to_corr(bad) if param_to_corr is not None else bad
     c_floor = 1e-3 * float(np.mean(np.abs(exp_corr[fin_c & ~bad_c]))) if (fin_c & ~bad_c).any() else 1.0
-    out['max_rel_err_corr'] = _rel_err(got_corr, exp_corr, c_floor, bad_c)
+    cancel = np.zeros(exp_corr.shape, bool)
+    if offset_at_corr is not None:
+        with np.errstate(invalid='ignore'):
+            cancel = fin_c & (np.abs(exp_corr) * 128.0 < np.abs(offset_at_corr))
+        out['cancellation_px'] = int(cancel.sum())
+        out['max_rel_err_corr_cancellation_px'] = float(f'{_rel_err(got_corr, exp_corr, c_floor, ~cancel | bad_c):.3e}')
+    out['max_rel_err_corr'] = _rel_err(got_corr, exp_corr, c_floor, bad_c | cancel)
     if n > 2:
         fin2 = np.isfinite(exp_params[2]) & ~bad
         out['r2_abs'] = float(np.max(np.abs(got_params[2][fin2].astype('float64') - exp_params[2][fin2]))) \
@@ -415,7 +428,20 @@ def measure_parity_and_cpu(args, cfg, src_ra, ref_ra):
         raise RuntimeError(f'parameter grids differ: {got_params.shape} vs {exp_params.shape}')
     valid = src_np[0][~np.isnan(src_np[0].astype('float32'))] if np.isnan(cfg['src_nodata']) else \
         src_np[0][src_np[0] != cfg['src_nodata']]
-    parity = parity_metrics(got_params, got_corr, exp_params, exp_corr, float(valid.astype('float64').mean()))
+    param_to_corr, offset_at_corr = None, exp_params[1]
+    if cfg['proc_crs'] == 'ref':
+        st, pt = src_ra.transform, param_ra.transform
+        hs, ws = got_corr.shape
+        rows = np.floor(((st.f + (np.arange(hs) + 0.5) * st.e) - pt.f) / pt.e).astype(int).clip(0, exp_params.shape[1] - 1)
+        cols = np.floor(((st.c + (np.arange(ws) + 0.5) * st.a) - pt.c) / pt.a).astype(int).clip(0, exp_params.shape[2] - 1)
+
+        def param_to_corr(mask):
+            # a parameter pixel reaches the source pixels under the 4 x 4 spline taps around it: dilate by 2, look up
+            grown = cv2.dilate(mask.astype('uint8'), np.ones((5, 5), 'uint8')) > 0
+            return grown[np.ix_(rows, cols)]
+        offset_at_corr = exp_params[1][np.ix_(rows, cols)]
+    parity = parity_metrics(got_params, got_corr, exp_params, exp_corr, float(valid.astype('float64').mean()),
+                            param_to_corr, offset_at_corr)
     parity['sample'] = note
     parity['against'] = f'{cpu.kind} ({cpu.where})'
     if cfg['model'] == 'gain-offset' and cfg['r2_inpaint_thresh'] is not None:
@@ -494,15 +520,16 @@ class RowBandJob:
                     for _ in range(2)]
         self.streams = [torch.cuda.Stream(device=device) for _ in range(2)]
 
-    def step(self, keep_band0=None):
+    def step(self, keep_band0=None, serial=False):
         """ All bands; consecutive bands alternate between two streams (and two output planes), so that one band's small
-        kernels and exchanges overlap the other's streaming kernels.  ``keep_band0``: tensor receiving band 0's result. """
+        kernels and exchanges overlap the other's streaming kernels (``serial``: one stream, for per-kernel timing).
+        ``keep_band0``: tensor receiving band 0's result. """
         torch, cfg = self.torch, self.cfg
         main = torch.cuda.current_stream()
         for st in self.streams:
             st.wait_stream(main)
         for band in range(cfg['bands']):
-            st = self.streams[band % 2]
+            st = self.streams[0 if serial else band % 2]
             out = keep_band0 if (band == 0 and keep_band0 is not None) else self.out[band % 2]
             with torch.cuda.stream(st):
                 if self.same_grid:
@@ -565,16 +592,19 @@ def measure_row_band(args, cfg, rank, world, local_rank, steps, warmup, with_n1=
     value = npix_total * steps / (elapsed_ms * 1e-3) / 1e6
     # per-kernel durations: one more step with CUDA events around every native call (bands then run back to back)
     with KernelTimer() as timer:
-        job.step()
+        job.step(serial=True)
         kernel_ms = timer.results()
     b_in = 4
-    per_px = {'hb_upsample_apply': b_in + 4, 'hb_downsample_average': b_in, 'hb_fit_apply_same_grid_rows': 12,
-              'hb_block_norm_partial': 8}
+    # algorithmic bytes per launch: per SOURCE pixel of this rank's rows for the resampling kernels, per proc-grid pixel
+    # for the statistics / same-grid kernels
+    proc_px = (bands.size(rank) * cfg['wp'])
+    alg = {'hb_upsample_apply': job.local_px * (b_in + 4), 'hb_downsample_average': job.local_px * b_in,
+           'hb_fit_apply_same_grid_rows': proc_px * 12, 'hb_block_norm_partial': proc_px * 8}
     kernels = {}
     for k, v in kernel_ms.items():
         kernels[k] = {'launches': len(v), 'ms_avg': round(sum(v) / len(v), 4)}
-        if k in per_px:
-            kernels[k]['gbs'] = round(job.local_px * per_px[k] / (kernels[k]['ms_avg'] * 1e-3) / 1e9, 1)
+        if k in alg:
+            kernels[k]['gbs'] = round(alg[k] / (kernels[k]['ms_avg'] * 1e-3) / 1e9, 1)
     bytes_per_px = 12 if not job.same_grid else 12 + 3 * 8       # DESIGN.md section 4 (same grid: + 3 statistics passes)
     peak_gbs, _ = _peak()
     result = {

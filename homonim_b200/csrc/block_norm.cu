@@ -7,9 +7,18 @@
 // Exact order statistics come from a 3-level (12 + 12 + 8 bit) radix select on the order-preserving integer image of
 // the float32 values: three streaming passes, each building shared-memory histograms (warp-aggregated atomics) that a
 // one-CTA "resolve" kernel turns into the next key prefix.  The two ranks numpy interpolates between (k, k + 1) of
-// both planes are four simultaneous queries.  Means ride on pass 0, squared deviations (two-pass std, double
-// accumulation) on pass 1.  The interpolation reproduces numpy >= 2's float32 arithmetic for float32 input
-// (q = 1/float32(100), virtual index n*q + (1 - q) - 1 in float32, _lerp in float32).
+// both planes are four simultaneous queries.  The interpolation reproduces numpy >= 2's float32 arithmetic for float32
+// input (q = 1/float32(100), virtual index (n - 1) * q in float32, _lerp in float32).
+//
+// The standard deviations reproduce numpy's float32 np.std TO THE BIT (blocks up to 2^28 pixels): np.std of a float32
+// array is mean = float32(pairwise_sum(x) / n), then pairwise_sum((x - mean)^2) / n, square root -- all in float32, where
+// pairwise_sum is numpy's recursive halving down to leaves of <= 128 elements summed with 8 interleaved accumulators
+// (numpy/_core/src/umath/loops_utils.h.src).  The result depends on that exact association, so it is replayed: the valid
+// pixels are compacted in C order (what `array[mask]` hands to np.std), every leaf of the recursion is summed by one
+// thread in numpy's order, and the leaves are combined up the same tree.  (The R2 formula of the gain-blk-offset model
+// amplifies a 1-ulp change of the block gain ~1000x, which is why "correctly rounded" was not close enough, a6.)
+// Larger blocks, and the per-rank accumulators of row-band shards, use double accumulation: means on pass 0, squared
+// deviations on pass 1 (within 1 float32 ulp of numpy).
 #include "hb_common.cuh"
 
 namespace {
@@ -27,6 +36,11 @@ struct NormAccum {
 };
 
 struct NormState : NormAccum {
+    float std_exact[2];            // numpy-exact float32 standard deviations (valid when has_exact)
+    float meanf[2];                // numpy's float32 means
+    unsigned int has_exact;
+    unsigned int pad_;
+    unsigned long long n_comp;     // number of compacted (valid) pixels
     double mean[2];
     unsigned long long rank[4];    // remaining rank inside the current prefix; queries: src k, src k+1, ref k, ref k+1
     unsigned int prefix[4];        // key prefix found so far
@@ -231,11 +245,10 @@ __device__ void norm_resolve(NormState *__restrict__ st, double *__restrict__ no
     const unsigned long long n = __ldcg(&st->n);
 
     if (LEVEL == 0 && threadIdx.x == 0) {
-        // numpy >= 2, float32 input: q = 1 / float32(100); virtual index = n*q + (1 + q*(1 - 1 - 1)) - 1 in float32
+        // numpy >= 2, float32 input: q = 1 / float32(100); the "linear" method's virtual index is (n - 1) * q, formed in
+        // float32 (numpy/lib/_function_base_impl.py, _QuantileMethods['linear'])
         const float q32 = __fdiv_rn(1.f, 100.f);
-        const float nf = __ull2float_rn(n);
-        float vi = __fsub_rn(__fadd_rn(__fmul_rn(nf, q32), __fadd_rn(1.f, __fmul_rn(q32, -1.f))), 1.f);
-        if (n == 0) vi = 0.f;
+        float vi = (n > 0) ? __fmul_rn(__ull2float_rn(n - 1), q32) : 0.f;
         long long k0 = (long long)floorf(vi);
         float gamma = (float)((double)vi - (double)k0);
         long long k1 = k0 + 1;
@@ -315,7 +328,8 @@ __device__ void norm_resolve(NormState *__restrict__ st, double *__restrict__ no
         double n0 = 0.0, n1 = 0.0;
         if (n > 0) {
             const double dn = (double)n;
-            const float std_s = (float)sqrt(__ldcg(&st->ssd[0]) / dn), std_r = (float)sqrt(__ldcg(&st->ssd[1]) / dn);   // np.std(f32) -> f32
+            float std_s = (float)sqrt(__ldcg(&st->ssd[0]) / dn), std_r = (float)sqrt(__ldcg(&st->ssd[1]) / dn);   // np.std(f32) -> f32
+            if (__ldcg(&st->has_exact)) { std_s = __ldcg(&st->std_exact[0]); std_r = __ldcg(&st->std_exact[1]); }
             n0 = (double)__fdiv_rn(std_r, std_s);                                                      // :227
             const float t = st->gamma;
             float p[2];
@@ -375,14 +389,231 @@ __global__ void norm_init_kernel(NormState *st)
         for (int q = 0; q < 4; q++) { st->rank[q] = 0; st->prefix[q] = 0; }
         st->gamma = 0.f;
         st->ticket = 0u;
+        st->has_exact = 0u; st->n_comp = 0ull;
+        st->std_exact[0] = st->std_exact[1] = 0.f; st->meanf[0] = st->meanf[1] = 0.f;
+    }
+}
+
+// ---- numpy-exact float32 np.std ------------------------------------------------------------------------------------------
+constexpr int kCompChunk = 2048;              // pixels per compaction chunk (256 threads x 8 consecutive pixels)
+constexpr int kCompThreads = 256;
+constexpr long kExactMaxPixels = 1L << 28;    // above this the double-accumulated statistics are used
+constexpr int kTreeDepth = 10, kTreeThreads = 1 << kTreeDepth;
+
+// valid pixels per chunk
+__global__ void __launch_bounds__(kCompThreads)
+norm_count_kernel(const float *__restrict__ src, NoData nd_s, const float *__restrict__ ref, NoData nd_r, long n,
+                  unsigned int *__restrict__ chunk_cnt)
+{
+    const long base = (long)blockIdx.x * kCompChunk + (long)threadIdx.x * 8;
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const long i = base + j;
+        if (i < n) c += (hb_valid(__ldg(src + i), nd_s) && hb_valid(__ldg(ref + i), nd_r)) ? 1 : 0;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    __shared__ int s_w[kCompThreads / 32];
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < kCompThreads / 32; w++) tot += s_w[w];
+        chunk_cnt[blockIdx.x] = (unsigned int)tot;
+    }
+}
+
+// exclusive scan of the chunk counts (one CTA): chunk_off[c] = valid pixels before chunk c; total -> st->n_comp
+__global__ void __launch_bounds__(1024)
+norm_scan_kernel(const unsigned int *__restrict__ chunk_cnt, unsigned long long *__restrict__ chunk_off, long nchunks,
+                 NormState *__restrict__ st)
+{
+    __shared__ unsigned long long s_part[1024];
+    const long per = (nchunks + 1023) / 1024;
+    const long lo = (long)threadIdx.x * per, hi = min(lo + per, nchunks);
+    unsigned long long acc = 0;
+    for (long c = lo; c < hi; c++) acc += chunk_cnt[c];
+    s_part[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int t = 0; t < 1024; t++) { const unsigned long long v = s_part[t]; s_part[t] = run; run += v; }
+        st->n_comp = run;
+    }
+    __syncthreads();
+    unsigned long long run = s_part[threadIdx.x];
+    for (long c = lo; c < hi; c++) { chunk_off[c] = run; run += chunk_cnt[c]; }
+}
+
+// stream compaction in C order: comp[2 * k] = src, comp[2 * k + 1] = ref of the k-th valid pixel
+__global__ void __launch_bounds__(kCompThreads)
+norm_scatter_kernel(const float *__restrict__ src, NoData nd_s, const float *__restrict__ ref, NoData nd_r, long n,
+                    const unsigned long long *__restrict__ chunk_off, float2 *__restrict__ comp)
+{
+    const long base = (long)blockIdx.x * kCompChunk + (long)threadIdx.x * 8;
+    float sv[8], rv[8];
+    unsigned int vm = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const long i = base + j;
+        sv[j] = rv[j] = 0.f;
+        if (i < n) {
+            sv[j] = __ldg(src + i); rv[j] = __ldg(ref + i);
+            if (hb_valid(sv[j], nd_s) && hb_valid(rv[j], nd_r)) vm |= 1u << j;
+        }
+    }
+    const int mine = __popc(vm);
+    int incl = mine;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    __shared__ int s_w[kCompThreads / 32];
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; w++) woff += s_w[w];
+    unsigned long long dst = chunk_off[blockIdx.x] + (unsigned long long)(woff + incl - mine);
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (vm & (1u << j)) comp[dst++] = make_float2(sv[j], rv[j]);
+}
+
+// the leaf of numpy's pairwise recursion over [0, n) that contains position p
+__device__ __forceinline__ void pw_leaf_of(long n, long p, long &start, long &len)
+{
+    start = 0; len = n;
+    while (len > 128) {
+        long n2 = len / 2;
+        n2 -= n2 % 8;
+        if (p < start + n2) len = n2;
+        else { start += n2; len -= n2; }
+    }
+}
+
+// One thread per 64 positions; the thread at the first multiple of 64 inside a leaf (every leaf of a recursion over more
+// than 128 elements is 64 .. 128 long) sums that leaf in numpy's order.  SQDEV: sum (x - mean)^2 with numpy's float32
+// subtract and multiply instead of x.
+template <bool SQDEV>
+__global__ void __launch_bounds__(256)
+norm_leaf_kernel(const float2 *__restrict__ comp, const NormState *__restrict__ st, float2 *__restrict__ leaf)
+{
+    const long n = (long)st->n_comp;
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long p = t * 64;
+    if (p >= n) return;
+    long start, len;
+    pw_leaf_of(n, p, start, len);
+    if (p - start >= 64) return;                       // an earlier multiple of 64 lies inside this leaf
+    const float ms = SQDEV ? st->meanf[0] : 0.f, mr = SQDEV ? st->meanf[1] : 0.f;
+    auto term = [&](long i) -> float2 {
+        float2 v = comp[i];
+        if (SQDEV) {
+            const float ds = __fsub_rn(v.x, ms), dr = __fsub_rn(v.y, mr);
+            v = make_float2(__fmul_rn(ds, ds), __fmul_rn(dr, dr));
+        }
+        return v;
+    };
+    float2 res;
+    if (len < 8) {
+        res = make_float2(0.f, 0.f);
+        for (long i = 0; i < len; i++) { const float2 v = term(start + i); res.x = __fadd_rn(res.x, v.x); res.y = __fadd_rn(res.y, v.y); }
+    } else {
+        float2 r[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] = term(start + j);
+        long i = 8;
+        for (; i < len - (len % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const float2 v = term(start + i + j); r[j].x = __fadd_rn(r[j].x, v.x); r[j].y = __fadd_rn(r[j].y, v.y); }
+        }
+        res.x = __fadd_rn(__fadd_rn(__fadd_rn(r[0].x, r[1].x), __fadd_rn(r[2].x, r[3].x)),
+                          __fadd_rn(__fadd_rn(r[4].x, r[5].x), __fadd_rn(r[6].x, r[7].x)));
+        res.y = __fadd_rn(__fadd_rn(__fadd_rn(r[0].y, r[1].y), __fadd_rn(r[2].y, r[3].y)),
+                          __fadd_rn(__fadd_rn(r[4].y, r[5].y), __fadd_rn(r[6].y, r[7].y)));
+        for (; i < len; i++) { const float2 v = term(start + i); res.x = __fadd_rn(res.x, v.x); res.y = __fadd_rn(res.y, v.y); }
+    }
+    leaf[t] = res;
+}
+
+// sum of the recursion node [start, start + len) from the leaf sums (numpy: left + right)
+__device__ float2 pw_node_sum(const float2 *__restrict__ leaf, long start, long len)
+{
+    if (len <= 128) return leaf[(start + 63) / 64];
+    long n2 = len / 2;
+    n2 -= n2 % 8;
+    const float2 a = pw_node_sum(leaf, start, n2), b = pw_node_sum(leaf, start + n2, len - n2);
+    return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+}
+
+// Combine the leaves up numpy's tree (one CTA): thread t takes the node reached from the root by the bits of t (most
+// significant first), sums its subtree, and the top kTreeDepth levels are reduced pairwise in shared memory (left +
+// right).  A node that is already a leaf above that depth is held by the thread whose remaining bits are zero.
+// SQDEV = false: writes numpy's float32 means; true: the float32 standard deviations.
+template <bool SQDEV>
+__global__ void __launch_bounds__(kTreeThreads)
+norm_tree_kernel(const float2 *__restrict__ leaf, NormState *__restrict__ st)
+{
+    __shared__ float2 s_val[kTreeThreads];
+    __shared__ unsigned char s_has[kTreeThreads];
+    const long n = (long)st->n_comp;
+    const int t = threadIdx.x;
+    long start = 0, len = n;
+    bool mine = n > 0;
+    for (int level = 0; level < kTreeDepth && mine; level++) {
+        if (len <= 128) {                              // a leaf above the cut: only the all-zero suffix owns it
+            mine = (t & ((1 << (kTreeDepth - level)) - 1)) == 0;
+            break;
+        }
+        long n2 = len / 2;
+        n2 -= n2 % 8;
+        if ((t >> (kTreeDepth - 1 - level)) & 1) { start += n2; len -= n2; }
+        else len = n2;
+    }
+    s_has[t] = mine ? 1 : 0;
+    s_val[t] = mine ? pw_node_sum(leaf, start, len) : make_float2(0.f, 0.f);
+    __syncthreads();
+    for (int sdist = 1; sdist < kTreeThreads; sdist <<= 1) {
+        if ((t % (2 * sdist)) == 0 && s_has[t] && s_has[t + sdist]) {
+            const float2 a = s_val[t], b = s_val[t + sdist];
+            s_val[t] = make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+        }
+        __syncthreads();
+    }
+    if (t == 0 && n > 0) {
+        const double dn = (double)n;
+        // numpy divides the float32 sum by the integer count in double and stores float32 (_methods._var)
+        const float qs = (float)((double)s_val[0].x / dn), qr = (float)((double)s_val[0].y / dn);
+        if (!SQDEV) { st->meanf[0] = qs; st->meanf[1] = qr; }
+        else { st->std_exact[0] = __fsqrt_rn(qs); st->std_exact[1] = __fsqrt_rn(qr); st->has_exact = 1u; }
     }
 }
 
 }  // namespace
 
+namespace {
+struct ExactLayout { size_t off_comp, off_cnt, off_off, off_leaf, total; long nchunks, nleaf; };
+ExactLayout exact_layout(long n)
+{
+    ExactLayout L;
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    L.nchunks = (n + kCompChunk - 1) / kCompChunk;
+    L.nleaf = n / 64 + 2;
+    L.off_comp = al(sizeof(NormState));
+    L.off_cnt = L.off_comp + al((size_t)n * sizeof(float2));
+    L.off_off = L.off_cnt + al((size_t)L.nchunks * sizeof(unsigned int));
+    L.off_leaf = L.off_off + al((size_t)L.nchunks * sizeof(unsigned long long));
+    L.total = L.off_leaf + al((size_t)L.nleaf * sizeof(float2));
+    return L;
+}
+}  // namespace
+
 extern "C" size_t hb_block_norm_workspace_bytes(long n)
 {
-    (void)n;
+    if (n > 0 && n <= kExactMaxPixels) return exact_layout(n).total;
     return sizeof(NormState);
 }
 
@@ -440,6 +671,29 @@ extern "C" int hb_block_norm(const float *src_dev, int src_has_nodata, double sr
     NormState *state = (NormState *)workspace_dev;
     norm_init_kernel<<<1, 256, 0, st>>>(state);
     HB_LAUNCH_OK("norm_init_kernel");
+    if (n <= kExactMaxPixels && workspace_bytes >= exact_layout(n).total && ((uintptr_t)workspace_dev) % 256 == 0) {
+        // numpy-exact float32 standard deviations: compact the valid pixels in C order, replay numpy's pairwise sums
+        const ExactLayout L = exact_layout(n);
+        char *base = (char *)workspace_dev;
+        float2 *comp = (float2 *)(base + L.off_comp), *leaf = (float2 *)(base + L.off_leaf);
+        unsigned int *cnt = (unsigned int *)(base + L.off_cnt);
+        unsigned long long *off = (unsigned long long *)(base + L.off_off);
+        norm_count_kernel<<<(unsigned)L.nchunks, kCompThreads, 0, st>>>(src_dev, nd_s, ref_dev, nd_r, n, cnt);
+        HB_LAUNCH_OK("norm_count_kernel");
+        norm_scan_kernel<<<1, 1024, 0, st>>>(cnt, off, L.nchunks, state);
+        HB_LAUNCH_OK("norm_scan_kernel");
+        norm_scatter_kernel<<<(unsigned)L.nchunks, kCompThreads, 0, st>>>(src_dev, nd_s, ref_dev, nd_r, n, off, comp);
+        HB_LAUNCH_OK("norm_scatter_kernel");
+        const unsigned lgrid = (unsigned)((n / 64 + 1 + 255) / 256);
+        norm_leaf_kernel<false><<<lgrid, 256, 0, st>>>(comp, state, leaf);
+        HB_LAUNCH_OK("norm_leaf_kernel");
+        norm_tree_kernel<false><<<1, kTreeThreads, 0, st>>>(leaf, state);
+        HB_LAUNCH_OK("norm_tree_kernel");
+        norm_leaf_kernel<true><<<lgrid, 256, 0, st>>>(comp, state, leaf);
+        HB_LAUNCH_OK("norm_leaf_kernel");
+        norm_tree_kernel<true><<<1, kTreeThreads, 0, st>>>(leaf, state);
+        HB_LAUNCH_OK("norm_tree_kernel");
+    }
     for (int level = 0; level < 3; level++) {
         const int rc = norm_launch_level(level, src_dev, nd_s, ref_dev, nd_r, n, state, norm_dev, st);
         if (rc) return rc;

@@ -51,7 +51,7 @@ constexpr int kWarpW = 32 * kPpt;          // destination columns per warp
 constexpr int kRb = HB_POLY_RB;                     // rows per cp.async stage
 constexpr int kStages = HB_POLY_STAGES;                 // stages in flight per warp
 constexpr int kMaxRows = 128;              // destination rows per CTA (upper bound)
-constexpr int kRowTableBytes = kMaxRows * (16 + 4);   // per-CTA row table: 4 float y-weights + tap row per row
+constexpr int kRowTableBytes = kMaxRows * (16 + 4 + 4);   // per-CTA row table: 4 float y-weights + tap row + weight sum per row
 
 // ---- packed float32 pairs -------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
@@ -88,6 +88,7 @@ __device__ __forceinline__ float pk_lo(pk2 v) { float lo, hi; asm("mov.b64 {%0, 
 __device__ __forceinline__ float pk_hi(pk2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); (void)lo; return hi; }
 __device__ __forceinline__ pk2 pk_fma(pk2 a, pk2 b, pk2 c) { pk2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ pk2 pk_mul(pk2 a, pk2 b) { pk2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ pk2 pk_add(pk2 a, pk2 b) { pk2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
 // ---- geometry shared by the fast kernel and the fix-up kernel (identical expressions => identical cell indices) -----
 __device__ __forceinline__ double up_src_coord(double scale, double off, long i) { return scale * ((double)i + 0.5) + off; }
@@ -346,7 +347,7 @@ upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restric
     constexpr int kRowBytes = 32 * kLaneBytes;
     constexpr int kStageBytes = kRb * kRowBytes;
     constexpr int kRingBytes = kStages * kStageBytes;
-    constexpr int kWBytes = 5 * 32 * (int)sizeof(float4);                  // x-weights of one warp
+    constexpr int kWBytes = 6 * 32 * (int)sizeof(float4);                  // x-weights (+ their sums) of one warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long Y0 = (long)blockIdx.y * rows_per_cta;
@@ -356,6 +357,7 @@ upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restric
     // per-CTA row table: y-weights and first tap row (+1) of the CTA's destination rows
     RowEntry *s_rows = reinterpret_cast<RowEntry *>(smem_raw);
     int *s_ky = reinterpret_cast<int *>(smem_raw + kMaxRows * sizeof(RowEntry));
+    float *s_sy = reinterpret_cast<float *>(smem_raw + kMaxRows * (sizeof(RowEntry) + sizeof(int)));
     if ((int)threadIdx.x < nrows) {
         double wy[4];
         long ky;
@@ -365,6 +367,7 @@ upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restric
         for (int j = 0; j < 4; j++) e.wy[j] = (float)wy[j];
         s_rows[threadIdx.x] = e;
         s_ky[threadIdx.x] = (int)min(max(ky, -4L), g.hp + 4);
+        s_sy[threadIdx.x] = (float)(((wy[0] + wy[1]) + wy[2]) + wy[3]);      // exactly 1.0f unless taps were dropped
     }
     __syncthreads();                                        // the only CTA barrier
 
@@ -408,13 +411,14 @@ upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restric
     int col0 = 0;                                           // first tap column of the lane's window
     int cellA = 0, cellB = 0;                               // flag columns (kx + 1) of the lane's first / last pixel
     {
-        float w5[kPpt][5];
+        float w5[kPpt][5], sx[kPpt];
         long kx0 = 0;
 #pragma unroll
         for (int k = 0; k < kPpt; k++) {
             double wx[4];
             long kx;
             up_axis_weights(g.sx, g.ox, X0 + k, g.wp, wx, kx);
+            sx[k] = (float)(((wx[0] + wx[1]) + wx[2]) + wx[3]);
             if (k == 0) kx0 = kx;
             const bool sh = (kx != kx0);                    // the pixel's window starts 0 or 1 column into the lane's
             if (k == kPpt - 1) cellB = (int)min(max(kx + 1, -1L), g.wp + 2);
@@ -428,6 +432,7 @@ upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restric
         cellA = (int)min(max(kx0 + 1, -1L), g.wp + 2);
 #pragma unroll
         for (int i = 0; i < 5; i++) s_w[i * 32] = make_float4(w5[0][i], w5[1][i], w5[2][i], w5[3][i]);
+        s_w[5 * 32] = make_float4(sx[0], sx[1], sx[2], sx[3]);
     }
     const int fw = (int)g.wp + 2, hp = (int)g.hp, wp = (int)g.wp;
     // cells outside the flag table hold no pixel with an in-range centre: DEAD
@@ -439,7 +444,18 @@ upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restric
     const typename SrcQuad<T>::Key nd_key = SrcQuad<T>::key(nd);
     // x-interpolated tap rows per pixel PAIR and band.  CLEAN lanes: the interpolated values; DEAD lanes: NaN (so that
     // the row arithmetic produces nodata by itself); DIRTY lanes / lanes beyond the raster: stale, never stored.
+    //
+    // The taps are interpolated RELATIVE TO A BASE VALUE `base` (the coarse pixel at the centre of the lane's window):
+    //     sum_i w_i t_i  =  base * sum_i w_i  +  sum_i w_i (t_i - base)
+    // The parameter planes are smooth, so the second term is small and its float32 rounding errors vanish against the
+    // result, while the first is exact (sum_i w_i == 1.0f wherever no tap was dropped) -- the float32 parameter the
+    // reference gets from GDAL's double-precision accumulation comes out correctly rounded in all but near-tie cases,
+    // and gain * src + offset is then formed with numpy's two float32 roundings (kernel_model.py:461).
     float2 q[2][NB][4];
+    float base[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) base[b] = 0.f;
+    const float4 sx4 = s_w[5 * 32];
     int q_ky = INT_MIN;
     bool do_store = false;
     float *orow = out + Y0 * g.ws + X0;
@@ -449,6 +465,7 @@ upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restric
     // steps with only a few warps per scheduler to hide shared-memory latency behind)
     int ky_next = s_ky[0];
     RowEntry ri_next = s_rows[0];
+    float sy_next = s_sy[0];
 #pragma unroll 1
     for (int r = 0; r < nrows; r++, orow += out_pitch) {
         if (APPLY && (r & (kRb - 1)) == 0) {                // (warp-uniform) a new stage: keep the ring full, wait for it
@@ -457,10 +474,12 @@ upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restric
         }
         const int ky = ky_next;
         const RowEntry ri = ri_next;
+        const float sy = sy_next;
         {
             const int rn = min(r + 1, nrows - 1);
             ky_next = s_ky[rn];
             ri_next = s_rows[rn];
+            sy_next = s_sy[rn];
         }
         if (ky != q_ky) {                                   // (warp-uniform) new tap rows: re-classify, re-interpolate
             q_ky = ky;
@@ -505,6 +524,18 @@ upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restric
                     wp01[i] = make_float2(w.x, w.y);
                     wp23[i] = make_float2(w.z, w.w);
                 }
+                {
+                    // base: the coarse pixel at tap row 1, tap column 1 of the lane's window (inside the raster, hence
+                    // usable in a CLEAN cell)
+                    const long boff = (long)min(max(ky, 0), hp - 1) * wp + coff[1];
+                    if (NB == 2) {
+                        const float2 v = __ldg(reinterpret_cast<const float2 *>(coarse_v) + boff);
+                        base[0] = v.x;
+                        base[NB - 1] = v.y;
+                    } else {
+                        base[0] = __ldg(reinterpret_cast<const float *>(coarse_v) + boff);
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const long row_off = (long)min(max(ky - 1 + j, 0), hp - 1) * wp;
@@ -514,14 +545,14 @@ upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restric
 #pragma unroll
                         for (int i = 0; i < 5; i++) {
                             // (the 5th column has weight 0 when unused, but may be NaN: skip it)
-                            const float2 v = (i < 4 || five) ? __ldg(p + coff[i]) : make_float2(0.f, 0.f);
-                            t[0][i] = v.x;
-                            t[NB - 1][i] = v.y;
+                            const float2 v = (i < 4 || five) ? __ldg(p + coff[i]) : make_float2(base[0], base[NB - 1]);
+                            t[0][i] = __fsub_rn(v.x, base[0]);
+                            t[NB - 1][i] = __fsub_rn(v.y, base[NB - 1]);
                         }
                     } else {
                         const float *p = reinterpret_cast<const float *>(coarse_v) + row_off;
 #pragma unroll
-                        for (int i = 0; i < 5; i++) t[0][i] = (i < 4 || five) ? __ldg(p + coff[i]) : 0.f;
+                        for (int i = 0; i < 5; i++) t[0][i] = __fsub_rn((i < 4 || five) ? __ldg(p + coff[i]) : base[0], base[0]);
                     }
 #pragma unroll
                     for (int b = 0; b < NB; b++) {          // x-interpolation of tap row j at the lane's 4 pixel columns
@@ -542,12 +573,17 @@ upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restric
         float2 gv[2], ov[2];
 #pragma unroll
         for (int p = 0; p < 2; p++) {
-            gv[p] = ffma2(q[p][0][3], w3, ffma2(q[p][0][2], w2, ffma2(q[p][0][1], w1, fmul2(q[p][0][0], w0))));
-            if (NB > 1)
-                ov[p] = ffma2(q[p][NB - 1][3], w3, ffma2(q[p][NB - 1][2], w2, ffma2(q[p][NB - 1][1], w1,
-                              fmul2(q[p][NB - 1][0], w0))));
-            else
+            // weight sum of the pixel = (sum of its x-weights) * (sum of the row's y-weights): 1.0f away from the edges
+            const float2 wsum = fmul2(p == 0 ? make_float2(sx4.x, sx4.y) : make_float2(sx4.z, sx4.w), splat(sy));
+            const float2 dg = ffma2(q[p][0][3], w3, ffma2(q[p][0][2], w2, ffma2(q[p][0][1], w1, fmul2(q[p][0][0], w0))));
+            gv[p] = ffma2(splat(base[0]), wsum, dg);
+            if (NB > 1) {
+                const float2 dof = ffma2(q[p][NB - 1][3], w3, ffma2(q[p][NB - 1][2], w2, ffma2(q[p][NB - 1][1], w1,
+                                         fmul2(q[p][NB - 1][0], w0))));
+                ov[p] = ffma2(splat(base[NB - 1]), wsum, dof);
+            } else {
                 ov[p] = splat(0.f);
+            }
         }
         float4 res[NOUT];
         if constexpr (APPLY) {
@@ -555,7 +591,8 @@ upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restric
             bool ok[4];
             SrcQuad<T>::get_shared(ring_rd, nd_key, s, ok);
             ring_rd = (ring_rd + kRowBytes == ring_sa + kRingBytes) ? ring_sa : ring_rd + kRowBytes;
-            const float2 c0 = ffma2(gv[0], s[0], ov[0]), c1 = ffma2(gv[1], s[1], ov[1]);   // corr = gain*src + offset
+            // corr = gain * src + offset with numpy's two float32 roundings (kernel_model.py:461)
+            const float2 c0 = fadd2(fmul2(gv[0], s[0]), ov[0]), c1 = fadd2(fmul2(gv[1], s[1]), ov[1]);
             res[0] = make_float4(ok[0] ? c0.x : qnan, ok[1] ? c0.y : qnan, ok[2] ? c1.x : qnan, ok[3] ? c1.y : qnan);
         } else {
             res[0] = make_float4(gv[0].x, gv[0].y, gv[1].x, gv[1].y);
@@ -762,8 +799,9 @@ upsample_yfirst_kernel(const T *__restrict__ src, NoData nd, const void *__restr
             bool ok[4];
             SrcQuad<T>::get_shared(ring_rd, nd_key, s, ok);
             ring_rd = (ring_rd + kRowBytes == ring_sa + kRingBytes) ? ring_sa : ring_rd + kRowBytes;
-            const pk2 c0 = pk_fma(o[0][0], pk(s[0].x, s[0].y), o[NB - 1][0]);   // corr = gain*src + offset
-            const pk2 c1 = pk_fma(o[0][1], pk(s[1].x, s[1].y), o[NB - 1][1]);
+            // corr = gain * src + offset with numpy's two float32 roundings (kernel_model.py:461)
+            const pk2 c0 = pk_add(pk_mul(o[0][0], pk(s[0].x, s[0].y)), o[NB - 1][0]);
+            const pk2 c1 = pk_add(pk_mul(o[0][1], pk(s[1].x, s[1].y)), o[NB - 1][1]);
             res[0] = make_float4(ok[0] ? pk_lo(c0) : qnan, ok[1] ? pk_hi(c0) : qnan, ok[2] ? pk_lo(c1) : qnan,
                                  ok[3] ? pk_hi(c1) : qnan);
         } else {
@@ -1083,7 +1121,7 @@ upsample_fixup_kernel(const T *__restrict__ src, NoData nd, const float *__restr
                         }
                     }
                     if (APPLY) {
-                        out[Y * g.ws + X] = fmaf(r[0], s, r[NB - 1]);
+                        out[Y * g.ws + X] = __fadd_rn(__fmul_rn(r[0], s), r[NB - 1]);   // two roundings, as numpy
                     } else {
                         out[Y * g.ws + X] = r[0];
                         if constexpr (NOUT == 2) out[g.hs * g.ws + Y * g.ws + X] = r[1];
@@ -1166,7 +1204,7 @@ int launch_poly(const void *src, NoData nd, const float *coarse, const UpPolyGeo
         // a lane spanning 3 coarse cells (fewer than ~3.4 destination pixels per coarse pixel): the "y first" kernel
         const bool yfirst = (g.sx > 0.3);
         const size_t ring = APPLY ? (size_t)kStages * kRb * 32 * kPpt * sizeof(T) : 0;
-        const size_t smem = kRowTableBytes + ((yfirst ? kYfCols : 5) * 32 * sizeof(float4) + ring) * kWarps;
+        const size_t smem = kRowTableBytes + ((yfirst ? kYfCols : 6) * 32 * sizeof(float4) + ring) * kWarps;
         const long cta_w = (long)kWarpW * kWarps;
         const long gx = (g.ws + cta_w - 1) / cta_w;
         auto kern = yfirst ? upsample_yfirst_kernel<T, NB, APPLY> : upsample_poly_kernel<T, NB, APPLY>;

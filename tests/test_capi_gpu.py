@@ -137,7 +137,8 @@ def test_block_norm():
     _, kmnp = _oracle()
     lib = _native.lib()
     rng = np.random.default_rng(5)
-    for n, nodata in ((1, NAN), (7, NAN), (1000, NAN), (250_000, 0.0), (1_000_003, NAN)):
+    for n, nodata in ((1, NAN), (7, NAN), (9, NAN), (129, NAN), (1000, NAN), (4097, 0.0), (250_000, 0.0), (1_000_003, NAN),
+                      (9_000_000, NAN)):
         src = rng.normal(3000, 900, n).astype('float32')
         ref = (0.7 * src + 100 + rng.normal(0, 30, n)).astype('float32')
         bad = rng.random(n) < 0.05
@@ -159,11 +160,10 @@ def test_block_norm():
         if n == 1:
             assert np.isnan(got[0]) == np.isnan(expected[0])      # std == 0 -> 0/0
             continue
-        # norm[0]: numpy's float32 np.std is good to ~1e-6; norm[1] = P1(ref) - P1(src) * norm[0] is a difference of
-        # O(3000 * 0.7) terms, so its error scales with those terms, not with its own size
-        assert got[0] == pytest.approx(expected[0], rel=2e-6), (n, got, expected)
-        scale = max(abs(np.percentile(ref[mask], 1)), abs(np.percentile(src[mask], 1) * expected[0]))
-        assert abs(got[1] - expected[1]) <= 4e-6 * scale, (n, got, expected)
+        # bit for bit: the float32 standard deviations replay numpy's pairwise summation (np.std of `array[mask]`), the
+        # order statistics are exact and the interpolation follows numpy's float32 arithmetic
+        assert got[0] == expected[0], (n, got, expected)
+        assert got[1] == expected[1], (n, got, expected)
 
 
 def test_block_norm_empty_mask():

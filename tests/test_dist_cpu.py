@@ -171,7 +171,7 @@ class _NumpyBlockNorm:
                 return
             self.mean = [acc[1] / self.n, acc[2] / self.n]
             q32 = np.float32(1) / np.float32(100)
-            vi = np.float32(np.float32(np.float32(self.n) * q32) + np.float32(np.float32(1) - q32)) - np.float32(1)
+            vi = np.float32(np.float32(self.n - 1) * q32)          # numpy's 'linear' method: (n - 1) * q in float32
             k0 = int(np.floor(vi))
             self.gamma = np.float32(float(vi) - k0)
             last = self.n - 1
