@@ -18,7 +18,7 @@ from homonim_b200.errors import NativeLibraryError
 HB_U8, HB_U16, HB_F32, HB_I16 = 0, 1, 2, 3
 HB_MODEL_GAIN, HB_MODEL_GAIN_BLK_OFFSET, HB_MODEL_GAIN_OFFSET = 0, 1, 2
 HB_UP_CUBIC_SPLINE, HB_UP_NEAREST = 0, 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _PKG_DIR = pathlib.Path(__file__).resolve().parent
 LIB_PATH = _PKG_DIR / 'libhomonim_b200.so'
@@ -45,18 +45,19 @@ SIGNATURES = {
     'hb_fit_same_grid': (c_int, [c_void_p, c_int, c_double, c_void_p, c_int, c_double, c_long, c_long, c_int, c_int,
                                  c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'hb_fit_apply_same_grid': (c_int, [c_void_p, c_int, c_double, c_void_p, c_int, c_double, c_long, c_long, c_int,
-                                       c_int, c_int, c_void_p, c_void_p, c_void_p]),
+                                       c_int, c_int, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),
     'hb_fit_same_grid_rows': (c_int, [c_void_p, c_int, c_double, c_void_p, c_int, c_double, c_long, c_long, c_long,
                                       c_long, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'hb_fit_apply_same_grid_rows': (c_int, [c_void_p, c_int, c_double, c_void_p, c_int, c_double, c_long, c_long,
-                                            c_long, c_long, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+                                            c_long, c_long, c_int, c_int, c_int, c_void_p, c_int, c_int, c_double,
+                                            c_void_p, c_void_p]),
     'hb_inpaint_workspace_bytes': (c_size_t, [c_long, c_long]),
     'hb_inpaint_refit': (c_int, [c_void_p, c_void_p, c_long, c_long, c_double, c_double, c_void_p, c_size_t,
                                  c_void_p]),
-    'hb_apply_same_grid': (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_void_p, c_long, c_long, c_void_p,
-                                   c_void_p]),
+    'hb_apply_same_grid': (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_void_p, c_long, c_long, c_int, c_int,
+                                   c_double, c_void_p, c_void_p]),
     'hb_upsample_apply': (c_int, [c_void_p, c_int, c_long, c_long, c_int, c_double, c_void_p, c_long, c_long, c_double,
-                                  c_double, c_double, c_double, c_void_p, c_void_p, c_void_p]),
+                                  c_double, c_double, c_double, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),
     'hb_resample_up': (c_int, [c_void_p, c_long, c_long, c_long, c_int, c_double, c_void_p, c_long, c_long, c_double,
                                c_double, c_double, c_double, c_int, c_void_p]),
     'hb_full_coverage_mask': (c_int, [c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_double, c_double, c_double,
@@ -68,10 +69,10 @@ SIGNATURES = {
                                 c_size_t, c_void_p]),
     'hb_fuse_refspace': (c_int, [c_void_p, c_int, c_long, c_long, c_int, c_double, c_void_p, c_long, c_long, c_int,
                                  c_double, c_double, c_double, c_double, c_double, c_int, c_int, c_int, c_int, c_int,
-                                 c_double, c_void_p, c_void_p, c_void_p]),
+                                 c_double, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]),
     'hb_fuse_refspace_host': (c_int, [c_void_p, c_int, c_long, c_long, c_int, c_double, c_void_p, c_long, c_long,
                                       c_int, c_double, c_double, c_double, c_double, c_double, c_int, c_int, c_int,
-                                      c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]),
+                                      c_int, c_int, c_double, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]),
 }
 
 

@@ -55,8 +55,8 @@ struct DevBuf {
 static int fuse_refspace_direct(const void *src_dev, int src_dtype, long hs, long ws, int src_has_nodata,
                                 double src_nodata, const float *ref_dev, long hr, long wr, int ref_has_nodata,
                                 double ref_nodata, double sx, double ox, double sy, double oy, int model, int kh, int kw,
-                                int want_r2, int do_inpaint, double r2_thresh, float *corr_dev, float *params_dev,
-                                void *stream)
+                                int want_r2, int do_inpaint, double r2_thresh, int out_dtype, int out_has_nodata,
+                                double out_nodata, void *corr_dev, float *params_dev, void *stream)
 {
     HB_REQUIRE(src_dev && ref_dev && corr_dev && hs > 0 && ws > 0 && hr > 0 && wr > 0, "hb_fuse_refspace: bad arguments");
     HB_REQUIRE(src_dtype == HB_U8 || src_dtype == HB_U16 || src_dtype == HB_F32, "hb_fuse_refspace: bad dtype");
@@ -101,7 +101,7 @@ static int fuse_refspace_direct(const void *src_dev, int src_dtype, long hs, lon
     }
     // source grid -> reference (param) grid is the inverse of the reference -> source map
     return hb_upsample_apply(src_dev, src_dtype, hs, ws, src_has_nodata, src_nodata, params, hr, wr, 1.0 / sx, -ox / sx,
-                             1.0 / sy, -oy / sy, nullptr, corr_dev, stream);
+                             1.0 / sy, -oy / sy, nullptr, out_dtype, out_has_nodata, out_nodata, corr_dev, stream);
 }
 
 // ---- CUDA-graph replay of repeated identical calls (opt-in: HOMONIM_B200_GRAPHS=1) ------------------------------------
@@ -115,10 +115,10 @@ static int fuse_refspace_direct(const void *src_dev, int src_dtype, long hs, lon
 // the direct path is not host-bound there.
 namespace {
 struct FuseKey {
-    const void *src; const float *ref; float *corr, *params;
+    const void *src; const float *ref; void *corr; float *params;
     long hs, ws, hr, wr;
-    double src_nodata, ref_nodata, sx, ox, sy, oy, r2_thresh;
-    int src_dtype, src_has_nodata, ref_has_nodata, model, kh, kw, want_r2, do_inpaint, device;
+    double src_nodata, ref_nodata, sx, ox, sy, oy, r2_thresh, out_nodata;
+    int src_dtype, src_has_nodata, ref_has_nodata, model, kh, kw, want_r2, do_inpaint, device, out_dtype, out_has_nodata;
     bool operator==(const FuseKey &o) const { return memcmp(this, &o, sizeof(FuseKey)) == 0; }
 };
 struct FuseGraph { FuseKey key; cudaGraphExec_t exec; long launches; unsigned long long last_use; int seen; };
@@ -142,11 +142,12 @@ bool graphs_enabled()
 extern "C" int hb_fuse_refspace(const void *src_dev, int src_dtype, long hs, long ws, int src_has_nodata,
                                 double src_nodata, const float *ref_dev, long hr, long wr, int ref_has_nodata,
                                 double ref_nodata, double sx, double ox, double sy, double oy, int model, int kh, int kw,
-                                int want_r2, int do_inpaint, double r2_thresh, float *corr_dev, float *params_dev,
-                                void *stream)
+                                int want_r2, int do_inpaint, double r2_thresh, int out_dtype, int out_has_nodata,
+                                double out_nodata, void *corr_dev, float *params_dev, void *stream)
 {
 #define HB_FUSE_ARGS src_dev, src_dtype, hs, ws, src_has_nodata, src_nodata, ref_dev, hr, wr, ref_has_nodata, ref_nodata, \
-                     sx, ox, sy, oy, model, kh, kw, want_r2, do_inpaint, r2_thresh, corr_dev, params_dev, stream
+                     sx, ox, sy, oy, model, kh, kw, want_r2, do_inpaint, r2_thresh, out_dtype, out_has_nodata, out_nodata, \
+                     corr_dev, params_dev, stream
     cudaStream_t st = (cudaStream_t)stream;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (!graphs_enabled() || cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
@@ -157,6 +158,7 @@ extern "C" int hb_fuse_refspace(const void *src_dev, int src_dtype, long hs, lon
     key.hs = hs; key.ws = ws; key.hr = hr; key.wr = wr;
     key.src_nodata = src_nodata; key.ref_nodata = ref_nodata; key.sx = sx; key.ox = ox; key.sy = sy; key.oy = oy;
     key.r2_thresh = r2_thresh;
+    key.out_nodata = out_nodata; key.out_dtype = out_dtype; key.out_has_nodata = out_has_nodata;
     key.src_dtype = src_dtype; key.src_has_nodata = src_has_nodata; key.ref_has_nodata = ref_has_nodata;
     key.model = model; key.kh = kh; key.kw = kw; key.want_r2 = want_r2; key.do_inpaint = do_inpaint;
     if (cudaGetDevice(&key.device) != cudaSuccess) return fuse_refspace_direct(HB_FUSE_ARGS);
@@ -237,8 +239,9 @@ extern "C" int hb_fuse_refspace(const void *src_dev, int src_dtype, long hs, lon
 extern "C" int hb_fuse_refspace_host(const void *src_host, int src_dtype, long hs, long ws, int src_has_nodata,
                                      double src_nodata, const float *ref_host, long hr, long wr, int ref_has_nodata,
                                      double ref_nodata, double sx, double ox, double sy, double oy, int model, int kh,
-                                     int kw, int want_r2, int do_inpaint, double r2_thresh, float *corr_host,
-                                     float *params_host, void *stream)
+                                     int kw, int want_r2, int do_inpaint, double r2_thresh, int out_dtype,
+                                     int out_has_nodata, double out_nodata, void *corr_host, float *params_host,
+                                     void *stream)
 {
     HB_REQUIRE(src_host && ref_host && corr_host && hs > 0 && ws > 0 && hr > 0 && wr > 0,
                "hb_fuse_refspace_host: bad arguments");
@@ -253,14 +256,18 @@ extern "C" int hb_fuse_refspace_host(const void *src_host, int src_dtype, long h
     HB_CUDA_OK(d_src.alloc(src_bytes));
     HB_CUDA_OK(d_ref.alloc(nr * sizeof(float)));
     HB_CUDA_OK(d_params.alloc(nr * sizeof(float) * 3));
-    HB_CUDA_OK(d_corr.alloc(ns * sizeof(float)));
+    HB_REQUIRE(hb_outspec_error(out_dtype, out_has_nodata, out_nodata) == nullptr, "hb_fuse_refspace_host: %s",
+               hb_outspec_error(out_dtype, out_has_nodata, out_nodata));
+    const size_t corr_bytes = ns * hb_out_size(out_dtype);
+    HB_CUDA_OK(d_corr.alloc(corr_bytes));
     HB_CUDA_OK(cudaMemcpyAsync(d_src.p, src_host, src_bytes, cudaMemcpyHostToDevice, st));
     HB_CUDA_OK(cudaMemcpyAsync(d_ref.p, ref_host, nr * sizeof(float), cudaMemcpyHostToDevice, st));
     const int rc = hb_fuse_refspace(d_src.p, src_dtype, hs, ws, src_has_nodata, src_nodata, (const float *)d_ref.p, hr, wr,
                                     ref_has_nodata, ref_nodata, sx, ox, sy, oy, model, kh, kw, want_r2, do_inpaint,
-                                    r2_thresh, (float *)d_corr.p, (float *)d_params.p, stream);
+                                    r2_thresh, out_dtype, out_has_nodata, out_nodata, d_corr.p, (float *)d_params.p,
+                                    stream);
     if (rc) return rc;
-    HB_CUDA_OK(cudaMemcpyAsync(corr_host, d_corr.p, ns * sizeof(float), cudaMemcpyDeviceToHost, st));
+    HB_CUDA_OK(cudaMemcpyAsync(corr_host, d_corr.p, corr_bytes, cudaMemcpyDeviceToHost, st));
     if (params_host)
         HB_CUDA_OK(cudaMemcpyAsync(params_host, d_params.p, nr * sizeof(float) * (r2 ? 3 : 2), cudaMemcpyDeviceToHost,
                                    st));

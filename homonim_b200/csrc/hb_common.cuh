@@ -112,6 +112,72 @@ __device__ __forceinline__ void hb_stg_stream16(void *p, float4 v)
                  : "memory");
 }
 
+// ---- output dtype of a corrected plane, fused into the apply kernels' stores ---------------------------------------------
+// RasterArray._convert_array_dtype (raster_array.py:353-387) as used by to_rio_dataset (:493-500): integer outputs are
+// rounded half-to-even (np.round) and clipped to the type's range, NaN (the corrected image's nodata) becomes the output
+// nodata value (0 when there is none); float32 output only substitutes the nodata value.
+struct OutSpec {
+    int dtype;      // HB_U8 / HB_U16 / HB_I16 / HB_F32
+    int plain;      // float32 with NaN nodata: store the values as they are
+    float nd;       // output nodata as float (integer types: cast on store)
+    float lo, hi;   // clip range of the integer types
+};
+
+static inline OutSpec hb_make_outspec(int out_dtype, int has_nodata, double nodata)
+{
+    OutSpec o;
+    o.dtype = out_dtype;
+    o.nd = has_nodata ? (float)nodata : (out_dtype == HB_F32 ? __builtin_nanf("") : 0.f);
+    o.plain = (out_dtype == HB_F32 && o.nd != o.nd) ? 1 : 0;
+    o.lo = (out_dtype == HB_I16) ? -32768.f : 0.f;
+    o.hi = (out_dtype == HB_U8) ? 255.f : (out_dtype == HB_I16 ? 32767.f : 65535.f);
+    return o;
+}
+static inline const char *hb_outspec_error(int out_dtype, int has_nodata, double nodata)
+{
+    if (out_dtype != HB_U8 && out_dtype != HB_U16 && out_dtype != HB_I16 && out_dtype != HB_F32) return "unsupported output dtype";
+    if (out_dtype != HB_F32 && has_nodata) {
+        const double lo = (out_dtype == HB_I16) ? -32768.0 : 0.0, hi = (out_dtype == HB_U8) ? 255.0 : (out_dtype == HB_I16 ? 32767.0 : 65535.0);
+        if (!(nodata >= lo && nodata <= hi && nodata == floor(nodata))) return "output nodata cannot be safely cast to the output dtype";
+    }
+    return nullptr;
+}
+static inline size_t hb_out_size(int out_dtype) { return out_dtype == HB_U8 ? 1 : (out_dtype == HB_F32 ? 4 : 2); }
+
+__device__ __forceinline__ int hb_out_int(float v, const OutSpec &o)
+{
+    const float r = fminf(fmaxf(rintf(v), o.lo), o.hi);
+    return (v != v) ? (int)o.nd : (int)r;
+}
+// 4 adjacent pixels starting at pixel index `pix` (a multiple of 4; the plane is 16 / 8 / 4-byte aligned accordingly)
+__device__ __forceinline__ void hb_store4_out(void *base, long pix, float4 v, const OutSpec &o)
+{
+    if (o.plain) {
+        hb_stg_stream16(reinterpret_cast<float *>(base) + pix, v);
+    } else if (o.dtype == HB_F32) {
+        hb_stg_stream16(reinterpret_cast<float *>(base) + pix,
+                        make_float4(v.x != v.x ? o.nd : v.x, v.y != v.y ? o.nd : v.y, v.z != v.z ? o.nd : v.z,
+                                    v.w != v.w ? o.nd : v.w));
+    } else {
+        const unsigned a = (unsigned)hb_out_int(v.x, o), b = (unsigned)hb_out_int(v.y, o), c = (unsigned)hb_out_int(v.z, o),
+                       d = (unsigned)hb_out_int(v.w, o);
+        if (o.dtype == HB_U8) {
+            const unsigned w = (a & 0xffu) | ((b & 0xffu) << 8) | ((c & 0xffu) << 16) | (d << 24);
+            asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(reinterpret_cast<unsigned char *>(base) + pix), "r"(w) : "memory");
+        } else {
+            const unsigned w0 = (a & 0xffffu) | (b << 16), w1 = (c & 0xffffu) | (d << 16);
+            asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(reinterpret_cast<unsigned short *>(base) + pix), "r"(w0), "r"(w1)
+                         : "memory");
+        }
+    }
+}
+__device__ __forceinline__ void hb_store1_out(void *base, long pix, float v, const OutSpec &o)
+{
+    if (o.dtype == HB_F32) reinterpret_cast<float *>(base)[pix] = (!o.plain && v != v) ? o.nd : v;
+    else if (o.dtype == HB_U8) reinterpret_cast<unsigned char *>(base)[pix] = (unsigned char)hb_out_int(v, o);
+    else reinterpret_cast<unsigned short *>(base)[pix] = (unsigned short)hb_out_int(v, o);
+}
+
 // Stream-ordered scratch (cudaMallocAsync) comes from the device's default memory pool.  By default the pool hands
 // freed memory back to the OS at every synchronisation, so that each call would pay for a fresh allocation; keep it.
 static inline cudaError_t hb_pool_keep_memory()

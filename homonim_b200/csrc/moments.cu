@@ -37,6 +37,7 @@ struct FitGeom {
     int rows_per_band;
     long row0, nrows;  // output rows [row0, row0 + nrows) of the plane; output arrays hold just these rows
     int aligned;       // planes are 16-byte aligned and w % 4 == 0: 16-byte loads / stores
+    OutSpec ospec;     // FUSED: output dtype / nodata of the corrected plane (conversion fused into the store)
 };
 
 // L2 residency hints.  Every input row is read twice by a CTA: when it enters the kh-row window and, kh rows later, when
@@ -139,7 +140,7 @@ template <int MODEL, bool WANT_R2, int NQ, int C, bool FUSED>
 __global__ void __launch_bounds__(kFitThreads, (NQ >= 5 && C == 4) ? HB_FIT_MIN_CTAS - 1 : HB_FIT_MIN_CTAS)
 fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__restrict__ ref, NoData nd_r,
                      FitGeom g, const double *__restrict__ norm, float *__restrict__ params,
-                     float *__restrict__ sums_out, float *__restrict__ corr_out)
+                     float *__restrict__ sums_out, float *__restrict__ corr_out)   // (corr_out: g.ospec.dtype elements)
 {
     constexpr bool NORM = (MODEL == HB_MODEL_GAIN_BLK_OFFSET);
     constexpr bool HAS_N = (NQ > 2);
@@ -465,13 +466,14 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
             float oc[C];
 #pragma unroll
             for (int i = 0; i < C; i++) oc[i] = __fadd_rn(__fmul_rn(o_gain[i], sc[i]), o_off[i]);
-            float *crow = corr_out + yo * g.w + cx;
+            const long cpix = yo * g.w + cx;                         // pixel index in the corrected plane
             if (vec_ok) {
-                hb_stg16_stream(crow, make_float4(oc[0], oc[C > 1 ? 1 : 0], oc[C > 2 ? 2 : 0], oc[C > 3 ? 3 : 0]));
+                hb_store4_out(corr_out, cpix, make_float4(oc[0], oc[C > 1 ? 1 : 0], oc[C > 2 ? 2 : 0], oc[C > 3 ? 3 : 0]),
+                              g.ospec);
             } else {
 #pragma unroll
                 for (int i = 0; i < C; i++)
-                    if ((cmask >> i) & 1u) crow[i] = oc[i];
+                    if ((cmask >> i) & 1u) hb_store1_out(corr_out, cpix + i, oc[i], g.ospec);
             }
         } else {
             float *prow = params + yo * g.w + cx;
@@ -507,10 +509,11 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
 
 template <int MODEL, bool WANT_R2, int NQ, int C>
 int launch_fit(const float *src, NoData nd_s, const float *ref, NoData nd_r, long h, long w, long row0, long nrows,
-               int kh, int kw, const double *norm, float *params, float *sums, float *corr, cudaStream_t stream)
+               int kh, int kw, const double *norm, float *params, float *sums, float *corr, OutSpec ospec,
+               cudaStream_t stream)
 {
     FitGeom g;
-    g.h = h; g.w = w; g.kh = kh; g.kw = kw; g.row0 = row0; g.nrows = nrows;
+    g.h = h; g.w = w; g.kh = kh; g.kw = kw; g.row0 = row0; g.nrows = nrows; g.ospec = ospec;
     const int hw = kw / 2;
     g.hw_al = ((hw + C - 1) / C) * C;
     g.tw_out = kFitThreads * C - 2 * g.hw_al;
@@ -548,7 +551,7 @@ int launch_fit(const float *src, NoData nd_s, const float *ref, NoData nd_r, lon
     g.aligned = ((C == 4) && (w % 4 == 0) && (((uintptr_t)src) % 16 == 0) && (((uintptr_t)ref) % 16 == 0) &&
                  (params == nullptr || ((uintptr_t)params) % 16 == 0) &&
                  (sums == nullptr || ((uintptr_t)sums) % 16 == 0) &&
-                 (corr == nullptr || ((uintptr_t)corr) % 16 == 0)) ? 1 : 0;
+                 (corr == nullptr || ((uintptr_t)corr) % (4 * hb_out_size(ospec.dtype)) == 0)) ? 1 : 0;
     if (corr != nullptr) {
         if constexpr (!WANT_R2)
             fit_same_grid_kernel<MODEL, false, NQ, C, true><<<grid, kFitThreads, 0, stream>>>(src, nd_s, ref, nd_r, g, norm,
@@ -565,16 +568,17 @@ int launch_fit(const float *src, NoData nd_s, const float *ref, NoData nd_r, lon
 
 template <int MODEL, bool WANT_R2, int NQ>
 int launch_fit_c(const float *src, NoData nd_s, const float *ref, NoData nd_r, long h, long w, long row0, long nrows,
-                 int kh, int kw, const double *norm, float *params, float *sums, float *corr, cudaStream_t stream)
+                 int kh, int kw, const double *norm, float *params, float *sums, float *corr, OutSpec ospec,
+                 cudaStream_t stream)
 {
     // small rasters: 1 column per thread (128-column strips) so that the grid still spreads over the SMs.  A window
     // may span at most two warps (one warp total in the look-up): 32-column warps carry kernels up to 31 wide,
     // 128-column warps up to 127.
     if (nrows * w < ((long)4 << 20) && kw <= 31)
         return launch_fit<MODEL, WANT_R2, NQ, 1>(src, nd_s, ref, nd_r, h, w, row0, nrows, kh, kw, norm, params, sums,
-                                                 corr, stream);
+                                                 corr, ospec, stream);
     return launch_fit<MODEL, WANT_R2, NQ, 4>(src, nd_s, ref, nd_r, h, w, row0, nrows, kh, kw, norm, params, sums, corr,
-                                             stream);
+                                             ospec, stream);
 }
 
 }  // namespace
@@ -582,7 +586,7 @@ int launch_fit_c(const float *src, NoData nd_s, const float *ref, NoData nd_r, l
 static int fit_dispatch(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
                         int ref_has_nodata, double ref_nodata, long h, long w, long row0, long nrows, int model, int kh,
                         int kw, int want_r2, const double *norm_dev, float *params_dev, float *sums_dev, float *corr_dev,
-                        void *stream, const char *who)
+                        void *stream, const char *who, OutSpec ospec = hb_make_outspec(HB_F32, 0, 0.0))
 {
     HB_REQUIRE(src_dev && ref_dev && (params_dev || corr_dev) && h > 0 && w > 0, "%s: bad arguments", who);
     HB_REQUIRE(row0 >= 0 && nrows > 0 && row0 + nrows <= h, "%s: output rows [%ld, %ld) outside the %ld-row plane", who,
@@ -597,22 +601,22 @@ static int fit_dispatch(const float *src_dev, int src_has_nodata, double src_nod
         case HB_MODEL_GAIN:
             HB_REQUIRE(sums_dev == nullptr, "%s: sums are only produced for the gain-offset model", who);
             if (want_r2)
-                return launch_fit_c<HB_MODEL_GAIN, true, 5>(HB_FIT_ARGS, nullptr, params_dev, nullptr, corr_dev, st);
-            return launch_fit_c<HB_MODEL_GAIN, false, 2>(HB_FIT_ARGS, nullptr, params_dev, nullptr, corr_dev, st);
+                return launch_fit_c<HB_MODEL_GAIN, true, 5>(HB_FIT_ARGS, nullptr, params_dev, nullptr, corr_dev, ospec, st);
+            return launch_fit_c<HB_MODEL_GAIN, false, 2>(HB_FIT_ARGS, nullptr, params_dev, nullptr, corr_dev, ospec, st);
         case HB_MODEL_GAIN_BLK_OFFSET:
             HB_REQUIRE(norm_dev != nullptr, "%s: gain-blk-offset needs the block normalisation", who);
             HB_REQUIRE(sums_dev == nullptr, "%s: sums are only produced for the gain-offset model", who);
             if (want_r2)
                 return launch_fit_c<HB_MODEL_GAIN_BLK_OFFSET, true, 5>(HB_FIT_ARGS, norm_dev, params_dev, nullptr,
-                                                                       corr_dev, st);
+                                                                       corr_dev, ospec, st);
             return launch_fit_c<HB_MODEL_GAIN_BLK_OFFSET, false, 2>(HB_FIT_ARGS, norm_dev, params_dev, nullptr,
-                                                                    corr_dev, st);
+                                                                    corr_dev, ospec, st);
         case HB_MODEL_GAIN_OFFSET:
             if (want_r2)
                 return launch_fit_c<HB_MODEL_GAIN_OFFSET, true, 5>(HB_FIT_ARGS, nullptr, params_dev, sums_dev, corr_dev,
-                                                                   st);
+                                                                   ospec, st);
             return launch_fit_c<HB_MODEL_GAIN_OFFSET, false, 4>(HB_FIT_ARGS, nullptr, params_dev, sums_dev, corr_dev,
-                                                                st);
+                                                                ospec, st);
     }
 #undef HB_FIT_ARGS
     HB_REQUIRE(false, "%s: unknown model %d", who, model);
@@ -640,19 +644,27 @@ extern "C" int hb_fit_same_grid_rows(const float *src_dev, int src_has_nodata, d
 
 extern "C" int hb_fit_apply_same_grid(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
                                       int ref_has_nodata, double ref_nodata, long h, long w, int model, int kh, int kw,
-                                      const double *norm_dev, float *corr_dev, void *stream)
+                                      const double *norm_dev, int out_dtype, int out_has_nodata, double out_nodata,
+                                      void *corr_dev, void *stream)
 {
     HB_REQUIRE(corr_dev != nullptr, "hb_fit_apply_same_grid: bad arguments");
+    HB_REQUIRE(hb_outspec_error(out_dtype, out_has_nodata, out_nodata) == nullptr, "hb_fit_apply_same_grid: %s",
+               hb_outspec_error(out_dtype, out_has_nodata, out_nodata));
     return fit_dispatch(src_dev, src_has_nodata, src_nodata, ref_dev, ref_has_nodata, ref_nodata, h, w, 0, h, model, kh,
-                        kw, 0, norm_dev, nullptr, nullptr, corr_dev, stream, "hb_fit_apply_same_grid");
+                        kw, 0, norm_dev, nullptr, nullptr, (float *)corr_dev, stream, "hb_fit_apply_same_grid",
+                        hb_make_outspec(out_dtype, out_has_nodata, out_nodata));
 }
 
 extern "C" int hb_fit_apply_same_grid_rows(const float *src_dev, int src_has_nodata, double src_nodata,
                                            const float *ref_dev, int ref_has_nodata, double ref_nodata, long h, long w,
                                            long row0, long nrows, int model, int kh, int kw, const double *norm_dev,
-                                           float *corr_dev, void *stream)
+                                           int out_dtype, int out_has_nodata, double out_nodata, void *corr_dev,
+                                           void *stream)
 {
     HB_REQUIRE(corr_dev != nullptr, "hb_fit_apply_same_grid_rows: bad arguments");
+    HB_REQUIRE(hb_outspec_error(out_dtype, out_has_nodata, out_nodata) == nullptr, "hb_fit_apply_same_grid_rows: %s",
+               hb_outspec_error(out_dtype, out_has_nodata, out_nodata));
     return fit_dispatch(src_dev, src_has_nodata, src_nodata, ref_dev, ref_has_nodata, ref_nodata, h, w, row0, nrows,
-                        model, kh, kw, 0, norm_dev, nullptr, nullptr, corr_dev, stream, "hb_fit_apply_same_grid_rows");
+                        model, kh, kw, 0, norm_dev, nullptr, nullptr, (float *)corr_dev, stream,
+                        "hb_fit_apply_same_grid_rows", hb_make_outspec(out_dtype, out_has_nodata, out_nodata));
 }

@@ -157,7 +157,10 @@ downsample_average_kernel(const T *__restrict__ src, long hs, long ws, NoData nd
             const T *p = src + ya * ws + c;
             // rows are fetched kDsBatch at a time, ALL loads of a batch issued before the first is used (the rare
             // nodata branch below would otherwise keep the compiler from hoisting loads: 1-3 in flight per thread)
-            constexpr int kDsBatch = 10;
+#ifndef HB_DS_BATCH
+#define HB_DS_BATCH 10
+#endif
+            constexpr int kDsBatch = HB_DS_BATCH;
             for (long yb0 = ya; yb0 < yb; yb0 += kDsBatch) {
             uint32_t wb[kDsBatch][NW];
 #pragma unroll
@@ -320,6 +323,129 @@ downsample_average_kernel(const T *__restrict__ src, long hs, long ws, NoData nd
     }
 }
 
+// ---- integer sources on aligned grids with an integer ratio (the benchmark configurations; any "aerial image against a
+//      coarser, snapped reference" case) ------------------------------------------------------------------------------------
+// Every destination pixel is then the exact box of ry x rx source pixels (all GDAL weights are 1), and with rx a multiple
+// of the G = 2 (uint16) / 4 (uint8) pixels of a 32-bit word no word straddles two destination pixels.  The kernel is
+// instruction-issue bound, not DRAM bound, in its general form (ncu: 9.6 lane-instructions per pixel, issue-active ~45 %),
+// so this variant spends as few instructions per WORD as it can:
+//   * one integer dot-product per word sums its G pixels at once (dp2a / dp4a against all-ones);
+//   * nodata is not counted per pixel: a packed running minimum of (word ^ nodata pattern) -- one min.u16x2 per word --
+//     tells after the loop whether ANY field of the thread's columns was nodata; only then are the rows re-read (L2
+//     hits) and counted exactly.  sum(valid) = sum(all) - nodata * count(nodata), count(valid) = all - count(nodata);
+//   * whole batches of rows are loaded without per-row clamps; the footprint rows are exactly ry;
+//   * the per-destination-pixel combination is a shared-memory integer atomic per thread and destination pixel (at most
+//     two per thread) instead of a serial loop over the footprint columns.
+// Sums are exact integers, so the result is bit-identical to the general kernel's (and to GDAL's double accumulation).
+template <typename T, bool NDSCAN>
+__global__ void __launch_bounds__(kDsThreads, 4)
+downsample_int_aligned_kernel(const T *__restrict__ src, long ws, NoData nd, float *__restrict__ dst, long wd, int rx,
+                              int ry, long cx0, long cy0, int ndc, int chunks)
+{
+    constexpr int NW = (sizeof(T) == 2) ? 4 : 2;                           // 32-bit words per thread and row (8 pixels)
+    constexpr int G = 4 / (int)sizeof(T);                                  // pixels per word
+    constexpr uint32_t kOnes = (sizeof(T) == 2) ? 0x00010001u : 0x01010101u;
+    constexpr uint32_t kHigh = (sizeof(T) == 2) ? 0x80008000u : 0x80808080u;
+    __shared__ unsigned int s_sum[kDsSpan / 8 + 8], s_cnt[kDsSpan / 8 + 8];   // per destination pixel of this CTA (rx >= 8)
+
+    const long i = blockIdx.x / chunks;
+    const int chunk = (int)(blockIdx.x % chunks);
+    const long j0 = (long)chunk * ndc;
+    const int nj = (int)min((long)ndc, wd - j0);
+    const int t = threadIdx.x;
+    for (int k = t; k < nj; k += kDsThreads) { s_sum[k] = 0u; s_cnt[k] = 0u; }
+    __syncthreads();
+
+    const long c_first = cx0 + j0 * rx;                                    // first source column of this CTA's footprint
+    const long c_base = (c_first / kDsVec) * kDsVec;                       // 16-byte aligned start of the staged span
+    const long c = c_base + (long)t * kDsVec;                              // this thread's 8 columns
+    const long c_end = c_first + (long)nj * rx;                            // one past the footprint's last column
+    const uint32_t ndpat = NDSCAN ? (uint32_t)nd.ivalue * kOnes : 0u;
+    if (c + kDsVec > c_first && c < c_end) {                               // (threads wholly outside the footprint idle)
+        uint32_t acc[NW], mn[NW];
+#pragma unroll
+        for (int w = 0; w < NW; w++) { acc[w] = 0u; mn[w] = 0xFFFFFFFFu; }
+        const T *p = src + (cy0 + i * ry) * ws + c;
+        auto add_row = [&](const uint32_t (&w)[NW]) {
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+                // (dp2a.lo multiplies the two 16-bit halves of the word by the two LOW BYTES of its second operand)
+                if (sizeof(T) == 2) acc[k] = __dp2a_lo(w[k], 0x0101u, acc[k]);
+                else acc[k] = __dp4a(w[k], 0x01010101u, acc[k]);
+                if (NDSCAN) {
+                    const uint32_t x = w[k] ^ ndpat;
+                    if (sizeof(T) == 2) asm("min.u16x2 %0, %0, %1;" : "+r"(mn[k]) : "r"(x));
+                    else mn[k] &= ~((x - kOnes) & ~x);                   // (a cleared high bit marks "some byte was zero")
+                }
+            }
+        };
+        auto load_row = [&](const T *q, uint32_t (&w)[NW]) {
+            if (sizeof(T) == 2) { const uint4 v = hb_ldg_stream16(q); w[0] = v.x; w[1] = v.y; w[NW > 2 ? 2 : 0] = v.z; w[NW > 3 ? 3 : 0] = v.w; }
+            else { const uint2 v = hb_ldg_stream8(q); w[0] = v.x; w[1] = v.y; }
+        };
+        constexpr int B = 10;
+        int r = 0;
+        for (; r + B <= ry; r += B) {                                      // whole batches: all loads issued before the first use
+            uint32_t wb[B][NW];
+#pragma unroll
+            for (int u = 0; u < B; u++) load_row(p + (long)(r + u) * ws, wb[u]);
+#pragma unroll
+            for (int u = 0; u < B; u++) add_row(wb[u]);
+        }
+        for (; r < ry; r++) { uint32_t w1[NW]; load_row(p + (long)r * ws, w1); add_row(w1); }
+        // nodata fields seen?  (uint16: a zero half-word in the running minimum; uint8: a cleared marker bit)
+        uint32_t ndcnt[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) ndcnt[k] = 0u;
+        if (NDSCAN) {
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+                if (sizeof(T) == 2) any = any || (((mn[k] - kOnes) & ~mn[k] & kHigh) != 0u);
+                else any = any || ((mn[k] & kHigh) != kHigh);
+            }
+            if (any) {                                                     // rare: count the nodata pixels exactly (rows are L2 hits)
+                for (int rr = 0; rr < ry; rr++) {
+                    uint32_t w1[NW];
+                    load_row(p + (long)rr * ws, w1);
+#pragma unroll
+                    for (int k = 0; k < NW; k++) {
+#pragma unroll
+                        for (int f = 0; f < G; f++) {
+                            const uint32_t v = (w1[k] >> (f * 8 * (int)sizeof(T))) & ((sizeof(T) == 2) ? 0xFFFFu : 0xFFu);
+                            ndcnt[k] += (v == (uint32_t)nd.ivalue) ? 1u : 0u;
+                        }
+                    }
+                }
+            }
+        }
+        // every word lies inside ONE destination pixel (rx % G == 0, cx0 % G == 0): merge this thread's words per
+        // destination pixel and add them with one shared-memory atomic each
+        int jprev = -1;
+        uint32_t psum = 0u, pcnt = 0u;
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            const long col = c + (long)k * G;
+            const bool inside = (col >= c_first) && (col < c_end);
+            const int jd = inside ? (int)((col - c_first) / rx) : -1;
+            const uint32_t vs = acc[k] - (NDSCAN ? (uint32_t)nd.ivalue * ndcnt[k] : 0u);
+            const uint32_t vc = (uint32_t)(G * ry) - ndcnt[k];
+            if (jd != jprev) {
+                if (jprev >= 0) { atomicAdd(&s_sum[jprev], psum); atomicAdd(&s_cnt[jprev], pcnt); }
+                jprev = jd; psum = 0u; pcnt = 0u;
+            }
+            if (inside) { psum += vs; pcnt += vc; }
+        }
+        if (jprev >= 0) { atomicAdd(&s_sum[jprev], psum); atomicAdd(&s_cnt[jprev], pcnt); }
+    }
+    __syncthreads();
+    const float qnan = __int_as_float(0x7fc00000);
+    for (int k = t; k < nj; k += kDsThreads) {
+        const uint32_t n = s_cnt[k];
+        dst[i * wd + j0 + k] = n ? (float)((double)s_sum[k] / (double)n) : qnan;
+    }
+}
+
 template <typename T>
 int launch_downsample(const void *src, long hs, long ws, NoData nd, float *dst, long hd, long wd, double sx, double ox,
                       double sy, double oy, cudaStream_t stream)
@@ -332,6 +458,26 @@ int launch_downsample(const void *src, long hs, long ws, NoData nd, float *dst, 
     const long blocks = hd * chunks;
     HB_REQUIRE(blocks > 0 && blocks < 2147483647L, "hb_downsample_average: grid too large");
     const bool aligned = ((ws * (long)sizeof(T)) % 16 == 0) && (((uintptr_t)src) % 16 == 0);
+    if constexpr (IsInt<T>::value) {
+        // integer ratio, integer offset, destination wholly inside the source, words never straddling destination pixels:
+        // the exact-box kernel (see downsample_int_aligned_kernel)
+        constexpr int G = 4 / (int)sizeof(T);
+        const double rxd = floor(sx + 0.5), ryd = floor(sy + 0.5), oxd = floor(ox + 0.5), oyd = floor(oy + 0.5);
+        const bool integral = fabs(sx - rxd) < 1e-12 && fabs(sy - ryd) < 1e-12 && fabs(ox - oxd) < 1e-9 && fabs(oy - oyd) < 1e-9;
+        if (aligned && integral && rxd >= 8 && rxd <= 255 && ryd >= 1 && ryd <= 255 && ((long)rxd % G) == 0 &&
+            oxd >= 0 && oyd >= 0 && ((long)oxd % G) == 0 && (long)oxd + wd * (long)rxd <= ws &&
+            (long)oyd + hd * (long)ryd <= hs) {
+            const bool ndscan = nd.has && nd.int_ok && (sizeof(T) == 2 || nd.ivalue <= 255);
+            if (ndscan)
+                downsample_int_aligned_kernel<T, true><<<(unsigned)blocks, kDsThreads, 0, stream>>>(
+                    (const T *)src, ws, nd, dst, wd, (int)rxd, (int)ryd, (long)oxd, (long)oyd, (int)ndc, (int)chunks);
+            else
+                downsample_int_aligned_kernel<T, false><<<(unsigned)blocks, kDsThreads, 0, stream>>>(
+                    (const T *)src, ws, nd, dst, wd, (int)rxd, (int)ryd, (long)oxd, (long)oyd, (int)ndc, (int)chunks);
+            HB_LAUNCH_OK("downsample_int_aligned_kernel");
+            return 0;
+        }
+    }
     if (aligned)
         downsample_average_kernel<T, true><<<(unsigned)blocks, kDsThreads, 0, stream>>>(
             (const T *)src, hs, ws, nd, dst, hd, wd, sx, ox, sy, oy, (int)ndc, (int)chunks);
@@ -440,6 +586,7 @@ struct UpGeom {
     double sx, ox, sy, oy;
     int ncols;            // coarse columns staged per warp (cells + 3)
     int rows_per_cta;
+    OutSpec ospec;        // output dtype / nodata of the corrected plane (APPLY); plain float32 otherwise
 };
 
 // T: storage type of the source plane (APPLY); NB: coarse bands (1 or 2); APPLY: fuse gain*src+offset;
@@ -548,17 +695,21 @@ upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ 
         for (int st = 0; st < kUpStages - 1; st++) prefetch(Y0 + (long)st * kUpRb, st);
     }
 
-    auto store_row = [&](float *orow, const float (&res)[NOUT][PPT]) {
+    // (APPLY: the corrected plane's output dtype conversion is fused into the store; `opix` = pixel index of the lane's
+    //  first pixel in the output plane)
+    auto store_row = [&](long opix, const float (&res)[NOUT][PPT]) {
         if (ALIGNED && full_vec) {
-            hb_stg_stream16(orow, make_float4(res[0][0], res[0][1], res[0][2], res[0][3]));
+            if constexpr (APPLY) hb_store4_out(out, opix, make_float4(res[0][0], res[0][1], res[0][2], res[0][3]), g.ospec);
+            else hb_stg_stream16(out + opix, make_float4(res[0][0], res[0][1], res[0][2], res[0][3]));
             if constexpr (NOUT == 2)
-                hb_stg_stream16(orow + g.hs * g.ws, make_float4(res[1][0], res[1][1], res[1][2], res[1][3]));
+                hb_stg_stream16(out + g.hs * g.ws + opix, make_float4(res[1][0], res[1][1], res[1][2], res[1][3]));
         } else {
 #pragma unroll
             for (int k = 0; k < PPT; k++) {
                 if ((X0 + k) < g.ws) {
-                    orow[k] = res[0][k];
-                    if constexpr (NOUT == 2) orow[g.hs * g.ws + k] = res[1][k];
+                    if constexpr (APPLY) hb_store1_out(out, opix + k, res[0][k], g.ospec);
+                    else out[opix + k] = res[0][k];
+                    if constexpr (NOUT == 2) out[g.hs * g.ws + opix + k] = res[1][k];
                 }
             }
         }
@@ -592,7 +743,7 @@ upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ 
         const unsigned char *ring_b = s_ring + ((batch % kUpStages) * kUpRb) * kRowBytes;
 
         for (int rr = 0; rr < nrows; rr++) {
-            float *orow = out + (Yb + rr) * g.ws + X0;
+            const long orow = (Yb + rr) * g.ws + X0;
             const long Y = Yb + rr;
             const RowInfo ri = s_rows[Y - Y0];
 
@@ -706,7 +857,8 @@ upsample_kernel(const T *__restrict__ src, NoData nd, const float *__restrict__ 
 
 template <typename T, int NB, bool APPLY>
 int launch_upsample(const void *src, NoData nd, const float *coarse, long hs, long ws, long hp, long wp, double sx,
-                    double ox, double sy, double oy, const uint8_t *cover, float *out, cudaStream_t stream)
+                    double ox, double sy, double oy, const uint8_t *cover, float *out, cudaStream_t stream,
+                    OutSpec ospec = hb_make_outspec(HB_F32, 0, 0.0))
 {
     HB_REQUIRE(sx > 0 && sy > 0 && sx <= 1.0 + 1e-9 && sy <= 1.0 + 1e-9,
                "cubic-spline up-sampling needs a destination grid at least as fine as the source (scale %.4f, %.4f)",
@@ -714,6 +866,7 @@ int launch_upsample(const void *src, NoData nd, const float *coarse, long hs, lo
     HB_REQUIRE(hp < 2147483000L && wp < 2147483000L, "coarse raster too large");
     UpGeom g;
     g.hs = hs; g.ws = ws; g.hp = hp; g.wp = wp; g.sx = sx; g.ox = ox; g.sy = sy; g.oy = oy;
+    g.ospec = ospec;
     g.ncols = (int)ceil((double)kUpWarpW * sx) + 5;
     // rows per CTA: a couple of coarse rows' worth, so that the per-cell-row work is amortised
     long rpc = (long)ceil(2.0 / sy);
@@ -729,13 +882,14 @@ int launch_upsample(const void *src, NoData nd, const float *coarse, long hs, lo
     HB_REQUIRE(grid.y <= 65535u, "up-sampling destination has too many rows (%ld)", hs);
     const size_t align = APPLY ? sizeof(T) * kUpPpt : 16;
     const bool aligned = (!APPLY || (((ws * (long)sizeof(T)) % (long)align == 0) && (((uintptr_t)src) % align == 0))) &&
-                         (ws % 4 == 0) && (((uintptr_t)out) % 16 == 0);
+                         (ws % 4 == 0) && (((uintptr_t)out) % (4 * hb_out_size(ospec.dtype)) == 0);
     NoData ndk = nd;
     if (!ndk.int_ok) ndk.ivalue = -1;                       // integer sources: no pixel can equal it
     // ---- fast paths (upsample_poly.cu): aligned rasters, >= ~1.6 destination pixels per coarse pixel, no coverage mask
     if (aligned && cover == nullptr) {
         UpPolyGeom pg;
         pg.hs = hs; pg.ws = ws; pg.hp = hp; pg.wp = wp; pg.sx = sx; pg.ox = ox; pg.sy = sy; pg.oy = oy;
+        pg.ospec = ospec;
         if (hb_up_poly_eligible(pg)) {
             if (APPLY) return hb_up_poly_apply(src, hb_dtype_code<T>(), ndk, coarse, pg, out, stream);
             if (NB == 1) return hb_up_poly_resample(coarse, 1, pg, out, stream);   // (double precision: feeds a fit)
@@ -785,7 +939,7 @@ __global__ void nearest_kernel(const float *__restrict__ src, long nb, long hs, 
 // =====================================================================================================================
 template <typename T>
 __global__ void apply_same_grid_kernel(const T *__restrict__ src, NoData nd, int mask_src,
-                                       const float *__restrict__ params, long n, float *__restrict__ corr)
+                                       const float *__restrict__ params, long n, void *__restrict__ corr, OutSpec os)
 {
     const float qnan = __int_as_float(0x7fc00000);
     const long stride = (long)gridDim.x * blockDim.x;
@@ -793,7 +947,7 @@ __global__ void apply_same_grid_kernel(const T *__restrict__ src, NoData nd, int
         const float s = hb_to_f32<T>(src[i]);
         float r = __fadd_rn(__fmul_rn(__ldg(params + i), s), __ldg(params + n + i));   // kernel_model.py:461
         if (mask_src && !hb_valid(s, nd)) r = qnan;
-        corr[i] = r;
+        hb_store1_out(corr, i, r, os);                       // (output dtype conversion fused into the store)
     }
 }
 
@@ -918,22 +1072,27 @@ extern "C" int hb_downsample_average(const void *src_dev, int src_dtype, long hs
 
 extern "C" int hb_upsample_apply(const void *src_dev, int src_dtype, long hs, long ws, int has_nodata, double nodata,
                                  const float *params_dev, long hp, long wp, double sx, double ox, double sy, double oy,
-                                 const uint8_t *cover_dev, float *corr_dev, void *stream)
+                                 const uint8_t *cover_dev, int out_dtype, int out_has_nodata, double out_nodata,
+                                 void *corr_dev, void *stream)
 {
     HB_REQUIRE(src_dev && params_dev && corr_dev && hs > 0 && ws > 0 && hp > 0 && wp > 0,
                "hb_upsample_apply: bad arguments");
+    HB_REQUIRE(hb_outspec_error(out_dtype, out_has_nodata, out_nodata) == nullptr, "hb_upsample_apply: %s",
+               hb_outspec_error(out_dtype, out_has_nodata, out_nodata));
     const NoData nd = hb_make_nodata(has_nodata, nodata);
+    const OutSpec os = hb_make_outspec(out_dtype, out_has_nodata, out_nodata);
     cudaStream_t st = (cudaStream_t)stream;
+    float *out = (float *)corr_dev;                          // (typed by `os`; the kernels index it in pixels)
     switch (src_dtype) {
         case HB_U8:
             return launch_upsample<uint8_t, 2, true>(src_dev, nd, params_dev, hs, ws, hp, wp, sx, ox, sy, oy, cover_dev,
-                                                     corr_dev, st);
+                                                     out, st, os);
         case HB_U16:
             return launch_upsample<uint16_t, 2, true>(src_dev, nd, params_dev, hs, ws, hp, wp, sx, ox, sy, oy,
-                                                      cover_dev, corr_dev, st);
+                                                      cover_dev, out, st, os);
         case HB_F32:
             return launch_upsample<float, 2, true>(src_dev, nd, params_dev, hs, ws, hp, wp, sx, ox, sy, oy, cover_dev,
-                                                   corr_dev, st);
+                                                   out, st, os);
     }
     HB_REQUIRE(false, "hb_upsample_apply: unknown dtype %d", src_dtype);
 }
@@ -963,25 +1122,29 @@ extern "C" int hb_resample_up(const float *src_dev, long nb, long hs, long ws, i
 }
 
 extern "C" int hb_apply_same_grid(const void *src_dev, int src_dtype, int has_nodata, double nodata, int mask_src,
-                                  const float *params_dev, long h, long w, float *corr_dev, void *stream)
+                                  const float *params_dev, long h, long w, int out_dtype, int out_has_nodata,
+                                  double out_nodata, void *corr_dev, void *stream)
 {
     HB_REQUIRE(src_dev && params_dev && corr_dev && h > 0 && w > 0, "hb_apply_same_grid: bad arguments");
+    HB_REQUIRE(hb_outspec_error(out_dtype, out_has_nodata, out_nodata) == nullptr, "hb_apply_same_grid: %s",
+               hb_outspec_error(out_dtype, out_has_nodata, out_nodata));
     const NoData nd = hb_make_nodata(has_nodata, nodata);
+    const OutSpec os = hb_make_outspec(out_dtype, out_has_nodata, out_nodata);
     cudaStream_t st = (cudaStream_t)stream;
     const long n = h * w;
     const unsigned grid = grid_for(n, 256, 16);
     switch (src_dtype) {
         case HB_U8:
             apply_same_grid_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t *)src_dev, nd, mask_src, params_dev, n,
-                                                                  corr_dev);
+                                                                  corr_dev, os);
             break;
         case HB_U16:
             apply_same_grid_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)src_dev, nd, mask_src, params_dev,
-                                                                   n, corr_dev);
+                                                                   n, corr_dev, os);
             break;
         case HB_F32:
             apply_same_grid_kernel<float><<<grid, 256, 0, st>>>((const float *)src_dev, nd, mask_src, params_dev, n,
-                                                                corr_dev);
+                                                                corr_dev, os);
             break;
         default: HB_REQUIRE(false, "hb_apply_same_grid: unknown dtype %d", src_dtype);
     }

@@ -337,7 +337,7 @@ struct __align__(16) RowEntry { float wy[4]; };            // the row's B-spline
 // T: storage type of the source plane (APPLY); NB: coarse bands; APPLY: fuse corr = gain*src + offset.
 // coarse: NB == 2: interleaved (gain, offset) float2 [hp][wp]; NB == 1: the float plane.
 // rows_per_cta (<= kMaxRows) is chosen by the host so that the grid fills whole waves.
-template <typename T, int NB, bool APPLY>
+template <typename T, int NB, bool APPLY, bool CONVERT>
 __global__ void __launch_bounds__(kThreads, HB_POLY_MIN_CTAS)
 upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restrict__ coarse_v,
                      const uint8_t *__restrict__ flags, UpPolyGeom g, int rows_per_cta, float *__restrict__ out)
@@ -458,7 +458,7 @@ upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restric
     const float4 sx4 = s_w[5 * 32];
     int q_ky = INT_MIN;
     bool do_store = false;
-    float *orow = out + Y0 * g.ws + X0;
+    long opix = Y0 * g.ws + X0;                             // pixel index of the lane's 4 pixels in the output plane
     const long out_pitch = g.ws;
     uint32_t ring_rd = ring_sa;                             // this lane's pixels of the current row in the ring
     // the row table entry of row r + 1 is fetched while row r is computed (the loop is a chain of short dependent
@@ -467,7 +467,7 @@ upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restric
     RowEntry ri_next = s_rows[0];
     float sy_next = s_sy[0];
 #pragma unroll 1
-    for (int r = 0; r < nrows; r++, orow += out_pitch) {
+    for (int r = 0; r < nrows; r++, opix += out_pitch) {
         if (APPLY && (r & (kRb - 1)) == 0) {                // (warp-uniform) a new stage: keep the ring full, wait for it
             prefetch();
             cp_async_wait<kStages - 1>();
@@ -599,8 +599,9 @@ upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restric
             if constexpr (NOUT == 2) res[1] = make_float4(ov[0].x, ov[0].y, ov[1].x, ov[1].y);
         }
         if (do_store) {                                     // (DIRTY lanes are written by the fix-up kernel)
-            hb_stg_stream16(orow, res[0]);
-            if constexpr (NOUT == 2) hb_stg_stream16(orow + g.hs * g.ws, res[1]);
+            if constexpr (APPLY && CONVERT) hb_store4_out(out, opix, res[0], g.ospec);   // output dtype conversion in the store
+            else hb_stg_stream16(out + opix, res[0]);
+            if constexpr (NOUT == 2) hb_stg_stream16(out + g.hs * g.ws + opix, res[1]);
         }
     }
 }
@@ -616,7 +617,7 @@ upsample_poly_kernel(const T *__restrict__ src, NoData nd, const void *__restric
 // zeros elsewhere).  Same classification / fix-up / edge rules / cp.async ring as upsample_poly_kernel.
 constexpr int kYfCols = 6;
 
-template <typename T, int NB, bool APPLY>
+template <typename T, int NB, bool APPLY, bool CONVERT>
 __global__ void __launch_bounds__(kThreads, 2)
 upsample_yfirst_kernel(const T *__restrict__ src, NoData nd, const void *__restrict__ coarse_v,
                        const uint8_t *__restrict__ flags, UpPolyGeom g, int rows_per_cta, float *__restrict__ out)
@@ -715,7 +716,7 @@ upsample_yfirst_kernel(const T *__restrict__ src, NoData nd, const void *__restr
     pk2 t[NB][4][kYfCols / 2];                              // tap rows x window column pairs (packed float32 pairs)
     int q_ky = INT_MIN;
     bool do_store = false;
-    float *orow = out + Y0 * g.ws + X0;
+    long opix = Y0 * g.ws + X0;                             // pixel index of the lane's 4 pixels in the output plane
     const long out_pitch = g.ws;
     uint32_t ring_rd = ring_sa;
     auto load_tap_row = [&](int ky, int j) {
@@ -737,7 +738,7 @@ upsample_yfirst_kernel(const T *__restrict__ src, NoData nd, const void *__restr
             for (int p = 0; p < kYfCols / 2; p++) t[b][j][p] = pk(v[b][2 * p], v[b][2 * p + 1]);
     };
 #pragma unroll 1
-    for (int r = 0; r < nrows; r++, orow += out_pitch) {
+    for (int r = 0; r < nrows; r++, opix += out_pitch) {
         if (APPLY && (r & (kRb - 1)) == 0) {
             prefetch();
             cp_async_wait<kStages - 1>();
@@ -810,8 +811,9 @@ upsample_yfirst_kernel(const T *__restrict__ src, NoData nd, const void *__restr
                 res[1] = make_float4(pk_lo(o[NB - 1][0]), pk_hi(o[NB - 1][0]), pk_lo(o[NB - 1][1]), pk_hi(o[NB - 1][1]));
         }
         if (do_store) {
-            hb_stg_stream16(orow, res[0]);
-            if constexpr (NOUT == 2) hb_stg_stream16(orow + g.hs * g.ws, res[1]);
+            if constexpr (APPLY && CONVERT) hb_store4_out(out, opix, res[0], g.ospec);   // output dtype conversion in the store
+            else hb_stg_stream16(out + opix, res[0]);
+            if constexpr (NOUT == 2) hb_stg_stream16(out + g.hs * g.ws + opix, res[1]);
         }
     }
 }
@@ -1121,7 +1123,7 @@ upsample_fixup_kernel(const T *__restrict__ src, NoData nd, const float *__restr
                         }
                     }
                     if (APPLY) {
-                        out[Y * g.ws + X] = __fadd_rn(__fmul_rn(r[0], s), r[NB - 1]);   // two roundings, as numpy
+                        hb_store1_out(out, Y * g.ws + X, __fadd_rn(__fmul_rn(r[0], s), r[NB - 1]), g.ospec);   // two roundings, as numpy
                     } else {
                         out[Y * g.ws + X] = r[0];
                         if constexpr (NOUT == 2) out[g.hs * g.ws + Y * g.ws + X] = r[1];
@@ -1207,13 +1209,17 @@ int launch_poly(const void *src, NoData nd, const float *coarse, const UpPolyGeo
         const size_t smem = kRowTableBytes + ((yfirst ? kYfCols : 6) * 32 * sizeof(float4) + ring) * kWarps;
         const long cta_w = (long)kWarpW * kWarps;
         const long gx = (g.ws + cta_w - 1) / cta_w;
-        auto kern = yfirst ? upsample_yfirst_kernel<T, NB, APPLY> : upsample_poly_kernel<T, NB, APPLY>;
+        // (CONVERT: an output dtype / nodata other than plain float32 -- its own instantiation, so that the float32 path's
+        //  store stays a single 16-byte instruction)
+        const bool convert = APPLY && !g.ospec.plain;
+        auto kern = yfirst ? (convert ? upsample_yfirst_kernel<T, NB, APPLY, APPLY> : upsample_yfirst_kernel<T, NB, APPLY, false>)
+                           : (convert ? upsample_poly_kernel<T, NB, APPLY, APPLY> : upsample_poly_kernel<T, NB, APPLY, false>);
         if (smem > 48 * 1024)
             HB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // rows per CTA: as many as possible (fewer row tables / weight set-ups per pixel) such that the grid is just
         // under a whole number of waves of resident CTAs (every warp streams the same amount: no ragged tail)
-        static int ctas_cache[2] = {0, 0};
-        int &ctas_per_sm = ctas_cache[yfirst ? 1 : 0];
+        static int ctas_cache[4] = {0, 0, 0, 0};
+        int &ctas_per_sm = ctas_cache[(yfirst ? 1 : 0) + (convert ? 2 : 0)];
         if (ctas_per_sm == 0) {
             int n = 0;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kThreads, smem) != cudaSuccess || n < 1) n = 1;

@@ -219,19 +219,21 @@ class RasterFuse:
         return plan[1:]
 
     def _process_band(self, band_i: int, model: KernelModel, out=None, stage: bool = False,
-                      want_params: bool = True) -> Tuple[RasterArray, Optional[RasterArray]]:
+                      want_params: bool = True, out_nodata=float('nan')) -> Tuple[RasterArray, Optional[RasterArray]]:
         """
         One band of reference fuse.py:295-319 (``_process_block`` with a single block): read -> fit -> apply.
         ``stage``: copy a host band to the device once up front (fit and apply both read it) and leave the results
-        on the device; otherwise results live where the inputs live.
+        on the device; otherwise results live where the inputs live.  ``out`` / ``out_nodata``: device plane of the
+        OUTPUT dtype that the apply kernel writes directly (the reference converts when it writes the block,
+        raster_array.py:493-500; here the conversion is part of the kernel's store).
         """
         if self._src.is_device and self._ref.is_device and isinstance(model, RefSpaceModel):
             # device-resident rasters, proc_crs = ref: one native call per band on cached, prepared planes
             src_ra, ref_ra, ref_t, gm = self._band_plan(band_i)
             if model.can_fuse(src_ra, ref_ra):
                 corr, params = model._fuse_planes(src_ra.array, src_ra.nodata, ref_t, ref_ra.nodata, gm, out,
-                                                  want_params)
-                corr_ra = RasterArray(corr, src_ra.crs, src_ra.transform, nodata=float('nan'))
+                                                  want_params, out_nodata)
+                corr_ra = RasterArray(corr, src_ra.crs, src_ra.transform, nodata=out_nodata)
                 param_ra = None
                 if params is not None:
                     param_ra = RasterArray(params, ref_ra.crs, ref_ra.transform, nodata=float('nan'))
@@ -242,13 +244,13 @@ class RasterFuse:
             src_ra, ref_ra = src_ra.to_device(), ref_ra.to_device()
         if isinstance(model, SrcSpaceModel) and not want_params and model.can_fuse(src_ra, ref_ra):
             # fit + apply in one kernel: the parameters are not wanted, so they are never written
-            return model.fuse(src_ra, ref_ra, out=out), None
+            return model.fuse(src_ra, ref_ra, out=out, out_nodata=out_nodata), None
         if isinstance(model, RefSpaceModel) and model.can_fuse(src_ra, ref_ra):
             # fit + apply as one native call (same kernels, same order; the parameters are only materialised for the
             # caller when a parameter raster was asked for)
-            return model.fuse(src_ra, ref_ra, out=out, want_params=want_params)
+            return model.fuse(src_ra, ref_ra, out=out, want_params=want_params, out_nodata=out_nodata)
         param_ra = model.fit(src_ra, ref_ra)          # fuse.py:306
-        corr_ra = model.apply(src_ra, param_ra, out=out)       # fuse.py:307
+        corr_ra = model.apply(src_ra, param_ra, out=out, out_nodata=out_nodata)       # fuse.py:307
         return corr_ra, param_ra
 
     def process(self, corr_filename=None, model: Model = KernelModel.default_model,
@@ -309,11 +311,21 @@ class RasterFuse:
             corr_all = torch.empty((n_bands, hs, ws), dtype=getattr(torch, out_dtype), device=device)
         param_planes = [None] * n_bands
 
+        # output dtypes the apply kernels store themselves (conversion fused into their epilogue); anything else goes through
+        # a float32 plane and a separate conversion
+        fused_out = out_dtype in ('float32', 'uint8', 'uint16', 'int16')
+
         def run_band(band_i):
-            direct = (not to_host) and plain_f32       # the apply kernel writes its plane of corr_all itself
-            corr_ra, param_ra = self._process_band(band_i, kernel_model, out=corr_all[band_i] if direct else None,
-                                                   stage=True, want_params=param_filename is not None)
-            if not direct:
+            want = param_filename is not None
+            if fused_out:
+                plane = corr_all[band_i] if not to_host else torch.empty((hs, ws), dtype=getattr(torch, out_dtype),
+                                                                         device=device)
+                corr_ra, param_ra = self._process_band(band_i, kernel_model, out=plane, stage=True, want_params=want,
+                                                       out_nodata=out_nodata)
+                if to_host:
+                    corr_all[band_i].copy_(plane, non_blocking=True)
+            else:
+                corr_ra, param_ra = self._process_band(band_i, kernel_model, out=None, stage=True, want_params=want)
                 plane = _convert_dtype(corr_ra, out_dtype, out_nodata)
                 corr_all[band_i].copy_(plane, non_blocking=True)
             if param_ra is not None:

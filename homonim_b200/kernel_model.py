@@ -35,6 +35,7 @@ except ImportError:  # pragma: no cover
 
 NAN = float('nan')
 _DTYPE_CODES = {'uint8': _native.HB_U8, 'uint16': _native.HB_U16, 'float32': _native.HB_F32}
+_OUT_DTYPE_CODES = {'uint8': _native.HB_U8, 'uint16': _native.HB_U16, 'int16': _native.HB_I16, 'float32': _native.HB_F32}
 _MODEL_CODES = {
     Model.gain: _native.HB_MODEL_GAIN,
     Model.gain_blk_offset: _native.HB_MODEL_GAIN_BLK_OFFSET,
@@ -164,6 +165,20 @@ def _as_nan_nodata_f32(t, nodata):
     return torch.where(f == float(nodata), torch.full_like(f, NAN), f)
 
 
+def _out_args(out_t, out_nodata) -> Tuple[int, int, float]:
+    """
+    (out_dtype, out_has_nodata, out_nodata) of a corrected plane for the native apply calls: the tensor's dtype decides
+    the stored type; the conversion of RasterArray._convert_array_dtype (raster_array.py:353-387: round half-to-even,
+    clip, NaN -> nodata) happens inside the kernel's store.  float32 with NaN / no nodata = the values as they are.
+    """
+    name = str(out_t.dtype).replace('torch.', '')
+    if name not in _OUT_DTYPE_CODES:
+        raise TypeError(f'unsupported output dtype {name!r}: expected float32, uint8, uint16 or int16')
+    if out_nodata is None or (isinstance(out_nodata, float) and np.isnan(out_nodata)):
+        return _OUT_DTYPE_CODES[name], 0, 0.0
+    return _OUT_DTYPE_CODES[name], 1, float(out_nodata)
+
+
 def _result(array_dev, like_device: bool):
     """ Return results where the caller's rasters live. """
     if like_device:
@@ -269,7 +284,7 @@ class KernelModel:
                 params = params[:, int(rows[0]):int(rows[0]) + int(rows[1])].contiguous()
         return params
 
-    def _fit_apply_rows(self, src_t, src_nodata, ref_t, ref_nodata, row0, nrows, norm=None, out=None):
+    def _fit_apply_rows(self, src_t, src_nodata, ref_t, ref_nodata, row0, nrows, norm=None, out=None, out_nodata=NAN):
         """
         Fit fused with apply (``hb_fit_apply_same_grid_rows``) for the rows ``[row0, row0 + nrows)`` of two float32 device
         planes on one grid -> corrected float32 ``[nrows, W]``.  The parameters are not materialised (models whose
@@ -289,7 +304,7 @@ class KernelModel:
         kh, kw = self._kernel_shape
         _call('hb_fit_apply_same_grid_rows', src_t.data_ptr(), s_has, s_nd, ref_t.data_ptr(), r_has, r_nd, h, w,
               int(row0), int(nrows), _MODEL_CODES[self._model], kh, kw, norm.data_ptr() if norm is not None else None,
-              corr.data_ptr(), _stream())
+              *_out_args(corr, out_nodata), corr.data_ptr(), _stream())
         return corr
 
     def _full_coverage_mask(self, in_mask_t, in_transform, params_t, param_transform):
@@ -324,38 +339,43 @@ class KernelModel:
         params = self._fit_planes(src_t, src_ra.nodata, ref_t, ref_ra.nodata)
         return RasterArray(_result(params, on_device), src_ra.crs, src_ra.transform, nodata=NAN)
 
-    def apply(self, src_ra: RasterArray, param_ra: RasterArray, out=None) -> RasterArray:
+    def apply(self, src_ra: RasterArray, param_ra: RasterArray, out=None, out_nodata=NAN) -> RasterArray:
         """
-        Reference kernel_model.py:442-463.  ``out`` (optional, additive): a float32 CUDA tensor ``[H, W]`` to write the
-        corrected band into (device-resident callers avoid a copy); the returned RasterArray then wraps it.
+        Reference kernel_model.py:442-463.  ``out`` (optional, additive): a CUDA tensor ``[H, W]`` to write the corrected
+        band into (device-resident callers avoid a copy); the returned RasterArray then wraps it.  ``out`` may be
+        float32 (the reference's result, nodata NaN) or uint8 / uint16 / int16 with ``out_nodata``: the output dtype
+        conversion the reference performs when it writes the block (raster_array.py:353-387, 493-500) is then fused into
+        the apply kernel.
         """
         if (param_ra.transform != src_ra.transform) or (param_ra.shape != src_ra.shape):
             raise ValueError("'param_ra' and 'src_ra' must have the same CRS, transform and shape")
         _require_torch()
         on_device = (src_ra.is_device and param_ra.is_device) or out is not None
         src_t, par_t = _to_device(src_ra.array), _to_device(param_ra.array)
-        corr = self._apply_planes(src_t, src_ra.nodata, par_t, mask_src=False, out=out)
-        return RasterArray(_result(corr, on_device), param_ra.crs, param_ra.transform, nodata=param_ra.nodata)
+        corr = self._apply_planes(src_t, src_ra.nodata, par_t, mask_src=False, out=out, out_nodata=out_nodata)
+        return RasterArray(_result(corr, on_device), param_ra.crs, param_ra.transform,
+                           nodata=param_ra.nodata if out is None else out_nodata)
 
     @staticmethod
     def _check_out(out, h, w, device):
         if out is None:
             return torch.empty((h, w), dtype=torch.float32, device=device)
-        if (not is_tensor(out)) or (not out.is_cuda) or out.dtype != torch.float32 or tuple(out.shape) != (h, w) \
-                or not out.is_contiguous():
-            raise ValueError("'out' must be a contiguous float32 CUDA tensor with the shape of 'src_ra'")
+        if (not is_tensor(out)) or (not out.is_cuda) or tuple(out.shape) != (h, w) or not out.is_contiguous() \
+                or str(out.dtype).replace('torch.', '') not in _OUT_DTYPE_CODES:
+            raise ValueError("'out' must be a contiguous float32 / uint8 / uint16 / int16 CUDA tensor with the shape of "
+                             "'src_ra'")
         return out
 
     @staticmethod
-    def _apply_planes(src_t, src_nodata, par_t, mask_src: bool, out=None):
+    def _apply_planes(src_t, src_nodata, par_t, mask_src: bool, out=None, out_nodata=NAN):
         lib = _native.lib()
         if par_t.ndim != 3 or par_t.shape[0] < 2 or par_t.dtype != torch.float32:
             raise ValueError("'param_ra' must hold at least 2 float32 bands (gain, offset)")
         h, w = int(src_t.shape[-2]), int(src_t.shape[-1])
         corr = KernelModel._check_out(out, h, w, src_t.device)
         has, nd = _nodata_args(src_nodata)
-        _call('hb_apply_same_grid', src_t.data_ptr(), _plane_code(src_t), has, nd, int(mask_src),
-                                             par_t.data_ptr(), h, w, corr.data_ptr(), _stream())
+        _call('hb_apply_same_grid', src_t.data_ptr(), _plane_code(src_t), has, nd, int(mask_src), par_t.data_ptr(), h, w,
+              *_out_args(corr, out_nodata), corr.data_ptr(), _stream())
         return corr
 
 
@@ -457,7 +477,7 @@ class RefSpaceModel(KernelModel):
             return False
         return self._get_resampling(ref_ra.res, src_ra.res) == Resampling.cubic_spline
 
-    def fuse(self, src_ra: RasterArray, ref_ra: RasterArray, out=None, want_params: bool = False
+    def fuse(self, src_ra: RasterArray, ref_ra: RasterArray, out=None, want_params: bool = False, out_nodata=NAN
              ) -> Tuple[RasterArray, Optional[RasterArray]]:
         """
         ``apply(src_ra, fit(src_ra, ref_ra))`` -- one (band, block) of ``RasterFuse._process_block`` (fuse.py:304-307)
@@ -469,14 +489,15 @@ class RefSpaceModel(KernelModel):
         src_t, ref_t = _to_device(src_ra.array), _to_device(ref_ra.array)
         ref_t = _as_f32_plane(ref_t, ref_ra.nodata).contiguous()
         gm = grid_map(src_ra.transform, ref_ra.transform)         # reference grid -> source grid
-        corr, params = self._fuse_planes(src_t, src_ra.nodata, ref_t, ref_ra.nodata, gm, out, want_params)
-        corr_ra = RasterArray(_result(corr, on_device), src_ra.crs, src_ra.transform, nodata=NAN)
+        corr, params = self._fuse_planes(src_t, src_ra.nodata, ref_t, ref_ra.nodata, gm, out, want_params, out_nodata)
+        corr_ra = RasterArray(_result(corr, on_device), src_ra.crs, src_ra.transform, nodata=out_nodata)
         param_ra = None
         if params is not None:
             param_ra = RasterArray(_result(params, on_device), ref_ra.crs, ref_ra.transform, nodata=NAN)
         return corr_ra, param_ra
 
-    def _fuse_planes(self, src_t, src_nodata, ref_t, ref_nodata, gm, out=None, want_params: bool = False):
+    def _fuse_planes(self, src_t, src_nodata, ref_t, ref_nodata, gm, out=None, want_params: bool = False,
+                     out_nodata=NAN):
         """ `fuse` on prepared device planes (``ref_t``: contiguous float32; ``gm``: reference grid -> source grid):
         returns ``(corr, params or None)`` device tensors.  The lean inner call of ``RasterFuse.process``. """
         hs, ws = int(src_t.shape[-2]), int(src_t.shape[-1])
@@ -492,11 +513,11 @@ class RefSpaceModel(KernelModel):
         kh, kw = self._kernel_shape
         _call('hb_fuse_refspace', src_t.data_ptr(), _plane_code(src_t), hs, ws, s_has, s_nd, ref_t.data_ptr(), hr, wr,
               r_has, r_nd, gm.sx, gm.ox, gm.sy, gm.oy, _MODEL_CODES[self._model], kh, kw, int(want_r2), int(inpaint),
-              float(self._r2_inpaint_thresh) if inpaint else 0.0, corr.data_ptr(),
+              float(self._r2_inpaint_thresh) if inpaint else 0.0, *_out_args(corr, out_nodata), corr.data_ptr(),
               params.data_ptr() if params is not None else None, _stream())
         return corr, params
 
-    def apply(self, src_ra: RasterArray, param_ra: RasterArray, out=None) -> RasterArray:
+    def apply(self, src_ra: RasterArray, param_ra: RasterArray, out=None, out_nodata=NAN) -> RasterArray:
         _require_torch()
         lib = _native.lib()
         on_device = (src_ra.is_device and param_ra.is_device) or out is not None
@@ -518,8 +539,8 @@ class RefSpaceModel(KernelModel):
             has, nd = _nodata_args(src_ra.nodata)
             _call('hb_upsample_apply', src_t.data_ptr(), _plane_code(src_t), hs, ws, has, nd,
                                                 par2.data_ptr(), hp, wp, gm.sx, gm.ox, gm.sy, gm.oy,
-                                                cover.data_ptr() if cover is not None else None, corr.data_ptr(),
-                                                _stream())
+                                                cover.data_ptr() if cover is not None else None,
+                                                *_out_args(corr, out_nodata), corr.data_ptr(), _stream())
         else:
             # parameters finer than (or as fine as) the source: resample them, then the same-grid apply
             par_us = torch.stack([_resample_plane(par2[b], param_ra.transform, NAN, (hs, ws), src_ra.transform,
@@ -528,10 +549,12 @@ class RefSpaceModel(KernelModel):
                 cover_us = _resample_up(cover.to(torch.float32), param_ra.transform, None, (hs, ws),
                                         src_ra.transform, _native.HB_UP_NEAREST)
                 par_us[:, ~(cover_us > 0)] = NAN                                             # :497-498
-                corr = self._apply_planes(src_t, src_ra.nodata, par_us, mask_src=False, out=out)
+                corr = self._apply_planes(src_t, src_ra.nodata, par_us, mask_src=False, out=out, out_nodata=out_nodata)
             else:
-                corr = self._apply_planes(src_t, src_ra.nodata, par_us, mask_src=True, out=out)       # :500
-        return RasterArray(_result(corr, on_device), src_ra.crs, src_ra.transform, nodata=NAN)
+                corr = self._apply_planes(src_t, src_ra.nodata, par_us, mask_src=True, out=out,
+                                          out_nodata=out_nodata)                                      # :500
+        return RasterArray(_result(corr, on_device), src_ra.crs, src_ra.transform,
+                           nodata=NAN if out is None else out_nodata)
 
 
 class SrcSpaceModel(KernelModel):
@@ -544,7 +567,7 @@ class SrcSpaceModel(KernelModel):
             return False
         return not (self._model == Model.gain_offset and self._r2_inpaint_thresh is not None)
 
-    def fuse(self, src_ra: RasterArray, ref_ra: RasterArray, out=None) -> RasterArray:
+    def fuse(self, src_ra: RasterArray, ref_ra: RasterArray, out=None, out_nodata=NAN) -> RasterArray:
         """
         ``apply(src_ra, fit(src_ra, ref_ra))`` without materialising the parameters: the reference image is resampled to
         the source grid (kernel_model.py:518-520) and ``hb_fit_apply_same_grid`` writes the corrected pixels straight
@@ -565,9 +588,9 @@ class SrcSpaceModel(KernelModel):
         s_has, s_nd = _nodata_args(src_ra.nodata)
         kh, kw = self._kernel_shape
         _call('hb_fit_apply_same_grid', src_f.data_ptr(), s_has, s_nd, ref_us.data_ptr(), 1, NAN, h, w,
-              _MODEL_CODES[self._model], kh, kw, norm.data_ptr() if norm is not None else None, corr.data_ptr(),
-              _stream())
-        return RasterArray(_result(corr, on_device), src_ra.crs, src_ra.transform, nodata=NAN)
+              _MODEL_CODES[self._model], kh, kw, norm.data_ptr() if norm is not None else None,
+              *_out_args(corr, out_nodata), corr.data_ptr(), _stream())
+        return RasterArray(_result(corr, on_device), src_ra.crs, src_ra.transform, nodata=out_nodata)
 
     def fit(self, src_ra: RasterArray, ref_ra: RasterArray) -> RasterArray:
         _require_torch()

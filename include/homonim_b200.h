@@ -17,6 +17,11 @@
  *   - grid maps: destination pixel-EDGE coordinates (col u, row v) map to source pixel-edge coordinates
  *         src_col = sx * u + ox,   src_row = sy * v + oy          (sx, sy > 0; north-up grids of one CRS)
  *     so destination pixel j covers [j, j+1) and its centre is j + 0.5.
+ *   - corrected planes (`corr_dev`) are written in the OUTPUT dtype the caller asks for: `out_dtype` (HB_F32, HB_U8, HB_U16,
+ *     HB_I16) with `out_has_nodata` / `out_nodata`.  The conversion of RasterArray._convert_array_dtype
+ *     (homonim/raster_array.py:353-387, used by to_rio_dataset :493-500) -- round half-to-even, clip to the type's range,
+ *     NaN -> nodata (0 when there is none) -- is fused into the apply kernels' stores.  HB_F32 with no nodata (or NaN)
+ *     writes the float32 values as they are (nodata = NaN), which is the reference's default output profile.
  *   - return value: 0 on success, non-zero on failure; hb_last_error() then returns a message (thread-local).
  *     There is NO CPU fallback: without a CUDA device every compute entry point fails.
  */
@@ -30,7 +35,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 6
+#define HB_ABI_VERSION 7
 
 /* storage dtype of a source raster plane */
 enum { HB_U8 = 0, HB_U16 = 1, HB_F32 = 2, HB_I16 = 3 };   /* HB_I16: output of hb_convert_dtype only */
@@ -114,13 +119,15 @@ int hb_fit_same_grid_rows(const float *src_dev, int src_has_nodata, double src_n
  * R2 in-painting.  corr_dev: float32 [h][w]; NaN where either input is invalid. */
 int hb_fit_apply_same_grid(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
                            int ref_has_nodata, double ref_nodata, long h, long w, int model, int kh, int kw,
-                           const double *norm_dev, float *corr_dev, void *stream);
+                           const double *norm_dev, int out_dtype, int out_has_nodata, double out_nodata, void *corr_dev,
+                           void *stream);
 
 /* hb_fit_apply_same_grid for the output rows [row0, row0 + nrows) only (see hb_fit_same_grid_rows); corr_dev holds
  * nrows rows. */
 int hb_fit_apply_same_grid_rows(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
                                 int ref_has_nodata, double ref_nodata, long h, long w, long row0, long nrows, int model,
-                                int kh, int kw, const double *norm_dev, float *corr_dev, void *stream);
+                                int kh, int kw, const double *norm_dev, int out_dtype, int out_has_nodata,
+                                double out_nodata, void *corr_dev, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Low-R2 in-painting and gain refit: kernel_model.py:361-371 (rasterio.fill.fillnodata == GDALFillNodata with
@@ -138,7 +145,8 @@ int hb_inpaint_refit(float *params_dev, const float *sums_dev, long h, long w, d
  * kernel_model.py:533, folded in for callers that did not materialise it).
  * --------------------------------------------------------------------------------------------------------------- */
 int hb_apply_same_grid(const void *src_dev, int src_dtype, int has_nodata, double nodata, int mask_src,
-                       const float *params_dev, long h, long w, float *corr_dev, void *stream);
+                       const float *params_dev, long h, long w, int out_dtype, int out_has_nodata, double out_nodata,
+                       void *corr_dev, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Fused parameter up-sampling + apply: RefSpaceModel.apply (kernel_model.py:484-503).
@@ -146,13 +154,14 @@ int hb_apply_same_grid(const void *src_dev, int src_dtype, int has_nodata, doubl
  *   (sx, ox, sy, oy) maps SOURCE-grid pixel-edge coordinates to PARAM-grid pixel-edge coordinates.
  *   cover_dev  optional uint8 [hp][wp] full-coverage mask (mask_partial=True, kernel_model.py:493-498), looked up
  *              with nearest resampling; NULL = mask with the source nodata mask (kernel_model.py:500).
- *   corr       float32 [hs][ws] = up(gain) * src + up(offset), NaN where masked.  The up-sampled parameters are
- *              never written to memory.  Up-sampling is GDAL GRA_CubicSpline (4x4 cubic B-spline taps, invalid taps
+ *   corr       [hs][ws] of the output dtype = up(gain) * src + up(offset) (two float32 roundings, as numpy), nodata where
+ *              masked.  The up-sampled parameters are never written to memory.  Up-sampling is GDAL GRA_CubicSpline (4x4 cubic B-spline taps, invalid taps
  *              skipped and the rest renormalised).
  * --------------------------------------------------------------------------------------------------------------- */
 int hb_upsample_apply(const void *src_dev, int src_dtype, long hs, long ws, int has_nodata, double nodata,
                       const float *params_dev, long hp, long wp, double sx, double ox, double sy, double oy,
-                      const uint8_t *cover_dev, float *corr_dev, void *stream);
+                      const uint8_t *cover_dev, int out_dtype, int out_has_nodata, double out_nodata, void *corr_dev,
+                      void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Plain up-sampling of nb float32 bands (NaN nodata in, NaN nodata out): RasterArray.reproject(...,
@@ -174,7 +183,8 @@ int hb_full_coverage_mask(const uint8_t *in_mask_dev, long hi, long wi, const fl
                           double sx, double ox, double sy, double oy, int kh, int kw, uint8_t *out_dev,
                           void *workspace_dev, void *stream);
 
-/* Output dtype conversion of a corrected float32 plane (nodata = NaN), RasterArray._convert_array_dtype
+/* Stand-alone output dtype conversion of a float32 plane (nodata = NaN) -- for callers that already hold a float32
+ * corrected plane; the apply entry points above fuse the same conversion into their stores.  RasterArray._convert_array_dtype
  * (raster_array.py:353-387) as used by to_rio_dataset (:493-500): integer outputs are rounded half-to-even and clipped
  * to the type's range; NaN pixels become `nodata` (0 when has_nodata == 0).  out_dtype: HB_U8, HB_U16, HB_I16 or HB_F32
  * (nodata substitution only).  One pass: 4 bytes read + sizeof(out) written per pixel. */
@@ -210,7 +220,8 @@ int hb_compare_sums(const float *src_dev, int src_has_nodata, double src_nodata,
 int hb_fuse_refspace(const void *src_dev, int src_dtype, long hs, long ws, int src_has_nodata, double src_nodata,
                      const float *ref_dev, long hr, long wr, int ref_has_nodata, double ref_nodata, double sx, double ox,
                      double sy, double oy, int model, int kh, int kw, int want_r2, int do_inpaint, double r2_thresh,
-                     float *corr_dev, float *params_dev, void *stream);
+                     int out_dtype, int out_has_nodata, double out_nodata, void *corr_dev, float *params_dev,
+                     void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Host-buffer convenience entry point: one (band, block) of RasterFuse._process_block (homonim/fuse.py:304-307)
@@ -224,8 +235,8 @@ int hb_fuse_refspace(const void *src_dev, int src_dtype, long hs, long ws, int s
 int hb_fuse_refspace_host(const void *src_host, int src_dtype, long hs, long ws, int src_has_nodata,
                           double src_nodata, const float *ref_host, long hr, long wr, int ref_has_nodata,
                           double ref_nodata, double sx, double ox, double sy, double oy, int model, int kh, int kw,
-                          int want_r2, int do_inpaint, double r2_thresh, float *corr_host, float *params_host,
-                          void *stream);
+                          int want_r2, int do_inpaint, double r2_thresh, int out_dtype, int out_has_nodata,
+                          double out_nodata, void *corr_host, float *params_host, void *stream);
 
 #ifdef __cplusplus
 }

@@ -191,7 +191,15 @@ def test_fuse_refspace_host_entry_point():
     _native.check(lib.hb_fuse_refspace_host(
         src.ctypes.data, _native.HB_U16, src.shape[0], src.shape[1], 1, 0.0, ref.ctypes.data, ref.shape[0],
         ref.shape[1], 1, NAN, gm.sx, gm.ox, gm.sy, gm.oy, _native.HB_MODEL_GAIN_OFFSET, 15, 15, 1, 1, 0.25,
-        corr.ctypes.data, params.ctypes.data, _stream()))
+        _native.HB_F32, 0, 0.0, corr.ctypes.data, params.ctypes.data, _stream()))
+    # the same call with the output dtype conversion fused in: uint16, nodata 0 (raster_array.py:353-387)
+    corr16 = np.empty(src.shape, 'uint16')
+    _native.check(lib.hb_fuse_refspace_host(
+        src.ctypes.data, _native.HB_U16, src.shape[0], src.shape[1], 1, 0.0, ref.ctypes.data, ref.shape[0],
+        ref.shape[1], 1, NAN, gm.sx, gm.ox, gm.sy, gm.oy, _native.HB_MODEL_GAIN_OFFSET, 15, 15, 1, 1, 0.25,
+        _native.HB_U16, 1, 0.0, corr16.ctypes.data, None, _stream()))
+    exp16 = np.where(np.isnan(corr), 0, np.clip(np.round(np.nan_to_num(corr)), 0, 65535)).astype('uint16')
+    assert np.array_equal(corr16, exp16)
     exp_params, _, exp_corr = kmnp.fuse_band_blocks(src, tuple(src_ra.transform), 0, ref, tuple(ref_ra.transform), NAN,
                                                     'gain-offset', (15, 15), 'ref', True, 0.25)
     from conftest import check_params
@@ -439,6 +447,39 @@ def test_process_out_profile_dtype():
     a = f32.array.cpu().numpy()
     exp = np.where(np.isnan(a), 0, np.clip(np.round(np.nan_to_num(a)), 0, 65535)).astype('uint16')
     assert np.array_equal(u16.array.cpu().numpy().view('uint16'), exp)
+
+
+@pytest.mark.parametrize('dtype, nodata', [('uint8', 0), ('uint16', 0), ('uint16', 65535), ('int16', -32768),
+                                           ('float32', -9999.0)])
+@pytest.mark.parametrize('proc_crs, ratio, shape', [('ref', 20, (37, 41)), ('ref', 2, (150, 130)), ('ref', 7, (64, 53)),
+                                                    ('src', 2, (150, 130))])
+def test_fused_output_dtype_equals_reference_conversion(dtype, nodata, proc_crs, ratio, shape):
+    """ The output dtype conversion fused into the apply kernels' stores (every up-sampling kernel variant: polynomial,
+    'y first', fix-up, general; the same-grid fit + apply kernel) equals the reference's own `_convert_array_dtype`
+    (raster_array.py:353-387; oracle restatement pinned to tests/golden/convert_dtype.npz) of the float32 result, and the
+    host-staged path (device -> host copy of the narrow plane) gives the same. """
+    from homonim_b200 import Model, ProcCrs, RasterFuse
+    from homonim_b200.synthetic import make_pair
+    _, kmnp = _oracle()
+    mu = 120.0 if dtype == 'uint8' else 3000.0
+    src_ra, ref_ra = make_pair(shape[0], shape[1], ratio, bands=2, dtype='float32' if proc_crs == 'src' else 'uint16',
+                               mu=mu, seed=5, device='cuda', src_nodata=NAN if proc_crs == 'src' else 0)
+    kw = dict(model=Model.gain_blk_offset, kernel_shape=(5, 5))
+    with RasterFuse(src_ra, ref_ra, proc_crs=ProcCrs(proc_crs)) as fuse:
+        f32, _ = fuse.process(**kw)
+        out, _ = fuse.process(out_profile=dict(dtype=dtype, nodata=nodata), **kw)
+    assert str(out.array.dtype).replace('torch.', '') == dtype
+    a = f32.array.cpu().numpy()
+    exp = kmnp.convert_dtype(a, dtype, nodata)
+    got = out.array.cpu().numpy()
+    if dtype == 'uint16':
+        got = got.view('uint16')
+    assert np.array_equal(got, exp, equal_nan=True), f'{int((got != exp).sum())} pixels differ'
+    # host rasters: the narrow plane is what crosses PCIe
+    with RasterFuse(src_ra.to_host(), ref_ra.to_host(), proc_crs=ProcCrs(proc_crs)) as fuse:
+        out_h, _ = fuse.process(out_profile=dict(dtype=dtype, nodata=nodata), **kw)
+    got_h = np.asarray(out_h.array)
+    assert np.array_equal(got_h.view(exp.dtype) if got_h.dtype != exp.dtype else got_h, exp, equal_nan=True)
 
 
 def test_bench_contract_on_gpu():
