@@ -38,10 +38,12 @@ SIGNATURES = {
     'hb_block_norm_workspace_bytes': (c_size_t, [c_long]),
     'hb_block_norm': (c_int, [c_void_p, c_int, c_double, c_void_p, c_int, c_double, c_long, c_void_p, c_void_p,
                               c_size_t, c_void_p]),
-    'hb_block_norm_accum_bytes': (c_size_t, []),
-    'hb_block_norm_partial': (c_int, [c_int, c_void_p, c_int, c_double, c_void_p, c_int, c_double, c_long, c_void_p,
-                                      c_size_t, c_void_p]),
-    'hb_block_norm_merge': (c_int, [c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    'hb_block_norm_shard_workspace_bytes': (c_size_t, [c_long, c_long]),
+    'hb_block_norm_message_bytes': (c_size_t, [c_long, c_long]),
+    'hb_block_norm_partial': (c_int, [c_int, c_void_p, c_int, c_double, c_void_p, c_int, c_double, c_long, c_long, c_long,
+                                      c_void_p, c_size_t, c_void_p]),
+    'hb_block_norm_merge': (c_int, [c_int, c_void_p, c_int, c_int, c_long, c_long, c_void_p, c_size_t, c_void_p,
+                                    c_void_p]),
     'hb_fit_same_grid': (c_int, [c_void_p, c_int, c_double, c_void_p, c_int, c_double, c_long, c_long, c_int, c_int,
                                  c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'hb_fit_apply_same_grid': (c_int, [c_void_p, c_int, c_double, c_void_p, c_int, c_double, c_long, c_long, c_int,

@@ -20,11 +20,13 @@ pixels (utils.py:136-153).  Two regimes follow:
   - **block statistics** of gain-blk-offset (`block_norm_sharded`): ``_fit_block_norm`` (kernel_model.py:216-229) is a
     statistic of the WHOLE block, so its three streaming passes (counts + sums + 12-bit key histograms; squared
     deviations + next 12 bits; last 8 bits) run on each rank's own rows and every pass ends in one all-gather of the
-    131 KB of accumulators, summed in rank order by every rank (bit-identical statistics everywhere).  No rank ever
-    reads another rank's pixels.
+    message (131 KB of accumulators, the shard's first / last valid pixels and its pairwise-leaf sums), merged in rank
+    order by every rank: bit-identical statistics everywhere, and -- numpy's float32 pairwise ``np.std`` being replayed
+    over the concatenation of the shards' valid pixels -- identical to the unsharded statistics.  No rank ever reads
+    another rank's pixels beyond those few.
 
-  Results equal the single-GPU results up to the summation order of the fit kernel's running sums and of the block
-  sums (> 99.9 % of the parameters bit-identical).
+  Results equal the single-GPU results up to the summation order of the fit kernel's running sums (> 99.9 % of the
+  parameters bit-identical; the block statistics are identical).
 
 All timing of multi-GPU runs is done by the caller on the device (bench.py: CUDA events, max over ranks).
 """
@@ -214,7 +216,8 @@ def _all_gather_bytes(local: torch.Tensor, group=None) -> torch.Tensor:
 class NativeBlockNorm:
     """ The three accumulate / merge passes of ``hb_block_norm_partial`` / ``hb_block_norm_merge`` on device planes. """
 
-    def __init__(self, src_local: torch.Tensor, src_nodata, ref_local: torch.Tensor, ref_nodata):
+    def __init__(self, src_local: torch.Tensor, src_nodata, ref_local: torch.Tensor, ref_nodata, n_local_max: int,
+                 n_total: int, rank: int):
         from homonim_b200 import _native
         from homonim_b200 import kernel_model as km
         self._km, self._lib = km, _native.lib()
@@ -224,39 +227,56 @@ class NativeBlockNorm:
             raise ValueError('block statistics need contiguous planes (row ranges of a plane are fine)')
         self.src, self.ref = src_local, ref_local
         self.n = int(src_local.numel())
+        self.n_local_max, self.n_total, self.rank = int(n_local_max), int(n_total), int(rank)
         self.s_nd, self.r_nd = km._nodata_args(src_nodata), km._nodata_args(ref_nodata)
-        self.ws_bytes = int(self._lib.hb_block_norm_workspace_bytes(max(self.n, 1)))
-        self.accum_bytes = int(self._lib.hb_block_norm_accum_bytes())
+        self.ws_bytes = int(self._lib.hb_block_norm_shard_workspace_bytes(self.n_local_max, self.n_total))
+        self.msg_bytes = int(self._lib.hb_block_norm_message_bytes(self.n_local_max, self.n_total))
         self.work = torch.empty(self.ws_bytes, dtype=torch.uint8, device=src_local.device)
         self.norm = torch.empty(2, dtype=torch.float64, device=src_local.device)
 
     def partial(self, level: int) -> torch.Tensor:
         km = self._km
         km._call('hb_block_norm_partial', level, self.src.data_ptr() if self.n else None, self.s_nd[0], self.s_nd[1],
-                 self.ref.data_ptr() if self.n else None, self.r_nd[0], self.r_nd[1], self.n, self.work.data_ptr(),
-                 self.ws_bytes, km._stream())
-        return self.work[:self.accum_bytes]
+                 self.ref.data_ptr() if self.n else None, self.r_nd[0], self.r_nd[1], self.n, self.n_local_max,
+                 self.n_total, self.work.data_ptr(), self.ws_bytes, km._stream())
+        return self.work[:self.msg_bytes]
 
     def merge(self, level: int, gathered: torch.Tensor, world: int):
         km = self._km
-        km._call('hb_block_norm_merge', level, gathered.data_ptr(), world, self.work.data_ptr(), self.ws_bytes,
-                 self.norm.data_ptr(), km._stream())
+        km._call('hb_block_norm_merge', level, gathered.data_ptr(), world, self.rank, self.n_local_max, self.n_total,
+                 self.work.data_ptr(), self.ws_bytes, self.norm.data_ptr(), km._stream())
 
 
 def block_norm_sharded(src_local: torch.Tensor, src_nodata, ref_local: torch.Tensor, ref_nodata, group=None,
-                       backend=NativeBlockNorm) -> torch.Tensor:
+                       backend=NativeBlockNorm, n_local_max: Optional[int] = None, n_total: Optional[int] = None
+                       ) -> torch.Tensor:
     """
     ``KernelModel._fit_block_norm`` (kernel_model.py:216-229) of a block whose rows are spread over the ranks: every rank
-    passes ITS rows of the two planes and gets the two float64 statistics of the whole block (identical on all ranks).
-    Three passes, each followed by one all-gather of the pass's accumulators (counts, sums, histograms; 131 KB per rank)
-    and a merge in rank order.  ``backend`` supplies the two native steps (the CPU tests substitute a numpy stand-in to
-    exercise this protocol over gloo).
+    passes ITS rows of the two planes and gets the two float64 statistics of the whole block -- identical on all ranks,
+    and (blocks up to 2^28 pixels) identical to the unsharded ``hb_block_norm``, numpy's pairwise float32 ``np.std``
+    included.  Three passes, each followed by one all-gather of the pass's message (counts, sums, histograms, the shard's
+    first / last valid pixels and its pairwise-leaf sums; ~131 KB + 1/8 byte per pixel) and a merge in rank order.
+    ``n_local_max`` / ``n_total``: pixels of the largest shard / of the whole block (callers that partition the raster
+    know them; otherwise one small all-reduce finds them).  ``backend`` supplies the two native steps (the CPU tests
+    substitute a numpy stand-in to exercise this protocol over gloo).
     """
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    state = backend(src_local, src_nodata, ref_local, ref_nodata)
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = int(src_local.numel())
+    if n_local_max is None or n_total is None:
+        if world > 1:
+            counts = torch.tensor([n, n], dtype=torch.int64, device=src_local.device if not _host_staged(src_local, group)
+                                  else 'cpu')
+            total, largest = counts[:1].clone(), counts[1:].clone()
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(largest, op=dist.ReduceOp.MAX, group=group)
+            n_total, n_local_max = int(total.item()), int(largest.item())
+        else:
+            n_total = n_local_max = n
+    state = backend(src_local, src_nodata, ref_local, ref_nodata, max(int(n_local_max), 1), max(int(n_total), 1), rank)
     for level in range(3):
-        acc = state.partial(level)
-        gathered = _all_gather_bytes(acc, group) if world > 1 else acc
+        msg = state.partial(level)
+        gathered = _all_gather_bytes(msg, group) if world > 1 else msg
         state.merge(level, gathered, world)
     return state.norm
 
@@ -332,7 +352,9 @@ def fuse_refspace_sharded(model, src_local: RasterArray, ref_ra: RasterArray, ba
     # 2. whole-block statistics from per-rank accumulators
     norm = None
     if model.model == Model.gain_blk_offset:
-        norm = block_norm_sharded(src_ds_local, nan, ref_t[a:b], ref_ra.nodata, group)
+        widest = max(bands.size(g) for g in range(len(bands.starts) - 1)) * ref_ra.width
+        norm = block_norm_sharded(src_ds_local, nan, ref_t[a:b], ref_ra.nodata, group, n_local_max=widest,
+                                  n_total=ref_ra.height * ref_ra.width)
     # 3. halo rows of the down-sampled plane, point to point
     inpaint = model.model == Model.gain_offset and model._r2_inpaint_thresh is not None
     halo = halo_rows(model.kernel_shape, proc_crs_ref=True, inpaint=inpaint)
@@ -361,7 +383,10 @@ def fit_same_grid_sharded(model, src_local: torch.Tensor, src_nodata, ref_local:
     rank = dist.get_rank(group)
     norm = None
     if model.model == Model.gain_blk_offset:
-        norm = block_norm_sharded(src_local.contiguous(), src_nodata, ref_local.contiguous(), ref_nodata, group)
+        width = int(src_local.shape[-1])
+        norm = block_norm_sharded(src_local.contiguous(), src_nodata, ref_local.contiguous(), ref_nodata, group,
+                                  n_local_max=max(bands.size(g) for g in range(len(bands.starts) - 1)) * width,
+                                  n_total=bands.starts[-1] * width)
     src_ext, top = exchange_halos(src_local, bands, halo, group)
     ref_ext, _ = exchange_halos(ref_local, bands, halo, group)
     return model._fit_planes(src_ext.contiguous(), src_nodata, ref_ext.contiguous(), ref_nodata, norm=norm,
@@ -386,7 +411,10 @@ def fit_apply_same_grid_sharded(model, src_ext: torch.Tensor, src_nodata, ref_ex
     top, n_local = a - lo, b - a
     norm = None
     if model.model == Model.gain_blk_offset:
-        norm = block_norm_sharded(src_ext[top:top + n_local], src_nodata, ref_ext[top:top + n_local], ref_nodata, group)
+        width = int(src_ext.shape[-1])
+        norm = block_norm_sharded(src_ext[top:top + n_local], src_nodata, ref_ext[top:top + n_local], ref_nodata, group,
+                                  n_local_max=max(bands.size(g) for g in range(len(bands.starts) - 1)) * width,
+                                  n_total=bands.starts[-1] * width)
     if dist.is_initialized():
         exchange_halos_inplace(src_ext, bands, halo, group)
         exchange_halos_inplace(ref_ext, bands, halo, group)

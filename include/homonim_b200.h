@@ -65,7 +65,9 @@ int hb_downsample_average(const void *src_dev, int src_dtype, long hs, long ws, 
  * Block normalisation statistics: KernelModel._fit_block_norm (kernel_model.py:216-229).
  *   norm[0] = std(ref[mask]) / std(src[mask]);  norm[1] = P1(ref[mask]) - P1(src[mask]) * norm[0]
  * over mask = valid(src) & valid(ref), numpy-linear 1st percentile; {0, 0} for an empty mask.
- * norm_dev: 2 doubles on the device.  workspace_dev: hb_block_norm_workspace_bytes(n) bytes of device scratch.
+ * norm_dev: 2 doubles on the device.  workspace_dev: hb_block_norm_workspace_bytes(n) bytes of device scratch,
+ * 256-byte aligned.  Up to 2^28 pixels the float32 standard deviations replay numpy's pairwise float32 np.std to the bit
+ * (compaction of the valid pixels in C order + numpy's summation tree); larger blocks use double accumulation.
  * --------------------------------------------------------------------------------------------------------------- */
 size_t hb_block_norm_workspace_bytes(long n);
 int hb_block_norm(const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
@@ -75,19 +77,24 @@ int hb_block_norm(const float *src_dev, int src_has_nodata, double src_nodata, c
 /* Row-band shards (one raster split by rows over several GPUs): _fit_block_norm is a statistic of the
  * WHOLE block (kernel_model.py:216-229), so the three streaming passes of hb_block_norm are run per shard and resolved
  * after an exchange.  Per level (0, 1, 2, in this order), every rank calls
- *     hb_block_norm_partial(level, its rows of both planes, n_local, workspace)       -- accumulate only
- * all-gathers the first hb_block_norm_accum_bytes() bytes of its workspace (counts, sums, histograms of the level)
- * into `gathered_dev` = world x accum_bytes, in rank order, and calls
- *     hb_block_norm_merge(level, gathered_dev, world, workspace, norm_dev)            -- sum over ranks + resolve
- * The merge adds the ranks' accumulators in rank order, so every rank derives bit-identical statistics; after level 2
- * norm_dev holds the same two doubles hb_block_norm gives for the unsharded planes (the double sums are associated
- * per rank, so the float32 standard deviations can differ from the unsharded ones in the last bit).  n_local may be 0. */
-size_t hb_block_norm_accum_bytes(void);
+ *     hb_block_norm_partial(level, its rows of both planes, n_local, ...)             -- accumulate only
+ * all-gathers the first hb_block_norm_message_bytes(n_local_max, n_total) bytes of its workspace (the level's counts,
+ * sums, histograms, the shard's first / last valid pixels and its pairwise-leaf sums) into `gathered_dev` = world x
+ * message_bytes, in rank order, and calls
+ *     hb_block_norm_merge(level, gathered_dev, world, rank, ...)                      -- sum over ranks + resolve
+ * n_local_max = pixels of the largest shard, n_total = pixels of the whole block (both the same on every rank); the
+ * workspace holds hb_block_norm_shard_workspace_bytes(n_local_max, n_total) bytes, 256-byte aligned.  The merge adds the
+ * shards' accumulators in rank order, so every rank derives bit-identical statistics, and up to 2^28 pixels per block
+ * the float32 standard deviations replay numpy's pairwise np.std over the concatenation of the shards' valid pixels:
+ * after level 2 norm_dev holds exactly the two doubles hb_block_norm gives for the unsharded planes.  n_local may be 0;
+ * at most 64 shards. */
+size_t hb_block_norm_shard_workspace_bytes(long n_local_max, long n_total);
+size_t hb_block_norm_message_bytes(long n_local_max, long n_total);
 int hb_block_norm_partial(int level, const float *src_dev, int src_has_nodata, double src_nodata, const float *ref_dev,
-                          int ref_has_nodata, double ref_nodata, long n_local, void *workspace_dev,
-                          size_t workspace_bytes, void *stream);
-int hb_block_norm_merge(int level, const void *gathered_dev, int world, void *workspace_dev, size_t workspace_bytes,
-                        double *norm_dev, void *stream);
+                          int ref_has_nodata, double ref_nodata, long n_local, long n_local_max, long n_total,
+                          void *workspace_dev, size_t workspace_bytes, void *stream);
+int hb_block_norm_merge(int level, const void *gathered_dev, int world, int rank, long n_local_max, long n_total,
+                        void *workspace_dev, size_t workspace_bytes, double *norm_dev, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Same-grid fit: KernelModel.fit -> _fit_gain / _fit_gain_blk_offset / _fit_gain_offset + _r2_array

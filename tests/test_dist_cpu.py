@@ -130,10 +130,12 @@ class _NumpyBlockNorm:
     """ Stand-in for dist.NativeBlockNorm: what hb_block_norm_partial / hb_block_norm_merge compute, in numpy. """
     BINS = 4096
 
-    def __init__(self, src_local, src_nodata, ref_local, ref_nodata):
+    def __init__(self, src_local, src_nodata, ref_local, ref_nodata, n_local_max, n_total, rank):
+        self.sizes = (n_local_max, n_total, rank)
         s, r = src_local.numpy().ravel(), ref_local.numpy().ravel()
         valid = ~np.isnan(s) & ~np.isnan(r)
         self.s, self.r = s[valid], r[valid]
+        _NumpyBlockNorm.last_sizes = self.sizes
         self.norm = torch.zeros(2, dtype=torch.float64)
         self.n, self.mean, self.prefix, self.rank, self.gamma = 0, [0.0, 0.0], [0] * 4, [0] * 4, 0.0
 
@@ -222,6 +224,8 @@ def _norm_worker(rank, world, port, result_dir):
         a, b = bands.band(rank)
         norm = block_norm_sharded(torch.from_numpy(src[a:b].copy()), float('nan'), torch.from_numpy(ref[a:b].copy()),
                                   float('nan'), backend=_NumpyBlockNorm)
+        # (the shard sizes the native back end needs were found with one small all-reduce)
+        assert _NumpyBlockNorm.last_sizes == (max(bands.size(g) for g in range(world)) * w, h * w, rank)
         mask = ~np.isnan(src) & ~np.isnan(ref)
         exp0 = np.std(ref[mask]) / np.std(src[mask])
         exp1 = np.percentile(ref[mask], 1) - np.percentile(src[mask], 1) * exp0

@@ -88,7 +88,7 @@ def _worker(rank, world, port, result_dir, shared_gpu):
         norm_full = km._block_norm(s_full, nan, r_full, nan)
         norm_sh = block_norm_sharded(s_full[a:b], nan, r_full[a:b], nan)
         nf, ns = norm_full.cpu().numpy(), norm_sh.cpu().numpy()
-        assert np.all(np.abs(nf - ns) <= 4e-7 * np.maximum(np.abs(nf), 0.1)), (nf, ns)
+        assert np.array_equal(nf, ns), (nf, ns)          # (numpy's pairwise np.std replayed across the shards: identical)
         # ---- C5b: same grid, gain-blk-offset 15 x 15 (BASELINE configs[4]): statistics merged over the ranks, halo rows
         #      received in place, fit + apply in one kernel on the rank's rows ----------------------------------------------
         for model_name in (Model.gain_blk_offset, Model.gain_offset):
