@@ -516,30 +516,63 @@ class RowBandJob:
             # the (small) reference planes are replicated: gather every rank's rows once, outside the timed region
             self.ref = [hd.all_gather_rows(r, bands, group) if bands.starts[-1] != (b - a) else r for r in self.ref]
         self.local_px = (b - a) * ratio * cfg['wp'] * ratio
+        n_streams = int(os.environ.get('HB_ROW_BAND_STREAMS', '4'))
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(max(1, min(n_streams, cfg['bands'])))]
+        # the small kernels / exchanges between a band's two streaming kernels run on high-priority twins of the streams
+        self.hi_streams = [torch.cuda.Stream(device=device, priority=-1) for _ in self.streams]
         self.out = [torch.empty(((b - a) * ratio, cfg['wp'] * ratio), dtype=torch.float32, device=device)
-                    for _ in range(2)]
-        self.streams = [torch.cuda.Stream(device=device) for _ in range(2)]
+                    for _ in range(len(self.streams))]
+        self.stagger = os.environ.get('HB_ROW_BAND_STAGGER', '1') == '1'
 
     def step(self, keep_band0=None, serial=False):
-        """ All bands; consecutive bands alternate between two streams (and two output planes), so that one band's small
-        kernels and exchanges overlap the other's streaming kernels (``serial``: one stream, for per-kernel timing).
-        ``keep_band0``: tensor receiving band 0's result. """
+        """ All bands, each on its own stream (and output plane), so that one band's small kernels and exchanges overlap the
+        others' streaming kernels (``serial``: one stream, for per-kernel timing).  ``keep_band0``: tensor receiving band
+        0's result. """
         torch, cfg = self.torch, self.cfg
         main = torch.cuda.current_stream()
-        for st in self.streams:
+        for st in self.streams + self.hi_streams:
             st.wait_stream(main)
-        for band in range(cfg['bands']):
-            st = self.streams[0 if serial else band % 2]
-            out = keep_band0 if (band == 0 and keep_band0 is not None) else self.out[band % 2]
-            with torch.cuda.stream(st):
-                if self.same_grid:
+        ns = len(self.streams)
+        pick = (lambda band: 0) if serial else (lambda band: band % ns)
+        outs = [keep_band0 if (band == 0 and keep_band0 is not None) else self.out[pick(band)]
+                for band in range(cfg['bands'])]
+        if self.same_grid:
+            for band in range(cfg['bands']):
+                with torch.cuda.stream(self.streams[pick(band)]):
                     self.hd.fit_apply_same_grid_sharded(self.model, self.src[band], cfg['src_nodata'], self.ref[band],
-                                                        NAN, self.bands, self.group, out=out)
-                else:
+                                                        NAN, self.bands, self.group, out=outs[band])
+        else:
+            # stage 1 of every band first (the down-sampling: a streaming kernel, no communication), then the stages 2:
+            # while the host issues one band's statistics / exchanges / fit, the GPU still has the other bands' streaming
+            # kernels queued.  (serial: band after band on one stream, for the per-kernel timing.)
+            shards = {}
+
+            def begin(band):
+                with torch.cuda.stream(self.streams[pick(band)]):
                     src_local = self.RasterArray(self.src[band], self.crs, self.src_local_tf, nodata=cfg['src_nodata'])
                     ref_ra = self.RasterArray(self.ref[band], self.crs, self.ref_global_tf, nodata=NAN)
-                    self.hd.fuse_refspace_sharded(self.model, src_local, ref_ra, self.bands, self.group, out=out)
-        for st in self.streams:
+                    shards[band] = self.hd.fuse_refspace_sharded_begin(self.model, src_local, ref_ra, self.bands,
+                                                                       self.group)
+
+            def end(band):
+                if serial or not self.stagger:
+                    with torch.cuda.stream(self.streams[pick(band)]):
+                        self.hd.fuse_refspace_sharded_end(shards.pop(band), out=outs[band])
+                else:
+                    with torch.cuda.stream(self.hi_streams[pick(band)]):
+                        self.hd.fuse_refspace_sharded_end(shards.pop(band), out=outs[band],
+                                                          apply_stream=self.streams[pick(band)])
+
+            if serial or not self.stagger:
+                for band in range(cfg['bands']):
+                    begin(band)
+                    end(band)
+            else:
+                for band in range(cfg['bands']):
+                    begin(band)
+                for band in range(cfg['bands']):
+                    end(band)
+        for st in self.streams + self.hi_streams:
             main.wait_stream(st)
 
 
@@ -570,6 +603,8 @@ def measure_row_band(args, cfg, rank, world, local_rank, steps, warmup, with_n1=
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(j, n_steps, n_warm, sync):
         for _ in range(n_warm):
             j.step()
@@ -577,14 +612,17 @@ def measure_row_band(args, cfg, rank, world, local_rank, steps, warmup, with_n1=
         lib.hb_reset_launch_count()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync()
+        t_host = time.perf_counter()
         start.record()
         for _ in range(n_steps):
             j.step()
         end.record()
+        host_ms[0] = (time.perf_counter() - t_host) * 1e3 / n_steps      # host time to ENQUEUE a step (no sync inside)
         sync()
         return start.elapsed_time(end), lib.hb_launch_count()
 
     elapsed_ms, launches = timed(job, steps, warmup, barrier)
+    host_enqueue_ms = host_ms[0]
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -594,6 +632,17 @@ def measure_row_band(args, cfg, rank, world, local_rank, steps, warmup, with_n1=
     with KernelTimer() as timer:
         job.step(serial=True)
         kernel_ms = timer.results()
+    if os.environ.get('HB_ROW_BAND_TRACE') == '1':
+        # where the native calls of one concurrent step ran on the device's clock (diagnostics; EVERY rank runs the step)
+        barrier()
+        barrier_ev = torch.cuda.Event(enable_timing=True)
+        with KernelTimer() as tracer:
+            barrier_ev.record()
+            job.step()
+            lines = tracer.timeline(barrier_ev)
+        if rank == 0:
+            for name, t0_, t1_ in lines:
+                print(f'trace {name:32s} {t0_:8.3f} -> {t1_:8.3f} ms', file=sys.stderr)
     b_in = 4
     # algorithmic bytes per launch: per SOURCE pixel of this rank's rows for the resampling kernels, per proc-grid pixel
     # for the statistics / same-grid kernels
@@ -611,6 +660,7 @@ def measure_row_band(args, cfg, rank, world, local_rank, steps, warmup, with_n1=
         'workload': cfg['desc'], 'value': round(value, 1), 'unit': 'Mpix/s', 'scaling': 'strong', 'n_gpus': world,
         'steps': steps, 'warmup': warmup, 'ms_per_step': round(elapsed_ms / steps, 4), 'gpu_launches': int(launches),
         'pixels_per_step': int(npix_total), 'generate_s': round(gen_s, 1),
+        'host_enqueue_ms_per_step': round(host_enqueue_ms, 3), 'streams': len(job.streams), 'staggered': bool(job.stagger),
         'sharding': f'row bands of {cfg["hp"]} proc rows over {world} rank(s); per band: 3 all-gathers of 131 KB of '
                     f'block statistics + P2P halo rows ({job.halo} proc rows per side); no rank reads another rank\'s '
                     f'pixels',
@@ -723,6 +773,8 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-row-band', action='store_true', help='skip the one-raster (C5a) measurement')
     ap.add_argument('--row-band-workload', default='c5a', choices=['c5a', 'c5b', 'tiny-band'])
+    ap.add_argument('--no-row-band-n1', action='store_true',
+                    help='N > 1: skip the single-GPU run of the same raster on rank 0 (efficiency / stripe parity)')
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', '0'))
@@ -774,7 +826,7 @@ def main():
         if rank == 0:
             sampler.start()
         t0 = time.perf_counter()
-        rb = measure_row_band(args, cfg, rank, world, local_rank, args.steps, args.warmup, with_n1=True)
+        rb = measure_row_band(args, cfg, rank, world, local_rank, args.steps, args.warmup, with_n1=not args.no_row_band_n1)
         t1 = time.perf_counter()
         stop.set()
         if rank == 0:
@@ -968,7 +1020,8 @@ def main():
         fuse.close()
         del fuse, src_ra, ref_ra
         torch.cuda.empty_cache()
-        row_band = measure_row_band(args, rb_cfg, rank, world, local_rank, steps=max(3, min(args.steps, 5)), warmup=3)
+        row_band = measure_row_band(args, rb_cfg, rank, world, local_rank, steps=max(3, min(args.steps, 5)), warmup=3,
+                                    with_n1=not args.no_row_band_n1)
 
     if rank == 0:
         line = {

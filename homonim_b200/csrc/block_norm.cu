@@ -31,6 +31,7 @@ constexpr int kNormThreads = 512;
 constexpr int kHead = 128, kTail = 64;      // compacted pixels a rank shares with its neighbours (a leaf is <= 128 long and
                                             // starts < 64 before the position that owns it)
 constexpr int kMaxWorld = 64;
+constexpr int kNodeDepth = 13, kNodes = 1 << kNodeDepth;   // see norm_nodes_kernel
 
 // What one pass over (a shard of) the planes accumulates and the ranks of a row-band sharded raster exchange: this
 // struct sits at the start of the workspace, immediately followed by the shard's pairwise-leaf sums -- together the
@@ -69,6 +70,8 @@ struct NormWs {
     float2 *comp;                  // compacted pixels with kTail entries of headroom in front and kHead behind
     unsigned int *chunk_cnt;
     unsigned long long *chunk_off;
+    float2 *nodes;                 // sums of the recursion's nodes at depth kNodeDepth (large blocks: computed by many CTAs)
+    unsigned char *node_has;
     long nleaf, nchunks;
     size_t msg_bytes, total;
     int exact;
@@ -376,7 +379,8 @@ __device__ void norm_resolve(NormAccum *__restrict__ acc, NormState *__restrict_
 // every rank derives bit-identical statistics) into this shard's accumulators and resolve the level.  One CTA.
 // Level 0 also lays out the compacted pixels of all shards (off[]) and completes this shard's compacted array with the
 // neighbours' first / last pixels; levels 1 / 2 first combine the shards' pairwise-leaf sums up numpy's tree (exact mode).
-template <int LEVEL> __device__ void norm_tree(const char *gathered, size_t msg_bytes, NormState *st);
+template <int LEVEL> __device__ void norm_tree(const char *gathered, size_t msg_bytes, NormState *st, const float2 *nodes,
+                                               const unsigned char *node_has);
 
 template <int LEVEL>
 __global__ void __launch_bounds__(kNormThreads)
@@ -388,7 +392,7 @@ norm_merge_kernel(NormWs ws, const char *__restrict__ gathered, size_t msg_bytes
     constexpr int bins = (LEVEL == 2) ? 256 : kBins;
     constexpr int nq = (LEVEL == 0) ? 3 : 4;                 // level 0 fills hist[0] and hist[2] only
     auto msg = [&](int r) { return reinterpret_cast<const NormAccum *>(gathered + (size_t)r * msg_bytes); };
-    if (ws.exact && LEVEL > 0) norm_tree<LEVEL>(gathered, msg_bytes, st);      // (reads the gathered leaf sums only)
+    if (ws.exact && LEVEL > 0) norm_tree<LEVEL>(gathered, msg_bytes, st, ws.nodes, ws.node_has);   // (nodes: norm_nodes_kernel)
     if (gathered != reinterpret_cast<const char *>(acc)) {   // (one shard: the message IS the accumulator, nothing to add)
         for (int i = threadIdx.x; i < nq * bins; i += blockDim.x) {
             const int q = i / bins, b = i % bins;
@@ -644,12 +648,47 @@ __device__ float2 pw_node_sum(const LeafTable &lt, long start, long len)
     return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
 }
 
+// the node of numpy's recursion over [0, n) reached from the root by the `depth` bits of `k` (most significant first);
+// false when that path ends in a leaf before `depth` steps and k is not the path's first index (the leaf is then held by
+// the index whose remaining bits are zero)
+__device__ __forceinline__ bool pw_path_node(long n, int k, int depth, long &start, long &len)
+{
+    start = 0; len = n;
+    if (n <= 0) return false;
+    for (int level = 0; level < depth; level++) {
+        if (len <= 128) return (k & ((1 << (depth - level)) - 1)) == 0;
+        long n2 = len / 2;
+        n2 -= n2 % 8;
+        if ((k >> (depth - 1 - level)) & 1) { start += n2; len -= n2; }
+        else len = n2;
+    }
+    return true;
+}
+
+// Large blocks: the sums of the recursion's nodes at depth kNodeDepth, one thread per node, so that the one-CTA merge only
+// has the top of the tree left (a block of 9 M pixels has ~94 000 leaves: ~12 per node here, instead of ~180 per thread of
+// the merge CTA).
+__global__ void __launch_bounds__(256)
+norm_nodes_kernel(NormWs ws, const char *__restrict__ gathered, size_t msg_bytes)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= kNodes) return;
+    const NormState *st = ws.st;
+    const LeafTable lt{gathered, msg_bytes, st};
+    long start, len;
+    const bool mine = pw_path_node((long)st->off[st->world], k, kNodeDepth, start, len);
+    ws.node_has[k] = mine ? 1 : 0;
+    ws.nodes[k] = mine ? pw_node_sum(lt, start, len) : make_float2(0.f, 0.f);
+}
+
 // Combine the leaves up numpy's tree (all threads of the merge CTA): thread t takes the node reached from the root by
-// the bits of t (most significant first), sums its subtree, and the top levels are reduced pairwise in shared memory
-// (left + right).  A node that is already a leaf above that depth is held by the thread whose remaining bits are zero.
+// the bits of t (most significant first) and sums its subtree -- from the precomputed depth-kNodeDepth nodes when given,
+// else leaf by leaf -- and the top levels are reduced pairwise in shared memory (left + right).  A node that is already
+// a leaf above a cut is held by the index whose remaining bits are zero; absent nodes are skipped.
 // LEVEL 1: the sums of x -> numpy's float32 means; LEVEL 2: the sums of (x - mean)^2 -> the float32 standard deviations.
 template <int LEVEL>
-__device__ void norm_tree(const char *gathered, size_t msg_bytes, NormState *st)
+__device__ void norm_tree(const char *gathered, size_t msg_bytes, NormState *st, const float2 *nodes,
+                          const unsigned char *node_has)
 {
     constexpr int depth = 9, nthreads = 1 << depth;        // == kNormThreads
     static_assert(nthreads == kNormThreads, "one tree node per thread of the merge CTA");
@@ -657,21 +696,28 @@ __device__ void norm_tree(const char *gathered, size_t msg_bytes, NormState *st)
     __shared__ unsigned char s_has[nthreads];
     const long n = (long)st->off[st->world];
     const int t = threadIdx.x;
-    const LeafTable lt{gathered, msg_bytes, st};
-    long start = 0, len = n;
-    bool mine = n > 0;
-    for (int level = 0; level < depth && mine; level++) {
-        if (len <= 128) {                              // a leaf above the cut: only the all-zero suffix owns it
-            mine = (t & ((1 << (depth - level)) - 1)) == 0;
-            break;
+    if (nodes != nullptr) {
+        constexpr int per = kNodes / nthreads;             // this thread's depth-kNodeDepth nodes: one complete subtree
+        float2 v[per];
+        bool has[per];
+#pragma unroll
+        for (int i = 0; i < per; i++) { v[i] = __ldcg(&nodes[t * per + i]); has[i] = __ldcg(&node_has[t * per + i]) != 0; }
+#pragma unroll
+        for (int sdist = 1; sdist < per; sdist <<= 1) {
+#pragma unroll
+            for (int i = 0; i < per; i += 2 * sdist) {
+                if (has[i] && has[i + sdist]) v[i] = make_float2(__fadd_rn(v[i].x, v[i + sdist].x), __fadd_rn(v[i].y, v[i + sdist].y));
+            }
         }
-        long n2 = len / 2;
-        n2 -= n2 % 8;
-        if ((t >> (depth - 1 - level)) & 1) { start += n2; len -= n2; }
-        else len = n2;
+        s_has[t] = has[0] ? 1 : 0;
+        s_val[t] = v[0];
+    } else {
+        const LeafTable lt{gathered, msg_bytes, st};
+        long start, len;
+        const bool mine = pw_path_node(n, t, depth, start, len);
+        s_has[t] = mine ? 1 : 0;
+        s_val[t] = mine ? pw_node_sum(lt, start, len) : make_float2(0.f, 0.f);
     }
-    s_has[t] = mine ? 1 : 0;
-    s_val[t] = mine ? pw_node_sum(lt, start, len) : make_float2(0.f, 0.f);
     __syncthreads();
     for (int sdist = 1; sdist < nthreads; sdist <<= 1) {
         if ((t % (2 * sdist)) == 0 && s_has[t] && s_has[t + sdist]) {
@@ -836,7 +882,7 @@ norm_coop_kernel(const float *__restrict__ src, NoData nd_s, const float *__rest
         }
         norm_grid_sync(counter, epoch);
         if (blockIdx.x == 0) {
-            if (ws.exact && LEVEL > 0) norm_tree<LEVEL>(reinterpret_cast<const char *>(acc), ws.msg_bytes, st);
+            if (ws.exact && LEVEL > 0) norm_tree<LEVEL>(reinterpret_cast<const char *>(acc), ws.msg_bytes, st, nullptr, nullptr);
             norm_resolve<LEVEL>(acc, st, norm);           // (also clears the histograms for the next level)
         }
         norm_grid_sync(counter, epoch);
@@ -872,6 +918,8 @@ NormWs norm_layout(void *workspace, long n_local_max, long n_total)
     ws.comp = (float2 *)(base + off); off += ws.exact ? al((size_t)(n_local_max + kTail + kHead) * sizeof(float2)) : 0;
     ws.chunk_cnt = (unsigned int *)(base + off); off += al((size_t)ws.nchunks * sizeof(unsigned int));
     ws.chunk_off = (unsigned long long *)(base + off); off += al((size_t)ws.nchunks * sizeof(unsigned long long));
+    ws.nodes = (float2 *)(base + off); off += ws.exact ? al((size_t)kNodes * sizeof(float2)) : 0;
+    ws.node_has = (unsigned char *)(base + off); off += ws.exact ? al((size_t)kNodes) : 0;
     ws.total = off;
     return ws;
 }
@@ -950,6 +998,10 @@ int norm_partial(int level, const float *src_dev, const NoData &nd_s, const floa
 int norm_merge(int level, const NormWs &ws, const void *gathered, int world, int rank_id, double *norm_dev, cudaStream_t st)
 {
     const char *g = (const char *)gathered;
+    if (ws.exact && level > 0) {
+        norm_nodes_kernel<<<kNodes / 256, 256, 0, st>>>(ws, g, ws.msg_bytes);
+        HB_LAUNCH_OK("norm_nodes_kernel");
+    }
     if (level == 0) norm_merge_kernel<0><<<1, kNormThreads, 0, st>>>(ws, g, ws.msg_bytes, world, rank_id, norm_dev);
     else if (level == 1) norm_merge_kernel<1><<<1, kNormThreads, 0, st>>>(ws, g, ws.msg_bytes, world, rank_id, norm_dev);
     else norm_merge_kernel<2><<<1, kNormThreads, 0, st>>>(ws, g, ws.msg_bytes, world, rank_id, norm_dev);

@@ -108,6 +108,22 @@ def halo_rows(kernel_shape: Sequence[int], proc_crs_ref: bool, inpaint: bool) ->
     return int(kernel_shape[0]) // 2 + (2 if proc_crs_ref else 0) + (100 if inpaint else 0)
 
 
+def _halo_peers(bands: RowBands, rank: int, halo: int) -> List[int]:
+    """ Ranks that exchange rows with ``rank``: those whose band lies within ``halo`` rows of its band, on either side. """
+    a, b = bands.band(rank)
+    world = len(bands.starts) - 1
+    peers = []
+    for peer in range(rank - 1, -1, -1):                 # upwards until a band starts more than `halo` rows above
+        peers.append(peer)
+        if bands.starts[peer] <= a - halo:
+            break
+    for peer in range(rank + 1, world):                  # downwards likewise
+        peers.append(peer)
+        if bands.starts[peer + 1] >= b + halo:
+            break
+    return peers
+
+
 def exchange_halos(local: torch.Tensor, bands: RowBands, halo: int, group=None) -> Tuple[torch.Tensor, int]:
     """
     Point-to-point halo exchange between row-band neighbours.
@@ -124,9 +140,7 @@ def exchange_halos(local: torch.Tensor, bands: RowBands, halo: int, group=None) 
     sends, recvs, recv_bufs = [], [], []
     lead = local.shape[:-2]
     width = local.shape[-1]
-    for peer in range(world):
-        if peer == rank:
-            continue
+    for peer in _halo_peers(bands, rank, halo):
         pa, pb = bands.band(peer)
         plo, phi = bands.with_halo(peer, halo)
         # rows of mine that the peer needs
@@ -204,6 +218,9 @@ def _all_gather_bytes(local: torch.Tensor, group=None) -> torch.Tensor:
         dist.all_gather(parts, local.cpu(), group=group)
         return torch.cat(parts).to(local.device)
     out = torch.empty(world * local.numel(), dtype=local.dtype, device=local.device)
+    if local.is_cuda:
+        dist.all_gather_into_tensor(out, local, group=group)
+        return out
     try:
         dist.all_gather_into_tensor(out, local, group=group)
     except (RuntimeError, NotImplementedError):          # back ends without the flat variant
@@ -215,6 +232,7 @@ def _all_gather_bytes(local: torch.Tensor, group=None) -> torch.Tensor:
 
 class NativeBlockNorm:
     """ The three accumulate / merge passes of ``hb_block_norm_partial`` / ``hb_block_norm_merge`` on device planes. """
+    _sizes: dict = {}
 
     def __init__(self, src_local: torch.Tensor, src_nodata, ref_local: torch.Tensor, ref_nodata, n_local_max: int,
                  n_total: int, rank: int):
@@ -229,8 +247,11 @@ class NativeBlockNorm:
         self.n = int(src_local.numel())
         self.n_local_max, self.n_total, self.rank = int(n_local_max), int(n_total), int(rank)
         self.s_nd, self.r_nd = km._nodata_args(src_nodata), km._nodata_args(ref_nodata)
-        self.ws_bytes = int(self._lib.hb_block_norm_shard_workspace_bytes(self.n_local_max, self.n_total))
-        self.msg_bytes = int(self._lib.hb_block_norm_message_bytes(self.n_local_max, self.n_total))
+        key = (self.n_local_max, self.n_total)
+        if key not in NativeBlockNorm._sizes:
+            NativeBlockNorm._sizes[key] = (int(self._lib.hb_block_norm_shard_workspace_bytes(*key)),
+                                           int(self._lib.hb_block_norm_message_bytes(*key)))
+        self.ws_bytes, self.msg_bytes = NativeBlockNorm._sizes[key]
         self.work = torch.empty(self.ws_bytes, dtype=torch.uint8, device=src_local.device)
         self.norm = torch.empty(2, dtype=torch.float64, device=src_local.device)
 
@@ -307,9 +328,7 @@ def exchange_halos_inplace(ext: torch.Tensor, bands: RowBands, halo: int, group=
     if ext.shape[-2] != hi - lo:
         raise ValueError(f'`ext` must hold the {hi - lo} rows of the band with its halo, not {ext.shape[-2]}')
     sends, recvs = [], []
-    for peer in range(world):
-        if peer == rank:
-            continue
+    for peer in _halo_peers(bands, rank, halo):
         pa, pb = bands.band(peer)
         plo, phi = bands.with_halo(peer, halo)
         s0, s1 = max(a, plo), min(b, phi)                # rows of mine that the peer needs
@@ -324,6 +343,89 @@ def exchange_halos_inplace(ext: torch.Tensor, bands: RowBands, halo: int, group=
 # ---------------------------------------------------------------------------------------------------------------------
 # the two sharded regimes
 # ---------------------------------------------------------------------------------------------------------------------
+class _RefspaceShard(NamedTuple):
+    """ State between the two stages of `fuse_refspace_sharded` (one band of one rank). """
+    model: object
+    src_t: torch.Tensor
+    src_local: RasterArray
+    ref_ra: RasterArray
+    ref_t: torch.Tensor
+    bands: RowBands
+    group: object
+    src_ds_local: torch.Tensor
+    ds_done: object            # CUDA event: the down-sampling has finished (None on the host back end)
+
+
+def fuse_refspace_sharded_begin(model, src_local: RasterArray, ref_ra: RasterArray, bands: RowBands, group=None
+                                ) -> _RefspaceShard:
+    """
+    First stage of `fuse_refspace_sharded`: the down-sampling of this rank's source rows (the first of the band's two
+    streaming kernels; no communication).  Callers with several bands enqueue this stage for ALL bands first and the
+    second stages afterwards: the GPU then always has a streaming kernel queued while the host issues the small kernels
+    and exchanges of the second stages (with a slab of a few thousand rows per rank those are host-paced, not GPU-paced).
+    """
+    from homonim_b200 import kernel_model as km
+    rank = dist.get_rank(group)
+    a, b = bands.band(rank)
+    src_t = km._to_device(src_local.array)
+    ref_t = km._as_f32_plane(km._to_device(ref_ra.array), ref_ra.nodata).contiguous()
+    local_tf = ref_ra.transform * Affine.translation(0, a)
+    src_ds_local = km._downsample_average(src_t, src_local.transform, src_local.nodata, (b - a, ref_ra.width), local_tf)
+    ds_done = None
+    if src_ds_local.is_cuda:
+        ds_done = torch.cuda.Event()
+        ds_done.record()
+    return _RefspaceShard(model, src_t, src_local, ref_ra, ref_t, bands, group, src_ds_local, ds_done)
+
+
+def fuse_refspace_sharded_end(shard: _RefspaceShard, out=None, apply_stream=None) -> Tuple[RasterArray, RasterArray]:
+    """
+    Second stage of `fuse_refspace_sharded`: block statistics merged over the ranks, halo rows, fit, up-sample + apply.
+
+    The stage may run on a different stream than the first (it waits for the down-sampling's event), and
+    ``apply_stream`` (optional) receives the final up-sample + apply kernel.  That lets a caller keep the two STREAMING
+    kernels of every band on low-priority streams and this stage's small kernels and exchanges on a high-priority one:
+    the block scheduler dispatches pending kernels of equal priority in launch order, so at equal priority a small
+    kernel launched behind another band's streaming kernel only runs once that kernel has handed out all its CTAs
+    (measured: the stages then simply add up); with priorities it slips in between.
+    """
+    from homonim_b200.enums import Model
+    model, src_t, src_local, ref_ra, ref_t, bands, group, src_ds_local, ds_done = shard
+    rank = dist.get_rank(group)
+    a, b = bands.band(rank)
+    nan = float('nan')
+    if ds_done is not None:
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ds_done)
+        src_ds_local.record_stream(cur)
+    # whole-block statistics from per-rank accumulators
+    norm = None
+    if model.model == Model.gain_blk_offset:
+        widest = max(bands.size(g) for g in range(len(bands.starts) - 1)) * ref_ra.width
+        norm = block_norm_sharded(src_ds_local, nan, ref_t[a:b], ref_ra.nodata, group, n_local_max=widest,
+                                  n_total=ref_ra.height * ref_ra.width)
+    # halo rows of the down-sampled plane, point to point
+    inpaint = model.model == Model.gain_offset and model._r2_inpaint_thresh is not None
+    halo = halo_rows(model.kernel_shape, proc_crs_ref=True, inpaint=inpaint)
+    lo, hi, plo, phi = fit_row_window(bands, rank, halo)
+    src_ds, _ = exchange_halos(src_ds_local, bands, halo, group)
+    # fit the rows my source rows' spline taps touch, inside the held window
+    params = model._fit_planes(src_ds, nan, ref_t[lo:hi], ref_ra.nodata, norm=norm, rows=(plo - lo, phi - plo))
+    param_ra = RasterArray(params, ref_ra.crs, ref_ra.transform * Affine.translation(0, plo), nodata=nan)
+    # apply to my source rows
+    src_ra = RasterArray(src_t, src_local.crs, src_local.transform, nodata=src_local.nodata)
+    if apply_stream is not None and params.is_cuda:
+        fitted = torch.cuda.Event()
+        fitted.record()
+        apply_stream.wait_event(fitted)
+        params.record_stream(apply_stream)
+        with torch.cuda.stream(apply_stream):
+            corr_local = model.apply(src_ra, param_ra, out=out)
+    else:
+        corr_local = model.apply(src_ra, param_ra, out=out)
+    return corr_local, param_ra
+
+
 def fuse_refspace_sharded(model, src_local: RasterArray, ref_ra: RasterArray, bands: RowBands, group=None, out=None
                           ) -> Tuple[RasterArray, RasterArray]:
     """
@@ -335,38 +437,12 @@ def fuse_refspace_sharded(model, src_local: RasterArray, ref_ra: RasterArray, ba
     proc-grid rows they depend on (this rank's band plus the 2 rows of cubic-spline support on either side;
     ``param_ra.transform`` points at them).  ``out`` (optional): float32 CUDA tensor to receive the corrected rows.
 
-    Per rank: down-sample own rows -> block statistics over own proc rows, merged by `block_norm_sharded`
-    (gain-blk-offset) -> halo rows of the down-sampled source from the neighbours -> fit of the rows the up-sampler
-    needs -> up-sample + apply on own source rows.  No rank reads pixels outside its band + halo.
+    Per rank: down-sample own rows (`fuse_refspace_sharded_begin`) -> block statistics over own proc rows, merged by
+    `block_norm_sharded` (gain-blk-offset) -> halo rows of the down-sampled source from the neighbours -> fit of the rows
+    the up-sampler needs -> up-sample + apply on own source rows (`fuse_refspace_sharded_end`).  No rank reads pixels
+    outside its band + halo.
     """
-    from homonim_b200 import kernel_model as km
-    from homonim_b200.enums import Model
-    rank = dist.get_rank(group)
-    a, b = bands.band(rank)
-    nan = float('nan')
-    src_t = km._to_device(src_local.array)
-    ref_t = km._as_f32_plane(km._to_device(ref_ra.array), ref_ra.nodata).contiguous()
-    # 1. down-sample my source rows onto my proc rows
-    local_tf = ref_ra.transform * Affine.translation(0, a)
-    src_ds_local = km._downsample_average(src_t, src_local.transform, src_local.nodata, (b - a, ref_ra.width), local_tf)
-    # 2. whole-block statistics from per-rank accumulators
-    norm = None
-    if model.model == Model.gain_blk_offset:
-        widest = max(bands.size(g) for g in range(len(bands.starts) - 1)) * ref_ra.width
-        norm = block_norm_sharded(src_ds_local, nan, ref_t[a:b], ref_ra.nodata, group, n_local_max=widest,
-                                  n_total=ref_ra.height * ref_ra.width)
-    # 3. halo rows of the down-sampled plane, point to point
-    inpaint = model.model == Model.gain_offset and model._r2_inpaint_thresh is not None
-    halo = halo_rows(model.kernel_shape, proc_crs_ref=True, inpaint=inpaint)
-    lo, hi, plo, phi = fit_row_window(bands, rank, halo)
-    src_ds, _ = exchange_halos(src_ds_local, bands, halo, group)
-    # 4. fit the rows my source rows' spline taps touch, inside the held window
-    params = model._fit_planes(src_ds, nan, ref_t[lo:hi], ref_ra.nodata, norm=norm, rows=(plo - lo, phi - plo))
-    param_ra = RasterArray(params, ref_ra.crs, ref_ra.transform * Affine.translation(0, plo), nodata=nan)
-    # 5. apply to my source rows
-    corr_local = model.apply(RasterArray(src_t, src_local.crs, src_local.transform, nodata=src_local.nodata), param_ra,
-                             out=out)
-    return corr_local, param_ra
+    return fuse_refspace_sharded_end(fuse_refspace_sharded_begin(model, src_local, ref_ra, bands, group), out=out)
 
 
 def fit_same_grid_sharded(model, src_local: torch.Tensor, src_nodata, ref_local: torch.Tensor, ref_nodata,

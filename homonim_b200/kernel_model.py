@@ -114,6 +114,13 @@ class KernelTimer:
             out.setdefault(name, []).append(start.elapsed_time(end))
         return out
 
+    def timeline(self, origin) -> list:
+        """ ``[(entry point, start ms, end ms)]`` relative to the CUDA event ``origin`` (recorded before the calls), in
+        issue order -- where on the device's clock every native call of a multi-stream step ran. """
+        torch.cuda.synchronize()
+        return [(name, round(origin.elapsed_time(start), 3), round(origin.elapsed_time(end), 3))
+                for name, start, end in self._events]
+
 
 def _call(name: str, *args):
     """ Invoke C-ABI entry point ``name`` and raise on failure. """
