@@ -825,17 +825,22 @@ upsample_yfirst_kernel(const T *__restrict__ src, NoData nd, const void *__restr
 // The reference's float32 numerator N*sum(sr) - sum(s)*sum(r) cancels catastrophically, so last-bit differences of the
 // up-sampled pixels are amplified past 1e-4 in the parameters: this path must round like GDAL does -- double
 // accumulation, one rounding to float32 -- and cannot use the packed-float32 kernels above.
-struct __align__(16) RowEntryD { double wy[4]; double sum; double pad; };   // sum: NaN when the row's centre is out of range
-
+struct __align__(16) RowEntryD { double wy[4]; double sum; double jc; };   // sum: NaN when the row's centre is out of range;
+                                                                            // jc: tap row (0..3) of the centre coarse row, -1: none
+// Self-contained (no classification pre-pass, no fix-up kernel): a lane keeps the 4 tap rows x 6 window columns of its 4
+// pixels in registers -- when the tap rows advance by one coarse row (every `ratio` destination rows) the window is
+// SHIFTED and only the new row is loaded -- and evaluates every destination row with the fast separable formula (all
+// taps valid).  A NaN result means some tap was invalid (or the pixel has no valid centre): those pixels, and only
+// those, are re-evaluated from the same registers with GDAL's general rule (invalid / out-of-range taps dropped,
+// renormalised unless the remaining weights sum to 1 within 1e-5, nodata when the centre coarse pixel is invalid or the
+// weights sum to < 1e-6), in the accumulation order of the fix-up kernel of the two-band path.
 __global__ void __launch_bounds__(kThreads, 2)
-upsample_yfirst_f64_kernel(const float *__restrict__ coarse, const uint8_t *__restrict__ flags, UpPolyGeom g,
-                           int rows_per_cta, float *__restrict__ out)
+upsample_yfirst_f64_kernel(const float *__restrict__ coarse, UpPolyGeom g, int rows_per_cta, float *__restrict__ out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long Y0 = (long)blockIdx.y * rows_per_cta;
     const int nrows = (int)min((long)rows_per_cta, g.hs - Y0);
-    const float qnan = __int_as_float(0x7fc00000);
     const double dnan = __longlong_as_double(0x7ff8000000000000LL);
 
     RowEntryD *s_rows = reinterpret_cast<RowEntryD *>(smem_raw);
@@ -846,20 +851,23 @@ upsample_yfirst_f64_kernel(const float *__restrict__ coarse, const uint8_t *__re
         bool ok;
         up_axis_weights_raw(g.sy, g.oy, Y0 + threadIdx.x, g.hp, e.wy, ky, e.sum, ok);
         if (!ok) e.sum = dnan;
-        e.pad = 0.0;
+        const double srcy = up_src_coord(g.sy, g.oy, Y0 + threadIdx.x);
+        long cy = (long)floor(srcy + 1e-10);
+        if (cy == g.hp) cy--;
+        const long jc = cy - (ky - 1);
+        e.jc = (ok && jc >= 0 && jc <= 3) ? (double)jc : -1.0;
         s_rows[threadIdx.x] = e;
         s_ky[threadIdx.x] = (int)min(max(ky, -4L), g.hp + 4);
     }
     __syncthreads();
 
     const long X0 = ((long)blockIdx.x * kWarps + warp) * kWarpW + (long)lane * kPpt;
-    if (X0 - lane * kPpt >= g.ws) return;
-    const bool lane_in = X0 < g.ws;
+    if (X0 >= g.ws) return;                                 // (ws % 4 == 0: a lane is wholly inside or outside)
     // x-weights of the warp: s_w[(c * 2 + h) * 32 + lane] = window column c, pixels (2h, 2h + 1), as double2
     double2 *s_w = reinterpret_cast<double2 *>(smem_raw + kMaxRows * (sizeof(RowEntryD) + sizeof(int)) +
                                                warp * (kYfCols * 2 * 32 * sizeof(double2))) + lane;
-    int col0 = 0, cellA = 0, ncell = 1;
-    bool geom_ok = lane_in;
+    int col0 = 0, ncell = 1;
+    int cc[kPpt];                                           // window column of every pixel's centre coarse pixel (-1: none)
     double xsum[kPpt];                                      // sum of the in-range x-weights per pixel (NaN: centre out of range)
     {
         double w6[kPpt][kYfCols];
@@ -873,16 +881,19 @@ upsample_yfirst_f64_kernel(const float *__restrict__ coarse, const uint8_t *__re
             if (!ok) xsum[k] = dnan;
             if (k == 0) kx0 = kx;
             kx3 = kx;
-            const long sh = kx - kx0;
-            geom_ok = geom_ok && sh >= 0 && sh <= 2;
+            const long sh = kx - kx0;                       // 0 .. 2 (>= 1.6 destination pixels per coarse pixel)
 #pragma unroll
             for (int c = 0; c < kYfCols; c++) {
                 const long i = c - sh;
                 w6[k][c] = (i >= 0 && i < 4) ? wx[i < 0 ? 0 : (i > 3 ? 3 : i)] : 0.0;
             }
+            const double srcx = up_src_coord(g.sx, g.ox, X0 + k);
+            long cx = (long)floor(srcx + 1e-10);
+            if (cx == g.wp) cx--;
+            const long ci = cx - (kx0 - 1);
+            cc[k] = (ok && ci >= 0 && ci < kYfCols) ? (int)ci : -1;
         }
         col0 = (int)min(max(kx0 - 1, -8L), g.wp + 8);
-        cellA = (int)min(max(kx0 + 1, -1L), g.wp + 2);
         ncell = (int)min(max(kx3 - kx0, 0L), 2L) + 1;
 #pragma unroll
         for (int c = 0; c < kYfCols; c++) {
@@ -890,46 +901,35 @@ upsample_yfirst_f64_kernel(const float *__restrict__ coarse, const uint8_t *__re
             s_w[(c * 2 + 1) * 32] = make_double2(w6[2][c], w6[3][c]);
         }
     }
-    const int fw = (int)g.wp + 2, hp = (int)g.hp, wp = (int)g.wp;
-    auto cell_flags = [&](int ky, int cell) -> unsigned {
-        if (ky < -1 || ky > hp || cell < 0 || cell >= fw) return 6u;
-        return flags[(long)(ky + 1) * fw + cell];
-    };
+    const int hp = (int)g.hp, wp = (int)g.wp;
     int coff[kYfCols];
 #pragma unroll
     for (int c = 0; c < kYfCols; c++) coff[c] = min(max(col0 + c, 0), wp - 1);
     const int ncols_used = 3 + ncell;
+    auto load_tap_row = [&](int row, double (&dst)[kYfCols]) {
+        // (rows / columns outside the raster carry weight 0: read the clamped position)
+        const float *p = coarse + (long)min(max(row, 0), hp - 1) * wp;
+#pragma unroll
+        for (int c = 0; c < kYfCols; c++) dst[c] = (c < ncols_used) ? (double)__ldg(p + coff[c]) : 0.0;
+    };
 
     const bool x_plain = (xsum[0] == 1.0) && (xsum[1] == 1.0) && (xsum[2] == 1.0) && (xsum[3] == 1.0);
     double t[4][kYfCols];
     int q_ky = INT_MIN;
-    bool do_store = false;
     float *orow = out + Y0 * g.ws + X0;
 #pragma unroll 1
     for (int r = 0; r < nrows; r++, orow += g.ws) {
         const int ky = s_ky[r];
-        if (ky != q_ky) {
-            unsigned f_or = 0, f_and = 7u;
-            bool each_ok = true;
-            for (int c = 0; c < ncell; c++) {
-                const unsigned f = cell_flags(ky, cellA + c);
-                f_or |= f; f_and &= f;
-                each_ok = each_ok && (f & 5u);
-            }
-            const int state = (!lane_in || !geom_ok) ? 1 : ((each_ok && (f_or & 1u)) ? 0 : ((f_and & 2u) ? 2 : 1));
-            do_store = (state != 1);
-            if (state == 2) {
+        if (ky != q_ky) {                                   // (warp-uniform)
+            if (ky == q_ky + 1) {                           // one coarse row further: shift the window, load the new row
 #pragma unroll
-                for (int j = 0; j < 4; j++)
+                for (int j = 0; j < 3; j++)
 #pragma unroll
-                    for (int c = 0; c < kYfCols; c++) t[j][c] = dnan;
-            } else if (state == 0) {
+                    for (int c = 0; c < kYfCols; c++) t[j][c] = t[j + 1][c];
+                load_tap_row(ky + 2, t[3]);
+            } else {
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float *p = coarse + (long)min(max(ky - 1 + j, 0), hp - 1) * wp;
-#pragma unroll
-                    for (int c = 0; c < kYfCols; c++) t[j][c] = (c < ncols_used) ? (double)__ldg(p + coff[c]) : 0.0;
-                }
+                for (int j = 0; j < 4; j++) load_tap_row(ky - 1 + j, t[j]);
             }
             q_ky = ky;
         }
@@ -958,8 +958,37 @@ upsample_yfirst_f64_kernel(const float *__restrict__ coarse, const uint8_t *__re
                 else if (wsum < 0.99999 || wsum > 1.00001) o[k] /= wsum;
             }
         }
-        if (do_store) hb_stg_stream16(orow, make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]));
-        (void)qnan;
+        // pixels with an invalid tap (NaN result): GDAL's general rule from the same registers
+        if ((o[0] != o[0]) || (o[1] != o[1]) || (o[2] != o[2]) || (o[3] != o[3])) {
+            const int jc = (int)ri.jc;
+#pragma unroll
+            for (int k = 0; k < kPpt; k++) {
+                if (o[k] == o[k]) continue;
+                double acc = 0.0, acc_w = 0.0, centre = dnan;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    double a = 0.0, m = 0.0;
+#pragma unroll
+                    for (int c = 0; c < kYfCols; c++) {
+                        const double2 wp2 = s_w[(c * 2 + (k >> 1)) * 32];
+                        const double wx = (k & 1) ? wp2.y : wp2.x;
+                        const double v = t[j][c];
+                        const bool ok = (wx != 0.0) && (v == v);
+                        a = fma(ok ? v : 0.0, ok ? wx : 0.0, a);     // dropped taps add exact zeros
+                        m += ok ? wx : 0.0;
+                        if (j == jc && c == cc[k]) centre = v;
+                    }
+                    acc = fma(ri.wy[j], a, acc);
+                    acc_w = fma(ri.wy[j], m, acc_w);
+                }
+                double res = dnan;
+                if (jc >= 0 && cc[k] >= 0 && centre == centre && !(acc_w < 0.000001)) {
+                    res = (acc_w < 0.99999 || acc_w > 1.00001) ? acc / acc_w : acc;
+                }
+                o[k] = res;
+            }
+        }
+        hb_stg_stream16(orow, make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]));
     }
 }
 
@@ -1275,54 +1304,31 @@ int hb_up_poly_apply(const void *src, int src_dtype, NoData nd, const float *par
 
 int hb_up_poly_resample(const float *coarse, int nb, const UpPolyGeom &g, float *out, cudaStream_t stream)
 {
-    // one band, double precision (see upsample_yfirst_f64_kernel); the caller keeps two-band requests on its general kernel
+    // one band, double precision, ONE kernel (see upsample_yfirst_f64_kernel); the caller keeps two-band requests on its
+    // general kernel
     HB_REQUIRE(nb == 1, "hb_up_poly_resample: one band per call");
-    const long fw = g.wp + 2, ncell = (g.hp + 2) * fw;
-    HB_REQUIRE(ncell < 2147483000L, "up-sampling: coarse raster too large");
-    const size_t off_list = 16, off_flags = off_list + (((size_t)ncell * 4 + 15) / 16) * 16;
-    const size_t total = off_flags + (((size_t)ncell + 15) / 16) * 16;
-    char *wsb = nullptr;
-    HB_CUDA_OK(hb_pool_keep_memory());
-    HB_CUDA_OK(cudaMallocAsync((void **)&wsb, total, stream));
-    int *count = (int *)wsb, *list = (int *)(wsb + off_list);
-    uint8_t *flags = (uint8_t *)(wsb + off_flags);
-    HB_CUDA_OK(cudaMemsetAsync(count, 0, 16, stream));
-    {
-        dim3 pgrid((unsigned)((fw + kPrepW - 1) / kPrepW), (unsigned)((g.hp + 2 + kPrepH - 1) / kPrepH));
-        HB_REQUIRE(pgrid.y <= 65535u, "up-sampling: coarse raster has too many rows (%ld)", g.hp);
-        upsample_prep_kernel<1, false><<<pgrid, kPrepW * kPrepH, 0, stream>>>(coarse, g.hp, g.wp, nullptr, flags, list, count);
-        HB_LAUNCH_OK("upsample_prep_kernel");
+    HB_REQUIRE(g.hp < 2147483000L && g.wp < 2147483000L, "up-sampling: coarse raster too large");
+    const size_t smem = kMaxRows * (sizeof(RowEntryD) + sizeof(int)) + (size_t)kWarps * kYfCols * 2 * 32 * sizeof(double2);
+    static HbOncePerDevice attr_once;
+    const int arc = hb_once_per_device(attr_once, [&]() -> int {
+        HB_CUDA_OK(cudaFuncSetAttribute(upsample_yfirst_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return 0;
+    });
+    if (arc) return arc;
+    const long cta_w = (long)kWarpW * kWarps;
+    const long gx = (g.ws + cta_w - 1) / cta_w;
+    const long slots = (long)hb_sm_count() * 2;
+    long rpc = kMaxRows;
+    double best = -1.0;
+    for (long cand = kMaxRows; cand >= 32; cand -= 4) {
+        const long ctas = gx * ((g.hs + cand - 1) / cand);
+        const long waves = (ctas + slots - 1) / slots;
+        const double eff = (double)ctas / (double)(waves * slots) * (cand >= 64 ? 1.0 : 0.97);
+        if (eff > best + 0.02) { best = eff; rpc = cand; }
     }
-    {
-        const size_t smem = kMaxRows * (sizeof(RowEntryD) + sizeof(int)) + (size_t)kWarps * kYfCols * 2 * 32 * sizeof(double2);
-        static HbOncePerDevice attr_once;
-        const int arc = hb_once_per_device(attr_once, [&]() -> int {
-            HB_CUDA_OK(cudaFuncSetAttribute(upsample_yfirst_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            return 0;
-        });
-        if (arc) return arc;
-        const long cta_w = (long)kWarpW * kWarps;
-        const long gx = (g.ws + cta_w - 1) / cta_w;
-        const long slots = (long)hb_sm_count() * 2;
-        long rpc = kMaxRows;
-        double best = -1.0;
-        for (long cand = kMaxRows; cand >= 32; cand -= 4) {
-            const long ctas = gx * ((g.hs + cand - 1) / cand);
-            const long waves = (ctas + slots - 1) / slots;
-            const double eff = (double)ctas / (double)(waves * slots) * (cand >= 64 ? 1.0 : 0.97);
-            if (eff > best + 0.02) { best = eff; rpc = cand; }
-        }
-        dim3 grid((unsigned)gx, (unsigned)((g.hs + rpc - 1) / rpc));
-        HB_REQUIRE(grid.y <= 65535u, "up-sampling destination has too many rows (%ld)", g.hs);
-        upsample_yfirst_f64_kernel<<<grid, kThreads, smem, stream>>>(coarse, flags, g, (int)rpc, out);
-        HB_LAUNCH_OK("upsample_yfirst_f64_kernel");
-    }
-    {
-        const unsigned blocks = (unsigned)hb_sm_count() * 16;
-        upsample_fixup_kernel<float, 1, false><<<blocks, kFixThreads, 0, stream>>>(nullptr, hb_make_nodata(0, 0.0), coarse,
-                                                                                 g, out, list, count);
-        HB_LAUNCH_OK("upsample_fixup_kernel");
-    }
-    HB_CUDA_OK(cudaFreeAsync(wsb, stream));
+    dim3 grid((unsigned)gx, (unsigned)((g.hs + rpc - 1) / rpc));
+    HB_REQUIRE(grid.y <= 65535u, "up-sampling destination has too many rows (%ld)", g.hs);
+    upsample_yfirst_f64_kernel<<<grid, kThreads, smem, stream>>>(coarse, g, (int)rpc, out);
+    HB_LAUNCH_OK("upsample_yfirst_f64_kernel");
     return 0;
 }

@@ -396,8 +396,8 @@ def test_resample_up_fast_paths(nb, ratio, shift):
     lib = _native.lib()
     lib.hb_reset_launch_count()
     got = hkm._resample_up(torch.from_numpy(arr).cuda(), TF_LO, NAN, (hd, wd), dst_tf).cpu().numpy()
-    # one band: pre-pass + double-precision "y first" kernel + fix-up; two bands stay on the general kernel
-    assert lib.hb_launch_count() == (3 if nb == 1 else 1)
+    # one band: ONE double-precision "y first" kernel (invalid taps handled inline); two bands: the general kernel
+    assert lib.hb_launch_count() == 1
     assert_same_mask(got, expected, 'cubic_spline')
     assert rel_err(got, expected, 1e-3) <= 1e-6
 
