@@ -215,6 +215,10 @@ template <class F> static inline int hb_once_per_device(HbOncePerDevice &once, F
     return rc;
 }
 
+// high-priority side stream with a fork / join event pair (defined in upsample_poly.cu); nullptr when none could be made
+struct SideStream { cudaStream_t s; cudaEvent_t fork, join; bool ok; };
+SideStream *hb_side_stream();
+
 static inline int hb_sm_count()
 {
     static int sms = 0;

@@ -36,6 +36,36 @@
 #include "hb_common.cuh"
 #include "upsample_poly.cuh"
 
+// A small per-device pool of HIGH-PRIORITY side streams (hb_common.cuh): pending kernels of equal priority are dispatched
+// in launch order, so a small kernel launched behind a streaming kernel of another band only runs once that kernel has
+// handed out all its CTAs; on a high-priority stream it slips in between.
+SideStream *hb_side_stream()
+{
+    constexpr int kPool = 8, kMaxDev = 64;
+    static SideStream pool[kMaxDev][kPool];
+    static bool made[kMaxDev] = {false};
+    static unsigned next[kMaxDev] = {0};
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!made[dev]) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);             // (hi is the numerically smallest = highest priority)
+        for (int i = 0; i < kPool; i++) {
+            SideStream &ss = pool[dev][i];
+            ss.ok = cudaStreamCreateWithPriority(&ss.s, cudaStreamNonBlocking, hi) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess;
+        }
+        cudaGetLastError();
+        made[dev] = true;
+    }
+    SideStream *ss = &pool[dev][next[dev]++ % kPool];
+    return ss->ok ? ss : nullptr;
+}
+
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -1166,33 +1196,6 @@ upsample_fixup_kernel(const T *__restrict__ src, NoData nd, const float *__restr
 // The fix-up kernel only depends on the pre-pass and writes pixels the streaming kernel skips: it runs on a side stream
 // forked after the pre-pass (a few latency-bound warps that would otherwise add ~15-20 us in front of / behind the
 // streaming kernel), joined before the scratch is released.  A small per-device pool of high-priority side streams.
-struct SideStream { cudaStream_t s; cudaEvent_t fork, join; bool ok; };
-SideStream *side_stream()
-{
-    constexpr int kPool = 8, kMaxDev = 64;
-    static SideStream pool[kMaxDev][kPool];
-    static bool made[kMaxDev] = {false};
-    static unsigned next[kMaxDev] = {0};
-    static std::mutex mu;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
-    std::lock_guard<std::mutex> lock(mu);
-    if (!made[dev]) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);             // (hi is the numerically smallest = highest priority)
-        for (int i = 0; i < kPool; i++) {
-            SideStream &ss = pool[dev][i];
-            ss.ok = cudaStreamCreateWithPriority(&ss.s, cudaStreamNonBlocking, hi) == cudaSuccess &&
-                    cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
-                    cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess;
-        }
-        cudaGetLastError();
-        made[dev] = true;
-    }
-    SideStream *ss = &pool[dev][next[dev]++ % kPool];
-    return ss->ok ? ss : nullptr;
-}
-
 template <typename T, int NB, bool APPLY>
 int launch_poly(const void *src, NoData nd, const float *coarse, const UpPolyGeom &g, float *out, cudaStream_t stream)
 {
@@ -1217,7 +1220,7 @@ int launch_poly(const void *src, NoData nd, const float *coarse, const UpPolyGeo
         HB_LAUNCH_OK("upsample_prep_kernel");
     }
     // fork: the fix-up kernel on a side stream, concurrently with the streaming kernel below
-    SideStream *side = side_stream();
+    SideStream *side = hb_side_stream();
     if (side != nullptr) {
         if (cudaEventRecord(side->fork, stream) != cudaSuccess || cudaStreamWaitEvent(side->s, side->fork, 0) != cudaSuccess) {
             cudaGetLastError();

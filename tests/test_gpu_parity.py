@@ -274,7 +274,7 @@ def test_ref_basic_apply_and_masking():
             assert (np.kron(eroded, np.ones((2, 2))).astype(bool) == out_ra.mask).all()
 
 
-@pytest.mark.parametrize('kernel_shape', [(5, 5), (5, 7), (9, 9)])
+@pytest.mark.parametrize('kernel_shape', [(3, 3), (5, 5), (5, 7), (9, 9), (11, 11), (15, 15)])
 def test_r2_inpainting(kernel_shape):
     """ reference tests/test_kernel_model.py:166-203. """
     _, ra50 = _conftest_rasters()

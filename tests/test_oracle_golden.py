@@ -144,3 +144,72 @@ def test_oracle_reproduces_reference_published_table_all_images():
     for name, published in mgd.PUBLISHED.items():
         src = mgd.read_geotiff(mgd.DATA / 'source' / name)
         mgd.check_rows(mgd.docs_rows(src['array'], src['transform'], s2, s2_tf, l8, l8_tf), published, name)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GDALFillNodata restatement (in-painting, kernel_model.py:366): GDAL is not installable here, so parity with GDAL itself
+# stays unpinned; what CAN be pinned is that the C restatement does what the algorithm's description says.
+# ---------------------------------------------------------------------------------------------------------------------
+def test_fillnodata_restatement_vs_independent_restatement():
+    """ oracle/gdal_restate.c::gr_fillnodata against oracle/fillnodata_alt.py (brute force, written from the algorithm's
+    description): bit-identical on random images / masks / search radii. """
+    from oracle import gdal_restate as gr
+    from oracle.fillnodata_alt import fillnodata_alt
+    rng = np.random.default_rng(0)
+    for case in range(16):
+        h, w = int(rng.integers(4, 50)), int(rng.integers(4, 60))
+        img = rng.normal(10, 3, (h, w)).astype('float32')
+        mask = rng.random((h, w)) < rng.choice([0.01, 0.05, 0.3, 0.9])
+        radius = float(rng.choice([2, 7, 100]))
+        a, b = gr.fillnodata(img, mask, radius), fillnodata_alt(img, mask, radius)
+        assert np.array_equal(a, b), f'case {case}: {int((a != b).sum())} pixels differ'
+
+
+def test_fillnodata_properties():
+    """ Properties of the four-quadrant inverse-distance fill that the description implies. """
+    from oracle import gdal_restate as gr
+    nan = np.float32('nan')
+    # (1) no source at all / none within reach: untouched
+    img = np.full((9, 9), 7.0, 'float32')
+    assert np.array_equal(gr.fillnodata(img, np.zeros((9, 9), bool), 100.0), img)
+    # (2) a single source at distance 1: the filled value IS the source value
+    img = np.zeros((5, 5), 'float32'); mask = np.zeros((5, 5), bool)
+    img[2, 1], mask[2, 1] = 3.25, True
+    assert gr.fillnodata(img, mask, 100.0)[2, 2] == np.float32(3.25)
+    # (3) the cut-off: a source exactly max_search_distance away fills, one pixel further does not
+    img = np.zeros((1, 130), 'float32'); mask = np.zeros((1, 130), bool)
+    img[0, 0], mask[0, 0] = 5.0, True
+    out = gr.fillnodata(img, mask, 100.0)
+    assert out[0, 100] == np.float32(5.0) and out[0, 101] == 0.0
+    # (4) a source on the pixel's own ROW is found by the top and the bottom quadrant of its side: it counts twice;
+    #     a source in its own COLUMN counts once (the centre column belongs to the left side only)
+    img = np.zeros((7, 7), 'float32'); mask = np.zeros((7, 7), bool)
+    img[3, 5], mask[3, 5] = 100.0, True         # same row, 2 to the right: top-right AND bottom-right quadrant
+    img[1, 3], mask[1, 3] = 40.0, True          # same column, 2 above: top-left quadrant only
+    got = gr.fillnodata(img, mask, 100.0)[3, 3]
+    assert got == np.float32((40.0 / 2 + 2 * 100.0 / 2) / (3 / 2))           # (40 + 100 + 100) / 3 = 80
+    # (4b) one source per quadrant at most, the nearest; at equal distance the one found at the smaller column step
+    img = np.zeros((7, 7), 'float32'); mask = np.zeros((7, 7), bool)
+    img[3, 1], mask[3, 1] = 10.0, True          # same row, 2 to the left (column step 2)
+    img[1, 3], mask[1, 3] = 40.0, True          # same column, 2 above (column step 0): takes the top-left quadrant
+    assert gr.fillnodata(img, mask, 100.0)[3, 3] == np.float32(25.0)        # (40 [tl] + 10 [bl]) / 2
+    # (5) up-down mirror symmetry (up to the order of the four-term sum).  Left-right mirroring does NOT hold in general:
+    #     the centre column belongs to the left side, so a source straight above / below changes sides -- also asserted
+    rng = np.random.default_rng(4)
+    img = rng.normal(5, 1, (23, 31)).astype('float32')
+    mask = rng.random((23, 31)) < 0.08
+    base = gr.fillnodata(img, mask, 100.0)
+    flipped = np.flipud(gr.fillnodata(np.ascontiguousarray(np.flipud(img)), np.ascontiguousarray(np.flipud(mask)), 100.0))
+    assert np.allclose(flipped, base, rtol=2e-6, atol=0)
+    mirrored = np.fliplr(gr.fillnodata(np.ascontiguousarray(np.fliplr(img)), np.ascontiguousarray(np.fliplr(mask)), 100.0))
+    differs = ~np.isclose(mirrored, base, rtol=2e-6, atol=0)
+    assert differs.any() and not differs[:, ~mask.any(axis=0)].any()       # only in columns that hold a source
+    # (6) sources are never modified, and only ORIGINAL sources are used (a filled pixel does not become a source)
+    out = gr.fillnodata(img, mask, 3.0)
+    assert np.array_equal(out[mask], img[mask])
+    far = np.ones(mask.shape, bool)
+    ys, xs = np.nonzero(mask)
+    for y, x in zip(ys, xs):
+        far[max(y - 3, 0):y + 4, max(x - 3, 0):x + 4] = False
+    assert np.array_equal(out[far], img[far])   # nothing within reach (Chebyshev > 3 implies Euclidean > 3): untouched
+    assert not np.isnan(out).any() and nan != nan
