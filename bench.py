@@ -332,7 +332,8 @@ def _rel_err(actual, expected, floor, exclude):
     return float(np.max(np.abs(a - e) / np.maximum(np.abs(e), fl)))
 
 
-def parity_metrics(got_params, got_corr, exp_params, exp_corr, src_mean, param_to_corr=None, offset_at_corr=None):
+def parity_metrics(got_params, got_corr, exp_params, exp_corr, src_mean, param_to_corr=None, offset_at_corr=None,
+                   kernel_px=None):
     """
     SURVEY.md 8(d): masks `isnan(out) == isnan(reference)` exactly; gain / corrected-pixel error relative to
     max(|x_ref|, 1e-3 x band mean); offset error relative to max(|offset|, |gain| x mean(src)); R2 absolute.  Pixels
@@ -344,6 +345,9 @@ def parity_metrics(got_params, got_corr, exp_params, exp_corr, src_mean, param_t
     reference's own float32 expression gain * src + offset (kernel_model.py:461) cancels by more than 2^7 (|corr| < |offset| /
     128: the value is then the rounding residue of two ~100x larger float32 terms) are counted in `cancellation_px` and
     likewise left out of `max_rel_err_corr` -- their worst error is reported separately, relative to the same floor.
+    ``kernel_px`` = 1 (a 1 x 1 kernel): R2 = 1 - ss_res / ss_tot with ss_tot = ref^2 - ref^2 / 1, i.e. BOTH terms are the
+    rounding residue of the reference's own float32 expression (kernel_model.py:280-302) -- the band carries no
+    information; it is reported (`r2_abs`, `r2_bit_identical_frac`) and flagged `r2_degenerate`, not held to 1e-4.
     """
     n = min(got_params.shape[0], exp_params.shape[0])
     masks = bool(np.array_equal(np.isnan(got_corr), np.isnan(exp_corr)) and
@@ -380,6 +384,10 @@ def parity_metrics(got_params, got_corr, exp_params, exp_corr, src_mean, param_t
         fin2 = np.isfinite(exp_params[2]) & ~bad
         out['r2_abs'] = float(np.max(np.abs(got_params[2][fin2].astype('float64') - exp_params[2][fin2]))) \
             if fin2.any() else 0.0
+        same_r2 = (got_params[2] == exp_params[2]) | (np.isnan(got_params[2]) & np.isnan(exp_params[2]))
+        out['r2_bit_identical_frac'] = round(float(same_r2.mean()), 6)
+        if kernel_px == 1:
+            out['r2_degenerate'] = '1 x 1 kernel: ss_tot is identically 0 up to float32 rounding; R2 not held to 1e-4'
     out['excluded_px'] = int(bad.sum())
     out['excluded_corr_px'] = int(bad_c.sum())
     same = (got_corr == exp_corr) | (np.isnan(got_corr) & np.isnan(exp_corr))
@@ -387,7 +395,7 @@ def parity_metrics(got_params, got_corr, exp_params, exp_corr, src_mean, param_t
     out['tolerance'] = 1e-4
     out['within_tolerance'] = bool(masks and infs_ok and out['max_rel_err_gain'] <= 1e-4 and
                                    out['max_rel_err_offset'] <= 1e-4 and out['max_rel_err_corr'] <= 1e-4 and
-                                   out.get('r2_abs', 0.0) <= 1e-4)
+                                   (out.get('r2_abs', 0.0) <= 1e-4 or 'r2_degenerate' in out))
     for k in ('max_rel_err_gain', 'max_rel_err_offset', 'max_rel_err_corr', 'r2_abs'):
         if k in out:
             out[k] = float(f'{out[k]:.3e}')
@@ -441,7 +449,7 @@ def measure_parity_and_cpu(args, cfg, src_ra, ref_ra):
             return grown[np.ix_(rows, cols)]
         offset_at_corr = exp_params[1][np.ix_(rows, cols)]
     parity = parity_metrics(got_params, got_corr, exp_params, exp_corr, float(valid.astype('float64').mean()),
-                            param_to_corr, offset_at_corr)
+                            param_to_corr, offset_at_corr, kernel_px=int(np.prod(cfg['kernel_shape'])))
     parity['sample'] = note
     parity['against'] = f'{cpu.kind} ({cpu.where})'
     if cfg['model'] == 'gain-offset' and cfg['r2_inpaint_thresh'] is not None:

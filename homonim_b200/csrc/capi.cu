@@ -3,7 +3,6 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include <mutex>
 
 #include "hb_common.cuh"
 
@@ -104,135 +103,18 @@ static int fuse_refspace_direct(const void *src_dev, int src_dtype, long hs, lon
                              1.0 / sy, -oy / sy, nullptr, out_dtype, out_has_nodata, out_nodata, corr_dev, stream);
 }
 
-// ---- CUDA-graph replay of repeated identical calls (opt-in: HOMONIM_B200_GRAPHS=1) ------------------------------------
-// A band's pipeline is ~8 kernels plus stream-ordered allocations: ~50 us of host time per call.  With
-// HOMONIM_B200_GRAPHS=1 the THIRD call with exactly the same arguments (pointers, shapes, geometry, model -- e.g. a
-// tiling loop over fixed staging buffers, or the same rasters corrected again) is captured into a graph and later ones
-// are one cudaGraphLaunch (measured on one B200: host time per RasterFuse.process() call 0.44 -> 0.26 ms).  Contents of
-// the buffers may change freely: only addresses and scalars are baked in.  Any capture problem falls back to the
-// direct path.  OFF by default: with 8 processes driving 8 GPUs of one box the replayed step was measured 2x SLOWER
-// than the direct path (1.99 vs 0.93 ms; graph launches with memory-allocation nodes under multi-process load), and
-// the direct path is not host-bound there.
-namespace {
-struct FuseKey {
-    const void *src; const float *ref; void *corr; float *params;
-    long hs, ws, hr, wr;
-    double src_nodata, ref_nodata, sx, ox, sy, oy, r2_thresh, out_nodata;
-    int src_dtype, src_has_nodata, ref_has_nodata, model, kh, kw, want_r2, do_inpaint, device, out_dtype, out_has_nodata;
-    bool operator==(const FuseKey &o) const { return memcmp(this, &o, sizeof(FuseKey)) == 0; }
-};
-struct FuseGraph { FuseKey key; cudaGraphExec_t exec; long launches; unsigned long long last_use; int seen; };
-constexpr int kMaxGraphs = 32;
-std::mutex g_graph_mu;
-FuseGraph g_graphs[kMaxGraphs];
-int g_n_graphs = 0;
-unsigned long long g_graph_clock = 0;
-
-bool graphs_enabled()
-{
-    static int on = -1;
-    if (on < 0) {
-        const char *e = getenv("HOMONIM_B200_GRAPHS");
-        on = (e != nullptr && e[0] == '1') ? 1 : 0;
-    }
-    return on == 1;
-}
-}  // namespace
-
+// No CUDA-graph cache here: replaying a captured band step (8 kernels + stream-ordered allocations) saved 0.18 ms of host
+// time per call on one idle GPU but was 2x slower with 8 processes driving 8 GPUs of one box (graph launches with memory
+// allocation nodes), and the direct path is not host-bound in either case -- measured in round 1, removed in round 2.
 extern "C" int hb_fuse_refspace(const void *src_dev, int src_dtype, long hs, long ws, int src_has_nodata,
                                 double src_nodata, const float *ref_dev, long hr, long wr, int ref_has_nodata,
                                 double ref_nodata, double sx, double ox, double sy, double oy, int model, int kh, int kw,
                                 int want_r2, int do_inpaint, double r2_thresh, int out_dtype, int out_has_nodata,
                                 double out_nodata, void *corr_dev, float *params_dev, void *stream)
 {
-#define HB_FUSE_ARGS src_dev, src_dtype, hs, ws, src_has_nodata, src_nodata, ref_dev, hr, wr, ref_has_nodata, ref_nodata, \
-                     sx, ox, sy, oy, model, kh, kw, want_r2, do_inpaint, r2_thresh, out_dtype, out_has_nodata, out_nodata, \
-                     corr_dev, params_dev, stream
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (!graphs_enabled() || cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
-        return fuse_refspace_direct(HB_FUSE_ARGS);
-    FuseKey key;
-    memset(&key, 0, sizeof(key));
-    key.src = src_dev; key.ref = ref_dev; key.corr = corr_dev; key.params = params_dev;
-    key.hs = hs; key.ws = ws; key.hr = hr; key.wr = wr;
-    key.src_nodata = src_nodata; key.ref_nodata = ref_nodata; key.sx = sx; key.ox = ox; key.sy = sy; key.oy = oy;
-    key.r2_thresh = r2_thresh;
-    key.out_nodata = out_nodata; key.out_dtype = out_dtype; key.out_has_nodata = out_has_nodata;
-    key.src_dtype = src_dtype; key.src_has_nodata = src_has_nodata; key.ref_has_nodata = ref_has_nodata;
-    key.model = model; key.kh = kh; key.kw = kw; key.want_r2 = want_r2; key.do_inpaint = do_inpaint;
-    if (cudaGetDevice(&key.device) != cudaSuccess) return fuse_refspace_direct(HB_FUSE_ARGS);
-
-    std::unique_lock<std::mutex> lock(g_graph_mu);
-    int slot = -1;
-    for (int i = 0; i < g_n_graphs; i++)
-        if (g_graphs[i].key == key) { slot = i; break; }
-    if (slot >= 0 && g_graphs[slot].exec != nullptr) {                     // replay
-        g_graphs[slot].last_use = ++g_graph_clock;
-        const cudaGraphExec_t exec = g_graphs[slot].exec;
-        const long n = g_graphs[slot].launches;
-        lock.unlock();
-        if (cudaGraphLaunch(exec, st) == cudaSuccess) {
-            hb_count_launch((int)n);
-            return 0;
-        }
-        cudaGetLastError();
-        return fuse_refspace_direct(HB_FUSE_ARGS);
-    }
-    if (slot < 0) {                                                        // first sighting: remember, run directly
-        if (g_n_graphs < kMaxGraphs) slot = g_n_graphs++;
-        else {                                                             // evict the least recently used entry
-            slot = 0;
-            for (int i = 1; i < kMaxGraphs; i++)
-                if (g_graphs[i].last_use < g_graphs[slot].last_use) slot = i;
-            if (g_graphs[slot].exec != nullptr) cudaGraphExecDestroy(g_graphs[slot].exec);
-        }
-        g_graphs[slot].key = key; g_graphs[slot].exec = nullptr; g_graphs[slot].launches = 0;
-        g_graphs[slot].last_use = ++g_graph_clock; g_graphs[slot].seen = 1;
-        lock.unlock();
-        return fuse_refspace_direct(HB_FUSE_ARGS);
-    }
-    // third sighting: capture the direct path into a graph, instantiate, launch (the second runs directly)
-    g_graphs[slot].last_use = ++g_graph_clock;
-    g_graphs[slot].seen++;
-    const bool try_capture = g_graphs[slot].seen == 3;                     // (only once: a failed capture stays direct)
-    lock.unlock();
-    if (!try_capture || cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-        cudaGetLastError();
-        return fuse_refspace_direct(HB_FUSE_ARGS);
-    }
-    const long before = hb_launch_count();
-    const int rc = fuse_refspace_direct(HB_FUSE_ARGS);
-    const long n_launch = hb_launch_count() - before;
-    cudaGraph_t graph = nullptr;
-    const cudaError_t end = cudaStreamEndCapture(st, &graph);
-    cudaGraphExec_t exec = nullptr;
-    if (rc != 0 || end != cudaSuccess || graph == nullptr ||
-        cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
-        if (graph) cudaGraphDestroy(graph);
-        cudaGetLastError();
-        hb_count_launch(-(int)n_launch);                                   // nothing was enqueued by the capture
-        return fuse_refspace_direct(HB_FUSE_ARGS);
-    }
-    cudaGraphDestroy(graph);
-    hb_count_launch(-(int)n_launch);
-    if (cudaGraphLaunch(exec, st) != cudaSuccess) {
-        cudaGetLastError();
-        cudaGraphExecDestroy(exec);
-        return fuse_refspace_direct(HB_FUSE_ARGS);
-    }
-    hb_count_launch((int)n_launch);
-    lock.lock();
-    if (g_graphs[slot].key == key && g_graphs[slot].exec == nullptr) {
-        g_graphs[slot].exec = exec;
-        g_graphs[slot].launches = n_launch;
-    } else {
-        lock.unlock();
-        cudaGraphExecDestroy(exec);                                        // (the slot was recycled meanwhile)
-        return 0;
-    }
-    return 0;
-#undef HB_FUSE_ARGS
+    return fuse_refspace_direct(src_dev, src_dtype, hs, ws, src_has_nodata, src_nodata, ref_dev, hr, wr, ref_has_nodata,
+                                ref_nodata, sx, ox, sy, oy, model, kh, kw, want_r2, do_inpaint, r2_thresh, out_dtype,
+                                out_has_nodata, out_nodata, corr_dev, params_dev, stream);
 }
 
 // One (band, block) of RasterFuse._process_block (homonim/fuse.py:304-307) for proc_crs = ref, host buffers in/out.

@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <math.h>
+#include <mutex>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -179,7 +180,10 @@ __device__ __forceinline__ void hb_store1_out(void *base, long pix, float v, con
 }
 
 // Stream-ordered scratch (cudaMallocAsync) comes from the device's default memory pool.  By default the pool hands
-// freed memory back to the OS at every synchronisation, so that each call would pay for a fresh allocation; keep it.
+// freed memory back to the OS at every synchronisation, so that each call would pay for a fresh allocation.  Keep a
+// BOUNDED amount cached (the pool is shared with the host application: an existing higher threshold is left alone, and
+// nothing is pinned for ever): 1 GiB covers the scratch of every entry point at BASELINE.json's largest configuration
+// (parameter-grid planes and work lists; full-resolution planes are the caller's).
 static inline cudaError_t hb_pool_keep_memory()
 {
     static thread_local int done_for = -1;
@@ -189,16 +193,15 @@ static inline cudaError_t hb_pool_keep_memory()
     cudaMemPool_t pool;
     err = cudaDeviceGetDefaultMemPool(&pool, dev);
     if (err != cudaSuccess) return err;
-    unsigned long long keep = ~0ull;
-    err = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    unsigned long long keep = 1ull << 30, have = 0ull;
+    err = cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &have);
+    if (err == cudaSuccess && have < keep) err = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     if (err == cudaSuccess) done_for = dev;
     return err;
 }
-
 // Per-device one-time set-up such as cudaFuncSetAttribute (function attributes belong to the device that is current
 // when they are set).  `once` is a call-site static; the set-up runs under its mutex and the device's bit is only set
 // AFTER it succeeded, so a second thread can never launch before the attribute is in place.
-#include <mutex>
 struct HbOncePerDevice {
     std::mutex mu;
     unsigned long long done = 0ull;
@@ -215,8 +218,10 @@ template <class F> static inline int hb_once_per_device(HbOncePerDevice &once, F
     return rc;
 }
 
-// high-priority side stream with a fork / join event pair (defined in upsample_poly.cu); nullptr when none could be made
-struct SideStream { cudaStream_t s; cudaEvent_t fork, join; bool ok; };
+// high-priority side stream with a fork / join event pair (defined in upsample_poly.cu); nullptr when none could be made.
+// The caller holds `mu` from the fork record to the join wait (a few host-side enqueues): the events of a slot are
+// re-recorded by every user, so two host threads must not interleave on one slot.
+struct SideStream { cudaStream_t s; cudaEvent_t fork, join; bool ok; std::mutex mu; };
 SideStream *hb_side_stream();
 
 static inline int hb_sm_count()

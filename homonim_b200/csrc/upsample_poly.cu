@@ -1221,7 +1221,9 @@ int launch_poly(const void *src, NoData nd, const float *coarse, const UpPolyGeo
     }
     // fork: the fix-up kernel on a side stream, concurrently with the streaming kernel below
     SideStream *side = hb_side_stream();
+    std::unique_lock<std::mutex> side_lock;
     if (side != nullptr) {
+        side_lock = std::unique_lock<std::mutex>(side->mu);
         if (cudaEventRecord(side->fork, stream) != cudaSuccess || cudaStreamWaitEvent(side->s, side->fork, 0) != cudaSuccess) {
             cudaGetLastError();
             side = nullptr;

@@ -35,6 +35,7 @@ except ImportError:  # pragma: no cover
 
 
 _STREAM_POOLS: Dict[int, list] = {}
+_STREAM_POOLS_LOCK = threading.Lock()
 
 
 def _band_streams(n: int) -> list:
@@ -44,10 +45,11 @@ def _band_streams(n: int) -> list:
     fresh cudaMallocs for every band).
     """
     dev = torch.cuda.current_device()
-    pool = _STREAM_POOLS.setdefault(dev, [])
-    while len(pool) < n:
-        pool.append(torch.cuda.Stream(device=dev))
-    return pool[:n]
+    with _STREAM_POOLS_LOCK:
+        pool = _STREAM_POOLS.setdefault(dev, [])
+        while len(pool) < n:
+            pool.append(torch.cuda.Stream(device=dev))
+        return pool[:n]
 
 
 def _validate_threads(threads: int) -> int:
@@ -112,8 +114,9 @@ class RasterFuse:
         self._ref_bands = self._ref_bands[:len(self._src_bands)]
         self._proc_crs = self._resolve_proc_crs(src, ref, ProcCrs(proc_crs))
         self._closed = True
-        self._corr_lock = threading.Lock()
-        self._param_lock = threading.Lock()
+        # `process` keeps its working state in locals and may be called from several threads at once; the only state
+        # they share is the per-band plan cache (the reference's write locks, fuse.py:92-93, guard its output FILES)
+        self._plan_lock = threading.Lock()
         self._plans: Dict[int, tuple] = {}
 
     @staticmethod
@@ -203,7 +206,8 @@ class RasterFuse:
         src_arr, ref_arr = self._src.array, self._ref.array
         key = (src_arr.data_ptr(), src_arr._version, tuple(src_arr.shape), ref_arr.data_ptr(), ref_arr._version,
                tuple(ref_arr.shape), self._src_bands[band_i], self._ref_bands[band_i])
-        plan = self._plans.get(band_i)
+        with self._plan_lock:
+            plan = self._plans.get(band_i)
         if plan is not None and plan[0] == key:
             return plan[1:]
         from homonim_b200.geometry import grid_map
@@ -215,7 +219,8 @@ class RasterFuse:
         ref_t = ref_t.contiguous()
         gm = grid_map(src_ra.transform, ref_ra.transform)         # reference grid -> source grid
         plan = (key, src_ra, ref_ra, ref_t, gm)
-        self._plans[band_i] = plan
+        with self._plan_lock:
+            self._plans[band_i] = plan
         return plan[1:]
 
     def _process_band(self, band_i: int, model: KernelModel, out=None, stage: bool = False,
@@ -279,6 +284,13 @@ class RasterFuse:
                         f"{what} image file exists and won't be overwritten without the `overwrite` option: {name}")
         model_type = Model(model)
         _ = overlap_for_kernel(kernel_shape)           # fuse.py:371 (single block per band: no overlap is needed)
+        if self._src.is_device and self._src.array.device.index != torch.cuda.current_device():
+            with torch.cuda.device(self._src.array.device):        # the native calls launch on the current device
+                return self.process(corr_filename, model, kernel_shape, param_filename, build_ovw, overwrite,
+                                    model_config, out_profile, block_config, corr_out)
+        if self._files is not None and is_path(corr_filename) and build_ovw:
+            warnings.warn('`build_ovw` is ignored: overviews are not built by this path (use gdaladdo on the output).',
+                          category=ConfigWarning)
         model_config = RasterFuse.create_model_config(**(model_config or {}))
         block_config = RasterFuse.create_block_config(**(block_config or {}))
         out_profile = RasterFuse.create_out_profile(**(out_profile or {}))
@@ -366,7 +378,9 @@ class RasterFuse:
             params = RasterArray(stack(planes), param_planes[0].crs, param_planes[0].transform, nodata=float('nan'))
         if self._files is not None and is_path(corr_filename):
             # a pair opened from files: write the outputs with the reference's metadata (fuse.py:264-293)
-            meta = dict(model=model_type, kernel_shape=tuple(kernel_shape), **model_config, **block_config)
+            # (every band is ONE block here: max_block_mem is recorded as what was applied, not what was asked for)
+            meta = dict(model=model_type, kernel_shape=tuple(kernel_shape), **model_config,
+                        **dict(block_config, max_block_mem='whole-band'))
             self._files.write_corrected(corr.to_host(), corr_filename, self.proc_crs, out_profile,
                                         overwrite=overwrite, **meta)
             if params is not None and is_path(param_filename):

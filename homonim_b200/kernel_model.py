@@ -16,7 +16,7 @@ Differences from the reference, all deliberate:
   * only the default resampling pair (average down / cubic_spline up) plus nearest are implemented natively; other
     ``downsampling`` / ``upsampling`` choices raise NotImplementedError rather than silently using something else.
 """
-import threading
+import functools
 import warnings
 from typing import Dict, Optional, Tuple
 
@@ -79,6 +79,22 @@ def _require_torch():
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def _on_raster_device(method):
+    """ Run a public model method with the first device-resident raster's GPU as the current device: the native entry points
+    launch on the current device's stream, and its per-device set-up (function attributes, scratch pool) is keyed by it. """
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        for a in args:
+            arr = getattr(a, 'array', None)
+            if is_tensor(arr) and arr.is_cuda:
+                if arr.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(arr.device):
+                        return method(self, *args, **kwargs)
+                break
+        return method(self, *args, **kwargs)
+    return wrapper
 
 
 class KernelTimer:
@@ -207,7 +223,6 @@ class KernelModel:
         self._mask_partial: bool = config['mask_partial']
         self._downsampling = config['downsampling']
         self._upsampling = config['upsampling']
-        self._lock = threading.Lock()
 
     @property
     def model(self) -> Model:
@@ -337,6 +352,7 @@ class KernelModel:
         return mask
 
     # ---- public API (reference kernel_model.py:411-463) -----------------------------------------------------------
+    @_on_raster_device
     def fit(self, src_ra: RasterArray, ref_ra: RasterArray) -> RasterArray:
         if (ref_ra.transform != src_ra.transform) or (ref_ra.shape != src_ra.shape):
             raise ValueError("'ref_ra' and 'src_ra' must have the same CRS, transform and shape")
@@ -346,6 +362,7 @@ class KernelModel:
         params = self._fit_planes(src_t, src_ra.nodata, ref_t, ref_ra.nodata)
         return RasterArray(_result(params, on_device), src_ra.crs, src_ra.transform, nodata=NAN)
 
+    @_on_raster_device
     def apply(self, src_ra: RasterArray, param_ra: RasterArray, out=None, out_nodata=NAN) -> RasterArray:
         """
         Reference kernel_model.py:442-463.  ``out`` (optional, additive): a CUDA tensor ``[H, W]`` to write the corrected
@@ -465,6 +482,7 @@ def reproject_raster(ra: RasterArray, crs=None, transform=None, shape=None, noda
 class RefSpaceModel(KernelModel):
     """ Fit on the reference grid, apply on the source grid (reference kernel_model.py:466-503). """
 
+    @_on_raster_device
     def fit(self, src_ra: RasterArray, ref_ra: RasterArray) -> RasterArray:
         _require_torch()
         on_device = src_ra.is_device and ref_ra.is_device
@@ -484,6 +502,7 @@ class RefSpaceModel(KernelModel):
             return False
         return self._get_resampling(ref_ra.res, src_ra.res) == Resampling.cubic_spline
 
+    @_on_raster_device
     def fuse(self, src_ra: RasterArray, ref_ra: RasterArray, out=None, want_params: bool = False, out_nodata=NAN
              ) -> Tuple[RasterArray, Optional[RasterArray]]:
         """
@@ -524,6 +543,7 @@ class RefSpaceModel(KernelModel):
               params.data_ptr() if params is not None else None, _stream())
         return corr, params
 
+    @_on_raster_device
     def apply(self, src_ra: RasterArray, param_ra: RasterArray, out=None, out_nodata=NAN) -> RasterArray:
         _require_torch()
         lib = _native.lib()
@@ -574,6 +594,7 @@ class SrcSpaceModel(KernelModel):
             return False
         return not (self._model == Model.gain_offset and self._r2_inpaint_thresh is not None)
 
+    @_on_raster_device
     def fuse(self, src_ra: RasterArray, ref_ra: RasterArray, out=None, out_nodata=NAN) -> RasterArray:
         """
         ``apply(src_ra, fit(src_ra, ref_ra))`` without materialising the parameters: the reference image is resampled to
@@ -599,6 +620,7 @@ class SrcSpaceModel(KernelModel):
               *_out_args(corr, out_nodata), corr.data_ptr(), _stream())
         return RasterArray(_result(corr, on_device), src_ra.crs, src_ra.transform, nodata=out_nodata)
 
+    @_on_raster_device
     def fit(self, src_ra: RasterArray, ref_ra: RasterArray) -> RasterArray:
         _require_torch()
         on_device = src_ra.is_device and ref_ra.is_device

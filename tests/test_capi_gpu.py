@@ -579,3 +579,64 @@ def test_compare_sums_all_invalid():
     assert np.array_equal(got, np.zeros(7))
     stats = RasterCompare._band_stats(*got)
     assert stats['n'] == 0 and np.isnan(stats['r2']) and np.isnan(stats['rmse'])
+
+
+def test_concurrent_process_and_fit_from_host_threads():
+    """ The reference runs its (band, block) jobs on a thread pool (fuse.py:396-408); here the equivalent is several
+    host threads driving one RasterFuse / one model object at once.  Every thread must get exactly the result a single
+    thread gets (shared state: the band-plan cache, the stream pool, the native side streams and one-time set-up). """
+    import threading
+    from homonim_b200 import Model, ProcCrs, RasterArray, RasterFuse, RefSpaceModel, SrcSpaceModel
+    from homonim_b200.synthetic import make_pair
+    src_ra, ref_ra = make_pair(128, 96, 12, bands=4, dtype='uint16', seed=5, device='cuda')
+    jobs = [(Model.gain_blk_offset, (5, 5), None), (Model.gain_offset, (5, 5), 0.25), (Model.gain, (1, 1), None),
+            (Model.gain_offset, (7, 5), None)]
+    with RasterFuse(src_ra, ref_ra, proc_crs=ProcCrs.ref) as fuse:
+        def run(job):
+            model, kshape, thresh = job
+            corr, params = fuse.process(model=model, kernel_shape=kshape, param_filename='p',
+                                        model_config=dict(r2_inpaint_thresh=thresh))
+            return corr.array.clone(), params.array.clone()
+        expected = [run(job) for job in jobs]
+        torch.cuda.synchronize()
+        results, errors = {}, []
+
+        def worker(i):
+            try:
+                for rep in range(3):
+                    results[(i, rep)] = run(jobs[i % len(jobs)])
+                torch.cuda.current_stream().synchronize()
+            except Exception as ex:     # noqa
+                errors.append(repr(ex))
+        threads = [threading.Thread(target=worker, args=(i,)) for i in range(8)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        torch.cuda.synchronize()
+        assert not errors, errors
+        for (i, rep), (corr, params) in results.items():
+            exp_c, exp_p = expected[i % len(jobs)]
+            assert torch.equal(corr.view(torch.int32), exp_c.view(torch.int32)), (i, rep)
+            assert torch.equal(params.view(torch.int32), exp_p.view(torch.int32)), (i, rep)
+    # one model object, fit() + apply() from 8 threads, both processing spaces
+    s1 = RasterArray(src_ra.array[0].float().contiguous(), src_ra.crs, src_ra.transform, nodata=0.0)
+    r1 = RasterArray(ref_ra.array[0].float().contiguous(), ref_ra.crs, ref_ra.transform, nodata=ref_ra.nodata)
+    for model in (RefSpaceModel(Model.gain_offset, (5, 5), find_r2=True),
+                  SrcSpaceModel(Model.gain_blk_offset, (9, 9), find_r2=True)):
+        exp_p = model.fit(s1, r1)
+        exp_c = model.apply(s1, exp_p).array.clone()
+        out, errors = {}, []
+
+        def fit_worker(i):
+            try:
+                p_ra = model.fit(s1, r1)
+                out[i] = (p_ra.array.clone(), model.apply(s1, p_ra).array.clone())
+            except Exception as ex:     # noqa
+                errors.append(repr(ex))
+        threads = [threading.Thread(target=fit_worker, args=(i,)) for i in range(8)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        torch.cuda.synchronize()
+        assert not errors, errors
+        for i, (p_t, c_t) in out.items():
+            assert torch.equal(p_t.view(torch.int32), exp_p.array.view(torch.int32)), (type(model).__name__, i)
+            assert torch.equal(c_t.view(torch.int32), exp_c.view(torch.int32)), (type(model).__name__, i)
