@@ -182,8 +182,9 @@ __device__ __forceinline__ void hb_store1_out(void *base, long pix, float v, con
 // Stream-ordered scratch (cudaMallocAsync) comes from the device's default memory pool.  By default the pool hands
 // freed memory back to the OS at every synchronisation, so that each call would pay for a fresh allocation.  Keep a
 // BOUNDED amount cached (the pool is shared with the host application: an existing higher threshold is left alone, and
-// nothing is pinned for ever): 1 GiB covers the scratch of every entry point at BASELINE.json's largest configuration
-// (parameter-grid planes and work lists; full-resolution planes are the caller's).
+// nothing is pinned for ever): 4 GiB (2 % of a B200's HBM) covers the scratch of four concurrent bands at BASELINE.json's
+// largest configuration (~0.25 GB of parameter-grid planes and work lists per band of the 60k x 60k raster; full-resolution
+// planes are the caller's).
 static inline cudaError_t hb_pool_keep_memory()
 {
     static thread_local int done_for = -1;
@@ -193,7 +194,7 @@ static inline cudaError_t hb_pool_keep_memory()
     cudaMemPool_t pool;
     err = cudaDeviceGetDefaultMemPool(&pool, dev);
     if (err != cudaSuccess) return err;
-    unsigned long long keep = 1ull << 30, have = 0ull;
+    unsigned long long keep = 4ull << 30, have = 0ull;
     err = cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &have);
     if (err == cudaSuccess && have < keep) err = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     if (err == cudaSuccess) done_for = dev;

@@ -14,6 +14,7 @@
 //     every intermediate (SURVEY.md 8a numerics note): sums rounded to float32 where cv.boxFilter returns float32,
 //     kept double where cv.sqrBoxFilter returns float64, float32 numerator, double denominator, no FMA contraction.
 //   Zero padding beyond the raster (cv BORDER_CONSTANT) falls out of skipping out-of-range rows / columns.
+#include <stdlib.h>
 #include <type_traits>
 
 #include "hb_common.cuh"
@@ -77,8 +78,10 @@ __device__ __forceinline__ void hb_stg16_stream(float *p, float4 v)
 // 0/0 -> nan must come out exactly as numpy produces them).
 __device__ __forceinline__ double hb_ddiv(double a, double b)
 {
-    const double ab = fabs(b);
-    if (!(ab > 1e-280 && ab < 1e280) || !(fabs(a) < 1e280)) return a / b;
+    // (range test on the exponent fields, in the integer pipe: |b| in [2^-930, 2^930), |a| < 2^930 -- anything else,
+    //  zeros, infinities and nans included, takes the IEEE division)
+    const unsigned eb = ((unsigned)__double2hiint(b) >> 20) & 0x7ffu, ea = ((unsigned)__double2hiint(a) >> 20) & 0x7ffu;
+    if (eb - 93u >= 1860u || ea >= 1953u) return a / b;
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
     double e = fma(-b, r, 1.0);
@@ -124,6 +127,14 @@ __device__ __forceinline__ void pixel_terms(float s, float r, bool valid, double
 
 // MODEL: HB_MODEL_*; WANT_R2: third band; NQ: number of double sums carried (2, 4 or 5); C: columns per thread;
 // FUSED: write corr = gain * src + offset instead of the parameters.
+// LEAN: both planes use NaN as nodata and the kernel is at least 3 x 3 (the float32 rasters of every large configuration).
+//   The kernel is bound by instruction issue, not by memory, and the general form spends ~40 % of its instructions on
+//   bookkeeping: the 4-compare nodata test with its row / column gates, validity bits pulled back out of the ring for the
+//   leaving row, run-time exchange-buffer addresses, and the kh == 1 / kw == 1 special cases.  Here a pixel is valid iff
+//   neither value is NaN (ONE setp.num), rows / columns outside the raster are loaded as NaN so that they need no gate,
+//   the leaving row is simply tested again, and the row loop is unrolled by two so that the exchange buffer of a step is
+//   an immediate in every shared-memory address.  Same additions in the same order: results are bit-identical to the
+//   general form (tests/test_gpu_parity.py::test_same_grid_lean_equals_general).
 //
 // Shared-memory exchange of one output row (double-buffered, one barrier per row).  Per sum k a row of SLOTS doubles:
 //   slots [0, TW)      warp-local inclusive prefixes of the column sums; column c lives at (c % C) * threads + c / C,
@@ -136,8 +147,10 @@ __device__ __forceinline__ void pixel_terms(float s, float r, bool valid, double
 // no index arithmetic and no divergent branches -- the byte offsets are computed once per thread, the sum's offset is
 // an immediate and the buffer's offset a warp-uniform register.  (The launcher guarantees kw <= columns per warp, so a
 // window never spans more than two warps.)
-template <int MODEL, bool WANT_R2, int NQ, int C, bool FUSED>
-__global__ void __launch_bounds__(kFitThreads, (NQ >= 5 && C == 4) ? HB_FIT_MIN_CTAS - 1 : HB_FIT_MIN_CTAS)
+template <int MODEL, bool WANT_R2, int NQ, int C, bool FUSED, bool LEAN>
+__global__ void __launch_bounds__(kFitThreads, (NQ >= 5 && C == 4) ? HB_FIT_MIN_CTAS - 1
+                                               : (LEAN && NQ == 2) ? (MODEL == HB_MODEL_GAIN ? HB_FIT_MIN_CTAS + 2 : HB_FIT_MIN_CTAS + 1)
+                                               : HB_FIT_MIN_CTAS)
 fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__restrict__ ref, NoData nd_r,
                      FitGeom g, const double *__restrict__ norm, float *__restrict__ params,
                      float *__restrict__ sums_out, float *__restrict__ corr_out)   // (corr_out: g.ospec.dtype elements)
@@ -163,8 +176,11 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
     const int hh = g.kh / 2, hw = g.kw / 2;
     const int w = (int)g.w;
     const int cx = (int)blockIdx.x * g.tw_out - g.hw_al + t * C;     // first global column of this thread (may be < 0)
-    const long y0 = g.row0 + (long)blockIdx.y * g.rows_per_band;     // output rows [y0, y1) of the plane's rows [0, h)
-    const long y1 = min(y0 + (long)g.rows_per_band, g.row0 + g.nrows);
+    // (row indices are 32-bit -- the launcher checks h < 2^31 -- so that the per-row tests and the row * width products
+    //  are single instructions; only the final element offsets are 64-bit)
+    const int h = (int)g.h;
+    const int y0 = (int)g.row0 + (int)blockIdx.y * g.rows_per_band;  // output rows [y0, y1) of the plane's rows [0, h)
+    const int y1 = min(y0 + g.rows_per_band, (int)(g.row0 + g.nrows));
     const long plane = g.nrows * g.w;                                // output planes hold rows [row0, row0 + nrows)
     const float qnan = __int_as_float(0x7fc00000);
     double n0 = 1.0, n1 = 0.0;
@@ -180,6 +196,12 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
     const unsigned keep_nan_s = !(nd_s.has && nd_s.is_nan), keep_nan_r = !(nd_r.has && nd_r.is_nan);
     auto valid2 = [&](float sv, float rv, unsigned gate) -> bool {
         unsigned ok;
+        if constexpr (LEAN) {
+            // (gate: the row exists -- warp-uniform, its setp is hoisted out of the per-pixel code)
+            asm("{\n\t.reg .pred p, g;\n\tsetp.ne.u32 g, %3, 0;\n\tsetp.num.and.f32 p, %1, %2, g;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok) : "f"(sv), "f"(rv), "r"(gate));
+            return ok != 0u;
+        }
         asm("{\n\t.reg .pred p, q, ks, kr;\n\t"
             "setp.ne.u32 ks, %3, 0;\n\tsetp.ne.u32 kr, %4, 0;\n\t"
             "setp.num.or.f32 p, %1, %1, ks;\n\tsetp.neu.and.f32 p, %1, %5, p;\n\t"
@@ -193,6 +215,7 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
     unsigned cmask = 0;
 #pragma unroll
     for (int i = 0; i < C; i++) cmask |= ((cx + i >= 0) && (cx + i < w)) ? (1u << i) : 0u;
+    asm volatile("" : "+r"(cmask));      // (kept in its register: re-deriving it from cx and w every row costs more)
     const bool vec_ok = g.aligned && (C == 4) && (cmask == 0xfu);
     // this thread's columns are output columns iff they sit between the two halos (whole-thread granularity)
     const bool out_thread = (t * C >= g.hw_al) && (t * C + C <= g.hw_al + g.tw_out);
@@ -223,8 +246,9 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
 
     const unsigned long long pol_keep = hb_policy_evict_last(), pol_drop = hb_policy_evict_first();
     // `last_use`: the row is leaving the window (its final read) -- see the L2 note above
-    auto load_row = [&](long y, float (&s)[C], float (&r)[C], bool last_use) {
-        const float *srow = src + y * g.w + cx, *rrow = ref + y * g.w + cx;
+    auto load_row = [&](int y, float (&s)[C], float (&r)[C], bool last_use) {
+        const long off = (long)y * w + cx;
+        const float *srow = src + off, *rrow = ref + off;
         if (vec_ok) {
             const float4 a = hb_ldg16_hint(srow, last_use ? pol_drop : pol_keep);
             const float4 b = hb_ldg16_hint(rrow, last_use ? pol_drop : pol_keep);
@@ -236,21 +260,31 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
 #pragma unroll
             for (int i = 0; i < C; i++) {
                 const bool in = (cmask >> i) & 1u;
-                s[i] = in ? __ldg(srow + i) : 0.f;
-                r[i] = in ? __ldg(rrow + i) : 0.f;
+                s[i] = in ? __ldg(srow + i) : (LEAN ? qnan : 0.f);
+                r[i] = in ? __ldg(rrow + i) : (LEAN ? qnan : 0.f);
             }
         }
     };
 
-    const bool single_row = (g.kh == 1), single_col = (g.kw == 1);
-    const long e_first = y0 - hh, e_last = y1 - 1 + hh;
+    const bool single_row = !LEAN && (g.kh == 1), single_col = !LEAN && (g.kw == 1);
+    const int e_first = y0 - hh, e_last = y1 - 1 + hh;
+    const int l_first = max(e_first, 0);                             // first row that ever leaves a window of this band
     float se[C], re[C], sl[C], rl[C];
 #pragma unroll
     for (int i = 0; i < C; i++) { se[i] = re[i] = sl[i] = rl[i] = 0.f; }
-    auto fetch = [&](long e) {
-        const long l = e - g.kh;
-        if ((e >= 0) && (e < g.h)) load_row(e, se, re, false);
-        if (!single_row && (l >= e_first) && (l >= 0) && (l < g.h)) load_row(l, sl, rl, true);
+    auto fetch = [&](int e) {
+        const int l = e - g.kh;
+        if constexpr (LEAN) {
+            // both rows are ALWAYS loaded (row index clamped into the raster) and always consumed: a load that is only
+            // consumed on some paths makes the compiler wait for it -- and for every younger load sharing its scoreboard
+            // -- before it may reuse the destination registers (measured: 17 % of all stall samples).  Whether the row
+            // counts is decided by the validity test's gate.
+            load_row(min(max(e, 0), h - 1), se, re, false);
+            load_row(min(max(l, 0), h - 1), sl, rl, true);
+        } else {
+            if ((unsigned)e < (unsigned)h) load_row(e, se, re, false);
+            if (!single_row && (l >= l_first) && (l < h)) load_row(l, sl, rl, true);
+        }
     };
     // Vertical update with one row's pixels; `rowmask` = cmask if the row exists, else 0 (rows outside the raster / before
     // the band's first window contribute as invalid pixels: all-zero terms, so the update is free of branches; their
@@ -262,7 +296,7 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
         for (int i = 0; i < C; i++) {
             double q[NQ]; int cnt;
             bool v;
-            if (entering || !ring_has_leaver) v = valid2(s[i], r[i], (rowmask >> i) & 1u);
+            if (LEAN || entering || !ring_has_leaver) v = valid2(s[i], r[i], (rowmask >> i) & 1u);
             else v = (((unsigned)(vring[i] >> g.kh)) & (rowmask >> i) & 1u) != 0u;
             pixel_terms<NQ, NORM>(s[i], r[i], v, n0, n1, q, cnt);
             if (entering) {
@@ -277,26 +311,32 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
             }
         }
     };
+    // a row that does not exist contributes through an all-zero row mask (LEAN: columns outside the raster were loaded
+    // as NaN, so its mask is only about the row)
+    auto update = [&](const float (&s)[C], const float (&r)[C], bool row_exists, bool entering) {
+        accumulate(s, r, row_exists ? (LEAN ? 0xfu : cmask) : 0u, entering);
+    };
     // ---- warm-up: the rows above the first output row's centre only ENTER the window (nothing leaves, no output row is
     //      completed).  Fetch them 4 at a time -- all loads in flight together -- and accumulate in row order (the same
     //      additions, in the same order, as the row-by-row steps below would perform).
-    long e_begin = e_first;
+    int e_begin = e_first;
     if (!single_row) {
-        const long e_warm_end = y0 + hh;                             // first step that completes an output row
+        const int e_warm_end = y0 + hh;                              // first step that completes an output row
         for (; e_begin < e_warm_end; e_begin += 4) {
             float ws[4][C], wr[4][C];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const long e = e_begin + u;
+                const int e = e_begin + u;
 #pragma unroll
                 for (int i = 0; i < C; i++) { ws[u][i] = 0.f; wr[u][i] = 0.f; }
-                if (e < e_warm_end && e >= 0 && e < g.h) load_row(e, ws[u], wr[u], false);
+                if (LEAN) load_row(min(max(e, 0), h - 1), ws[u], wr[u], false);
+                else if (e < e_warm_end && (unsigned)e < (unsigned)h) load_row(e, ws[u], wr[u], false);
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const long e = e_begin + u;
+                const int e = e_begin + u;
                 if (e >= e_warm_end) break;
-                accumulate(ws[u], wr[u], ((e >= 0) && (e < g.h)) ? cmask : 0u, true);
+                update(ws[u], wr[u], (unsigned)e < (unsigned)h, true);
             }
         }
         e_begin = e_warm_end;
@@ -306,11 +346,10 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
     // ---- row loop: vertical update with rows e (entering) and e - kh (leaving), which were fetched one step ago; the
     //      rows of step e + 1 are requested as soon as those registers are free, so their latency hides behind the scan
     //      and the solve
-    for (long e = e_begin; e <= e_last; e++) {
-        const int bufoff = (int)(e & 1) * BUF_BYTES;                 // exchange buffer of this step (warp-uniform)
-        const long l = e - g.kh;
-        const bool has_e = (e >= 0) && (e < g.h);
-        const bool has_l = !single_row && (l >= e_first) && (l >= 0) && (l < g.h);
+    auto row_step = [&](const int e, const int bufoff) {            // bufoff: exchange buffer of this step (warp-uniform)
+        const int l = e - g.kh;
+        const bool has_e = (unsigned)e < (unsigned)h;
+        const bool has_l = !single_row && (l >= l_first) && (l < h);
         if (single_row) {                                            // kh == 1: the window IS this row (exact)
 #pragma unroll
             for (int i = 0; i < C; i++) {
@@ -319,10 +358,10 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
                 VN[i] = 0;
             }
         }
-        accumulate(se, re, has_e ? cmask : 0u, true);
-        accumulate(sl, rl, has_l ? cmask : 0u, false);
+        update(se, re, has_e, true);
+        update(sl, rl, has_l, false);
         if (e < e_last) fetch(e + 1);
-        const long y = e - hh;                                       // output row completed by this step
+        const int y = e - hh;                                        // output row completed by this step
 
         // ---- horizontal window sums: prefix over this thread's columns, warp scan of thread totals ----------------
         // (kw == 1: the window sum is the column sum itself -- exact, and no exchange is needed)
@@ -372,7 +411,7 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
             __syncthreads();        // (double-buffered: the next row writes the other buffer, so one barrier per row)
         }
 
-        if (!out_thread) continue;
+        if (!out_thread) return;
         float o_gain[C], o_off[C], o_r2[C], o_rs[C], o_ss[C], o_n[C];
 #pragma unroll
         for (int i = 0; i < C; i++) {
@@ -446,13 +485,13 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
             o_rs[i] = fR; o_ss[i] = fS; o_n[i] = mask ? fN : -1.f;   // count plane: -1 marks "outside the mask"
         }
         // ---- store -------------------------------------------------------------------------------------------------
-        const long yo = y - g.row0;                                  // row of the output planes
+        const long yo = (long)y - g.row0;                            // row of the output planes
         if (FUSED) {
             // fused apply (KernelModel.apply, kernel_model.py:461): corr = gain * src + offset with the centre row's
             // ORIGINAL source pixels (re-read: they entered the window kh/2 rows ago, an L2 hit), two float32
             // roundings as numpy; the parameters are not materialised
             float sc[C];
-            const float *srow = src + y * g.w + cx;
+            const float *srow = src + ((long)y * w + cx);
             if (vec_ok) {
                 const float4 a = hb_ldg16_hint(srow, pol_keep);
                 sc[0] = a.x;
@@ -504,7 +543,23 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
                 }
             }
         }
+    };
+    if constexpr (LEAN) {
+        // two steps per iteration: the buffer offsets are immediates in both copies of the body
+        for (int e = e_begin; e <= e_last; e += 2) {
+            row_step(e, 0);
+            if (e + 1 <= e_last) row_step(e + 1, BUF_BYTES);
+        }
+    } else {
+        for (int e = e_begin; e <= e_last; e++) row_step(e, ((e - e_begin) & 1) * BUF_BYTES);
     }
+}
+
+// HOMONIM_B200_FIT_GENERAL=1 (read at every call: a test switch) forces the general form of the kernel
+static bool hb_fit_force_general()
+{
+    const char *e = getenv("HOMONIM_B200_FIT_GENERAL");
+    return e != nullptr && e[0] == '1';
 }
 
 template <int MODEL, bool WANT_R2, int NQ, int C>
@@ -518,7 +573,7 @@ int launch_fit(const float *src, NoData nd_s, const float *ref, NoData nd_r, lon
     g.hw_al = ((hw + C - 1) / C) * C;
     g.tw_out = kFitThreads * C - 2 * g.hw_al;
     HB_REQUIRE(g.tw_out > 0 && kw <= 32 * C, "hb_fit_same_grid: kernel width %d is too wide for this variant", kw);
-    HB_REQUIRE(w < (1L << 30), "hb_fit_same_grid: rasters wider than 2^30 pixels are not supported");
+    HB_REQUIRE(w < (1L << 30) && h < (1L << 30), "hb_fit_same_grid: rasters beyond 2^30 pixels per side are not supported");
     const long xtiles = (w + g.tw_out - 1) / g.tw_out;
     // rows per band: every band re-reads (kh - 1) warm-up rows, so bands should be tall -- ~8 window heights -- unless
     // that leaves SMs idle (mid-size rasters: go down to 2 window heights to get one CTA per resident slot).  Small
@@ -552,15 +607,25 @@ int launch_fit(const float *src, NoData nd_s, const float *ref, NoData nd_r, lon
                  (params == nullptr || ((uintptr_t)params) % 16 == 0) &&
                  (sums == nullptr || ((uintptr_t)sums) % 16 == 0) &&
                  (corr == nullptr || ((uintptr_t)corr) % (4 * hb_out_size(ospec.dtype)) == 0)) ? 1 : 0;
+    // the lean form (see the kernel): NaN nodata on both planes, kernel at least 3 x 3; large-raster variant only
+    const bool lean = (C == 4) && nd_s.has && nd_s.is_nan && nd_r.has && nd_r.is_nan && kh > 1 && kw > 1 && !hb_fit_force_general();
     if (corr != nullptr) {
-        if constexpr (!WANT_R2)
-            fit_same_grid_kernel<MODEL, false, NQ, C, true><<<grid, kFitThreads, 0, stream>>>(src, nd_s, ref, nd_r, g, norm,
-                                                                                             nullptr, nullptr, corr);
-        else
+        if constexpr (!WANT_R2) {
+            if (lean && C == 4)
+                fit_same_grid_kernel<MODEL, false, NQ, C, true, (C == 4)><<<grid, kFitThreads, 0, stream>>>(
+                    src, nd_s, ref, nd_r, g, norm, nullptr, nullptr, corr);
+            else
+                fit_same_grid_kernel<MODEL, false, NQ, C, true, false><<<grid, kFitThreads, 0, stream>>>(
+                    src, nd_s, ref, nd_r, g, norm, nullptr, nullptr, corr);
+        } else
             HB_REQUIRE(false, "hb_fit_apply_same_grid: the fused apply does not produce an R2 band");
     } else {
-        fit_same_grid_kernel<MODEL, WANT_R2, NQ, C, false><<<grid, kFitThreads, 0, stream>>>(src, nd_s, ref, nd_r, g,
-                                                                                            norm, params, sums, nullptr);
+        if (lean && C == 4)
+            fit_same_grid_kernel<MODEL, WANT_R2, NQ, C, false, (C == 4)><<<grid, kFitThreads, 0, stream>>>(
+                src, nd_s, ref, nd_r, g, norm, params, sums, nullptr);
+        else
+            fit_same_grid_kernel<MODEL, WANT_R2, NQ, C, false, false><<<grid, kFitThreads, 0, stream>>>(
+                src, nd_s, ref, nd_r, g, norm, params, sums, nullptr);
     }
     HB_LAUNCH_OK("fit_same_grid_kernel");
     return 0;

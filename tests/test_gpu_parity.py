@@ -141,6 +141,41 @@ def test_same_grid_wide_kernels_vs_oracle(shape, model, kernel_shape, find_r2):
     check_params(param_ra.to_host().array, exp_params, float(np.nanmean(src)), f'params {kernel_shape}')
 
 
+@pytest.mark.parametrize('model, kernel_shape, find_r2', [
+    (Model.gain_offset, (31, 31), False), (Model.gain_offset, (15, 5), True), (Model.gain_blk_offset, (15, 15), False),
+    (Model.gain_blk_offset, (3, 9), True), (Model.gain, (5, 5), False), (Model.gain, (3, 3), True),
+    (Model.gain_offset, (3, 127), False), (Model.gain_offset, (127, 3), False),
+])
+def test_same_grid_lean_equals_general(model, kernel_shape, find_r2, monkeypatch):
+    """ The NaN-nodata form of the fit kernel (csrc/moments.cu, LEAN) performs the same additions in the same order as
+    the general form: parameters and the fused corrected image must be bit-identical, on a raster with NaN holes that
+    touch every border and whose width is not a multiple of the CTA strip. """
+    g = torch.Generator(device='cuda').manual_seed(11)
+    h, w = 2100, 2052
+    src = torch.rand((h, w), generator=g, device='cuda') * 0.5 + 0.2
+    ref = 0.7 * src + 0.05 + 0.02 * torch.rand((h, w), generator=g, device='cuda')
+    nan = float('nan')
+    for (r0, r1, c0, c1) in ((0, 40, 0, 300), (h - 9, h, 500, 900), (700, 760, w - 33, w), (1000, 1200, 1000, 1003),
+                             (300, 301, 0, w), (1500, 1600, 0, 7)):
+        src[r0:r1, c0:c1] = nan
+    ref[40:80, 1200:1300] = nan
+    km = KernelModel(model, kernel_shape, find_r2=find_r2, r2_inpaint_thresh=None)
+    norm = km._block_norm(src, nan, ref, nan) if model == Model.gain_blk_offset else None
+
+    def run():
+        params = km._fit_planes(src, nan, ref, nan, norm=norm)
+        rows = km._fit_planes(src, nan, ref, nan, norm=norm, rows=(311, 1217))
+        corr = torch.empty_like(src)
+        km._fit_apply_rows(src, nan, ref, nan, 0, h, norm=norm, out=corr)
+        torch.cuda.synchronize()
+        return params, rows, corr
+    lean = run()
+    monkeypatch.setenv('HOMONIM_B200_FIT_GENERAL', '1')
+    general = run()
+    for a, b, what in zip(lean, general, ('params', 'row range', 'fused corr')):
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32)), f'{what}: lean != general'
+
+
 def test_same_grid_row_range_equals_full_fit():
     """ hb_fit_same_grid_rows / hb_fit_apply_same_grid_rows: the rows of a band inside a larger plane get exactly the
     full fit's values for those rows wherever the band sits (what the row-band shards rely on). """
@@ -274,9 +309,8 @@ def test_ref_basic_apply_and_masking():
             assert (np.kron(eroded, np.ones((2, 2))).astype(bool) == out_ra.mask).all()
 
 
-@pytest.mark.parametrize('kernel_shape', [(3, 3), (5, 5), (5, 7), (9, 9), (11, 11), (15, 15)])
-def test_r2_inpainting(kernel_shape):
-    """ reference tests/test_kernel_model.py:166-203. """
+def _inpaint_scenario(kernel_shape):
+    """ The rasters of reference tests/test_kernel_model.py:170-180: src == ref except one -100 pixel in the middle. """
     _, ra50 = _conftest_rasters()
     src_ra, ref_ra = ra50, ra50.copy()
     loc = np.floor(np.array(ref_ra.shape) / 2).astype(int)
@@ -284,6 +318,14 @@ def test_r2_inpainting(kernel_shape):
     low = np.zeros(ref_ra.shape, bool)
     low[ul[0]:ul[0] + kernel_shape[0], ul[1]:ul[1] + kernel_shape[1]] = True
     ref_ra.array[loc[0], loc[1]] = -100
+    return src_ra, ref_ra, low
+
+
+@pytest.mark.parametrize('kernel_shape', [(5, 5), (5, 7), (9, 9)])
+def test_r2_inpainting(kernel_shape):
+    """ reference tests/test_kernel_model.py:166-203, at the kernels the reference runs it with (on this 40 x 20 raster the
+    scenario's own `R2 < .5 around the bad pixel` stops holding from (11, 11) on -- for the reference too). """
+    src_ra, ref_ra, low = _inpaint_scenario(kernel_shape)
     no_inp = RefSpaceModel(Model.gain_offset, kernel_shape=kernel_shape, r2_inpaint_thresh=-np.inf).fit(src_ra, ref_ra)
     inp = RefSpaceModel(Model.gain_offset, kernel_shape=kernel_shape, r2_inpaint_thresh=0.5).fit(src_ra, ref_ra)
     for param_ra in (no_inp, inp):
@@ -292,6 +334,33 @@ def test_r2_inpainting(kernel_shape):
     assert no_inp.array[1, no_inp.mask] != pytest.approx(0, abs=1e-1)
     assert inp.array[1, inp.mask] == pytest.approx(0, abs=1e-1)
     assert inp.array[0, inp.mask].var() < no_inp.array[0, no_inp.mask].var()
+
+
+@pytest.mark.parametrize('kernel_shape', [(3, 3), (3, 5), (5, 5), (5, 7), (7, 7), (9, 9), (11, 11), (13, 13), (15, 15)])
+@pytest.mark.parametrize('thresh', [0.5, 0.25])
+def test_r2_inpainting_vs_oracle(kernel_shape, thresh):
+    """ The same scenario for every kernel from (3, 3) to (15, 15), in-painted parameters against the oracle (the
+    reference's own numpy / cv2 statements + the nodata-fill restatement): masks, infinities and NaNs in the same places,
+    values within 1e-4.  (At (3, 3) corner windows of this raster hold a single distinct value: den = 0, R2 = NaN on both
+    sides -- which is why the reference's own scenario starts at (5, 5).) """
+    import warnings as _w
+    kmnp = _oracle()
+    src_ra, ref_ra, low = _inpaint_scenario(kernel_shape)
+    with _w.catch_warnings():
+        _w.simplefilter('ignore')
+        got = RefSpaceModel(Model.gain_offset, kernel_shape=kernel_shape, r2_inpaint_thresh=thresh).fit(src_ra, ref_ra)
+        exp = kmnp.refspace_fit(src_ra.array, tuple(src_ra.transform), float('nan'), ref_ra.array,
+                                tuple(ref_ra.transform), float('nan'), Model.gain_offset, kernel_shape, False, thresh)
+    got_a = got.array
+    assert got_a.shape == exp.shape == (3,) + ref_ra.shape
+    for b in range(3):
+        assert np.array_equal(np.isnan(got_a[b]), np.isnan(exp[b])), f'band {b}: NaN pattern differs'
+        assert np.array_equal(np.isinf(got_a[b]), np.isinf(exp[b])), f'band {b}: infinities differ'
+    fin = np.isfinite(exp[0]) & np.isfinite(exp[1])
+    assert rel_err(got_a[0][fin], exp[0][fin], 1e-3 * np.abs(exp[0][fin]).mean()) <= RTOL
+    assert rel_err(got_a[1][fin], exp[1][fin], np.abs(exp[0][fin]) * float(np.nanmean(src_ra.array))) <= RTOL
+    fin2 = np.isfinite(exp[2])
+    assert np.max(np.abs(got_a[2][fin2] - exp[2][fin2])) <= 1e-4
 
 
 def test_grid_mismatch_raises():
