@@ -74,23 +74,38 @@ __device__ __forceinline__ void hb_stg16_stream(float *p, float4 v)
 // a / b in double with a quotient that is correctly rounded in all but a vanishing fraction of cases (approximate
 // reciprocal + 2 Newton steps + one residual correction: ~9 instructions instead of the ~35 of the IEEE routine).
 // Its result is immediately rounded to float32 by the callers, so a last-bit difference in double is invisible
-// except on an exact float32 tie.  Zero / non-finite / extreme operands take the IEEE division (x/0 -> +-inf,
-// 0/0 -> nan must come out exactly as numpy produces them).
-__device__ __forceinline__ double hb_ddiv(double a, double b)
+// except on an exact float32 tie.  Straight-line code: operands outside the form's range -- |b| not in [2^-930, 2^930),
+// |a| >= 2^930, zeros / infinities / nans included -- set `bad`, and the caller repeats that pixel with IEEE divisions
+// (x/0 -> +-inf, 0/0 -> nan must come out exactly as numpy produces them).  The range test reads the exponent fields
+// in the integer pipe.
+__device__ __forceinline__ double hb_ddiv_fast(double a, double b, bool &bad)
 {
-    // (range test on the exponent fields, in the integer pipe: |b| in [2^-930, 2^930), |a| < 2^930 -- anything else,
-    //  zeros, infinities and nans included, takes the IEEE division)
     const unsigned eb = ((unsigned)__double2hiint(b) >> 20) & 0x7ffu, ea = ((unsigned)__double2hiint(a) >> 20) & 0x7ffu;
-    if (eb - 93u >= 1860u || ea >= 1953u) return a / b;
+    bad = bad || (eb - 93u >= 1860u) || (ea >= 1953u);
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
     double e = fma(-b, r, 1.0);
     r = fma(r, e, r);
     e = fma(-b, r, 1.0);
     r = fma(r, e, r);
-    double q = a * r;
+    const double q = a * r;
     const double rem = fma(-b, q, a);
     return fma(rem, r, q);
+}
+
+// 1 / n in double for a window's pixel count n (an integer in [1, 127 * 127]), relative error < 2^-52.  Used for
+// offset = x / n in float32 (kernel_model.py:351) as RN_f32(x * (1 / n)): x * (1 / n) is within 2^-51.9 of the exact
+// quotient, while x / n, for a float32 x and an integer n < 2^14, is either exactly representable or at least 2^-39
+// (relative) away from the nearest float32 rounding tie -- so the rounded result IS the IEEE float32 quotient; infinite
+// and nan x propagate as they do in the division.  (n = 0 only occurs outside the mask, where the result is unused.)
+__device__ __forceinline__ double hb_drcp_count(double n)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(n));
+    double e = fma(-n, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-n, r, 1.0);
+    return fma(r, e, r);
 }
 
 // contribution of one pixel to the running sums
@@ -413,8 +428,18 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
 
         if (!out_thread) return;
         float o_gain[C], o_off[C], o_r2[C], o_rs[C], o_ss[C], o_n[C];
-#pragma unroll
-        for (int i = 0; i < C; i++) {
+        // One pixel: window sums from the exchange buffer, closed-form solve.  IEEE = false: every division takes the
+        // straight-line fast form and the pixel is reported "bad" when an operand is outside that form's range; bad pixels
+        // (zero / non-finite denominators: flat windows, borders of nodata areas -- rare) are then solved again with IEEE
+        // divisions.  With no branch inside the common path the compiler interleaves the C independent solves instead of
+        // running their ~25-deep dependent chains one after the other.
+        auto solve_pixel = [&](const int i, auto ieee_tag) -> bool {
+            constexpr bool IEEE = decltype(ieee_tag)::value;
+            bool bad = false;
+            auto ddiv = [&](double a, double b) -> double {
+                if constexpr (IEEE) return a / b;
+                else return hb_ddiv_fast(a, b, bad);
+            };
             double W[NQ];
             int N = 0;
             if (single_col) {
@@ -437,12 +462,15 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
                 fS = (float)W[Q_S];
                 const float fP = (float)W[Q_P];
                 fN = (float)N;
+                const double dN = (double)fN;
                 const float num = __fsub_rn(__fmul_rn(fN, fP), __fmul_rn(fS, fR));                  // :338, float32
-                const double den = __dsub_rn(__dmul_rn((double)fN, W[Q_S2]), (double)__fmul_rn(fS, fS));   // :342
-                gain = (float)hb_ddiv((double)num, den);                                             // :348
-                off = __fdiv_rn(__fsub_rn(fR, __fmul_rn(gain, fS)), fN);                            // :351
+                const double den = __dsub_rn(__dmul_rn(dN, W[Q_S2]), (double)__fmul_rn(fS, fS));    // :342
+                gain = (float)ddiv((double)num, den);                                                // :348
+                const float onum = __fsub_rn(fR, __fmul_rn(gain, fS));
+                if constexpr (IEEE) off = __fdiv_rn(onum, fN);                                       // :351
+                else off = (float)__dmul_rn((double)onum, hb_drcp_count(dN));   // == onum / fN correctly rounded, see there
                 if (WANT_R2) {
-                    const double ss_tot = __dsub_rn(__dmul_rn((double)fN, W[Q_R2]), (double)__fmul_rn(fR, fR));   // :179
+                    const double ss_tot = __dsub_rn(__dmul_rn(dN, W[Q_R2]), (double)__fmul_rn(fR, fR));   // :179
                     const double t1 = __dmul_rn((double)__fmul_rn(gain, gain), W[Q_S2]);
                     const float t2 = __fmul_rn(__fmul_rn(2.f, __fmul_rn(gain, off)), fS);
                     const float t3 = __fmul_rn(__fmul_rn(2.f, gain), fP);
@@ -453,14 +481,14 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
                     ss_res = __dsub_rn(ss_res, (double)t4);
                     ss_res = __dadd_rn(ss_res, W[Q_R2]);
                     ss_res = __dadd_rn(ss_res, (double)t6);
-                    ss_res = __dmul_rn(ss_res, (double)fN);                                          // :203
-                    r2 = __fsub_rn(1.f, (float)hb_ddiv(ss_res, ss_tot));                            // :212-213
+                    ss_res = __dmul_rn(ss_res, dN);                                                  // :203
+                    r2 = __fsub_rn(1.f, (float)ddiv(ss_res, ss_tot));                               // :212-213
                 }
             } else {
                 // gain (kernel_model.py:265) -- for gain-blk-offset on the normalised, float64 source sums
                 float g0;
-                if (NORM) g0 = (float)hb_ddiv((double)fR, W[Q_S]);
-                else { fS = (float)W[Q_S]; g0 = __fdiv_rn(fR, fS); }
+                if (NORM) g0 = (float)ddiv((double)fR, W[Q_S]);
+                else { fS = (float)W[Q_S]; g0 = __fdiv_rn(fR, fS); }   // (12 float32 instructions: cheaper than any double route)
                 if (WANT_R2) {
                     fN = (float)N;
                     const double ss_tot = __dsub_rn(__dmul_rn((double)fN, W[Q_R2]), (double)__fmul_rn(fR, fR));
@@ -469,7 +497,7 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
                     const double t3 = NORM ? __dmul_rn((double)g2, W[Q_P]) : (double)__fmul_rn(g2, (float)W[Q_P]);
                     double ss_res = __dadd_rn(__dsub_rn(t1, t3), W[Q_R2]);                           // :201
                     ss_res = __dmul_rn(ss_res, (double)fN);
-                    r2 = __fsub_rn(1.f, (float)hb_ddiv(ss_res, ss_tot));
+                    r2 = __fsub_rn(1.f, (float)ddiv(ss_res, ss_tot));
                 }
                 if (NORM) {
                     off = (float)__dmul_rn((double)g0, n1);                                          // :301
@@ -483,6 +511,15 @@ fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__
             o_off[i] = mask ? off : qnan;
             o_r2[i] = mask ? r2 : qnan;
             o_rs[i] = fR; o_ss[i] = fS; o_n[i] = mask ? fN : -1.f;   // count plane: -1 marks "outside the mask"
+            return bad && mask;                                      // (outside the mask the values are not used)
+        };
+        unsigned redo = 0u;
+#pragma unroll
+        for (int i = 0; i < C; i++) redo |= solve_pixel(i, std::false_type{}) ? (1u << i) : 0u;
+        if (redo != 0u) {
+#pragma unroll
+            for (int i = 0; i < C; i++)
+                if ((redo >> i) & 1u) solve_pixel(i, std::true_type{});
         }
         // ---- store -------------------------------------------------------------------------------------------------
         const long yo = (long)y - g.row0;                            // row of the output planes
