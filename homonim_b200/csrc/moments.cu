@@ -30,6 +30,22 @@ constexpr int kMaxHalfW = 63;                    // kw <= 127: a window spans at
 
 enum { Q_S = 0, Q_R = 1, Q_P = 2, Q_S2 = 3, Q_R2 = 4 };
 
+// resident CTAs per SM the register allocation aims for (measured on 16384 x 16384 planes, scratch/perf_fit.py): the
+// kernel is latency-bound, so the variants that carry fewer running sums trade registers for warps
+#ifndef HB_FIT_CTAS_NQ4
+#define HB_FIT_CTAS_NQ4 HB_FIT_MIN_CTAS
+#endif
+#ifndef HB_FIT_CTAS_NQ5
+#define HB_FIT_CTAS_NQ5 (HB_FIT_MIN_CTAS - 1)
+#endif
+constexpr int fit_min_ctas(int model, int nq, int c, bool lean)
+{
+    if (c != 4) return HB_FIT_MIN_CTAS;
+    if (nq >= 5) return lean ? HB_FIT_CTAS_NQ5 : HB_FIT_MIN_CTAS - 1;
+    if (nq == 4) return lean ? HB_FIT_CTAS_NQ4 : HB_FIT_MIN_CTAS;
+    return lean ? (model == HB_MODEL_GAIN ? HB_FIT_MIN_CTAS + 2 : HB_FIT_MIN_CTAS + 1) : HB_FIT_MIN_CTAS;
+}
+
 struct FitGeom {
     long h, w;
     int kh, kw;
@@ -163,9 +179,7 @@ __device__ __forceinline__ void pixel_terms(float s, float r, bool valid, double
 // an immediate and the buffer's offset a warp-uniform register.  (The launcher guarantees kw <= columns per warp, so a
 // window never spans more than two warps.)
 template <int MODEL, bool WANT_R2, int NQ, int C, bool FUSED, bool LEAN>
-__global__ void __launch_bounds__(kFitThreads, (NQ >= 5 && C == 4) ? HB_FIT_MIN_CTAS - 1
-                                               : (LEAN && NQ == 2) ? (MODEL == HB_MODEL_GAIN ? HB_FIT_MIN_CTAS + 2 : HB_FIT_MIN_CTAS + 1)
-                                               : HB_FIT_MIN_CTAS)
+__global__ void __launch_bounds__(kFitThreads, fit_min_ctas(MODEL, NQ, C, LEAN))
 fit_same_grid_kernel(const float *__restrict__ src, NoData nd_s, const float *__restrict__ ref, NoData nd_r,
                      FitGeom g, const double *__restrict__ norm, float *__restrict__ params,
                      float *__restrict__ sums_out, float *__restrict__ corr_out)   // (corr_out: g.ospec.dtype elements)

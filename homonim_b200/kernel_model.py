@@ -589,8 +589,9 @@ class SrcSpaceModel(KernelModel):
 
     def can_fuse(self, src_ra: RasterArray, ref_ra: RasterArray) -> bool:
         """ True when apply(fit()) can run with the apply step fused into the fit kernel (`fuse`): the parameters are
-        final after the fit (no R2 in-painting), no partial-coverage masking, no per-entry-point timer active. """
-        if self._mask_partial or KernelTimer.active is not None:
+        final after the fit (no R2 in-painting) and no partial-coverage masking.  (The fused form is still one C-ABI
+        call per kernel, so a per-entry-point timer sees the same launches as an untimed call.) """
+        if self._mask_partial:
             return False
         return not (self._model == Model.gain_offset and self._r2_inpaint_thresh is not None)
 
