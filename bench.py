@@ -51,6 +51,12 @@ NAN = float('nan')
 
 WORKLOADS = {
     # name: hp, wp (proc grid), ratio, bands, dtype, mu, src_nodata, model, kernel, thresh, proc_crs
+    # C1 (BASELINE.json configs[0]): the reference's own test images (real data, mis-aligned grids), committed as a fixture
+    'c1': dict(fixture='docs_cli_ngi1', hp=711, wp=403, ratio=2, bands=3, dtype='uint8', mu=100.0, src_nodata=0.0,
+               model='gain-blk-offset', kernel_shape=(5, 5), r2_inpaint_thresh=0.25, proc_crs='ref',
+               src_shape=(1421, 805),
+               desc='C1: the reference\'s test images ngi_rgb_byte_1.tif (3-band uint8 1421x805, 5 m) + sentinel2_b432_byte.tif '
+                    '(10 m, grids mis-aligned by a fraction of a pixel), gain-blk-offset 5x5, proc_crs=ref'),
     'c2': dict(hp=500, wp=500, ratio=20, bands=4, dtype='uint16', mu=3000.0, src_nodata=0.0, model='gain-offset',
                kernel_shape=(15, 15), r2_inpaint_thresh=0.25, proc_crs='ref',
                desc='C2: synthetic 4-band uint16 10000x10000 aerial vs 10 m reference (20x coarser), gain-offset '
@@ -84,13 +90,24 @@ WORKLOADS = {
 ROW_BAND_CHUNK = 125          # proc rows per generation chunk of the sharded rasters (independent of the rank count)
 
 
+def _data(cfg):
+    return ('real: the reference\'s own test images (tests/golden fixture)' if cfg.get('fixture') else 'synthetic')
+
+
+def _small(cfg):
+    """ Workloads whose inputs fit the 126 MB L2: timed step by step with an L2 flush in between. """
+    hs, ws = cfg.get('src_shape') or (cfg['hp'] * cfg['ratio'], cfg['wp'] * cfg['ratio'])
+    return hs * ws * cfg['bands'] * 4 < (256 << 20)
+
+
 def _config(cfg):
     """ The `config` object of the JSON line -- identical for both arms (`--impl b200` / `--impl reference`). """
-    hs, ws = cfg['hp'] * cfg['ratio'], cfg['wp'] * cfg['ratio']
+    hs, ws = cfg.get('src_shape') or (cfg['hp'] * cfg['ratio'], cfg['wp'] * cfg['ratio'])
     return {'workload': cfg['desc'], 'kernel_model': cfg['model'], 'kernel_shape': list(cfg['kernel_shape']),
             'r2_inpaint_thresh': cfg['r2_inpaint_thresh'], 'proc_crs': cfg['proc_crs'], 'bands': cfg['bands'],
             'src_dtype': cfg['dtype'], 'src_shape': [hs, ws], 'pixels_per_step_per_image': int(hs * ws * cfg['bands']),
-            'l2': 'inputs larger than L2 (no flush needed)'}
+            'l2': ('inputs fit in L2: a 512 MB buffer is written between timed steps (each step timed on its own)'
+                   if _small(cfg) else 'inputs larger than L2 (no flush needed)')}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -236,6 +253,21 @@ class CpuReference:
         return time.perf_counter() - t0, n_blocks
 
 
+def _fixture_pair(cfg, device):
+    """ The C1 pair from tests/golden (the reference's own test images, read once from its GeoTIFFs by
+    oracle/make_golden_docs.py): uint8 source with nodata 0, reference widened to float32 (it has no nodata). """
+    import torch
+    from homonim_b200 import CRS, Affine, RasterArray
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tests', 'golden')
+    meta = json.load(open(os.path.join(root, cfg['fixture'] + '.json')))
+    with np.load(os.path.join(root, cfg['fixture'] + '.npz')) as data:
+        src, ref = data['src'], data['s2'].astype('float32')
+    crs = CRS.from_epsg(32735)
+    src_ra = RasterArray(torch.from_numpy(src).to(device), crs, Affine(*meta['src_transform'][:6]), nodata=cfg['src_nodata'])
+    ref_ra = RasterArray(torch.from_numpy(ref).to(device), crs, Affine(*meta['s2_transform'][:6]), nodata=float('nan'))
+    return src_ra, ref_ra
+
+
 def _cpu_sample(cfg, src_ra, ref_ra, n_bands):
     """ Host arrays of the bounded CPU sample: whole bands for the proc_crs = ref workloads, a crop for the workloads
     that fit at source resolution (the full 20 000^2 float32 planes would take minutes per band on the host). """
@@ -267,8 +299,11 @@ def run_reference(args, cfg, rank):
         hp, wp = (min(cfg['hp'], ROW_BAND_CHUNK), cfg['wp']) if cfg['ratio'] > 1 else (min(cfg['hp'], 1024), cfg['wp'])
     else:
         hp, wp = (cfg['hp'], cfg['wp']) if cfg['proc_crs'] == 'ref' else (min(cfg['hp'], 2048), min(cfg['wp'], 2048))
-    src_ra, ref_ra = make_pair(hp, wp, cfg['ratio'], bands=cfg['bands'], dtype=cfg['dtype'], mu=cfg['mu'], seed=2,
-                               device='cpu', src_nodata=cfg['src_nodata'])
+    if cfg.get('fixture'):
+        src_ra, ref_ra = _fixture_pair(cfg, 'cpu')
+    else:
+        src_ra, ref_ra = make_pair(hp, wp, cfg['ratio'], bands=cfg['bands'], dtype=cfg['dtype'], mu=cfg['mu'], seed=2,
+                                   device='cpu', src_nodata=cfg['src_nodata'])
     n_bands = cfg['bands']
     src_np, ref_np = src_ra.to_host().array, ref_ra.to_host().array
     src_tf, ref_tf = tuple(src_ra.transform), tuple(ref_ra.transform)
@@ -321,7 +356,7 @@ def run_reference(args, cfg, rank):
         'impl': 'reference', 'metric': 'fit+apply Mpix/s', 'value': value, 'unit': 'Mpix/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
         'higher_is_better': True, 'scaling': 'strong' if cfg.get('sharded') else 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': _config(cfg),
+        'vs_baseline': None, 'dtype': 'f32', 'data': _data(cfg), 'config': _config(cfg),
         'cpu_baseline': {'value': value, 'unit': 'Mpix/s', 'cores': cores, 'kind': cpu.kind, 'sample': sample,
                          'headline_mode': head, 'modes': results, 'implementation': cpu.where,
                          'gdal': 'rasterio.warp.reproject / rasterio.fill.fillnodata served by oracle/gdal_restate '
@@ -871,8 +906,11 @@ def main():
         return
 
     # ---- inputs: every rank corrects its own source image (seeded per rank), resident in HBM ------------------------
-    src_ra, ref_ra = make_pair(cfg['hp'], cfg['wp'], cfg['ratio'], bands=cfg['bands'], dtype=cfg['dtype'],
-                               mu=cfg['mu'], seed=2 + rank, device=device, src_nodata=cfg['src_nodata'])
+    if cfg.get('fixture'):
+        src_ra, ref_ra = _fixture_pair(cfg, device)
+    else:
+        src_ra, ref_ra = make_pair(cfg['hp'], cfg['wp'], cfg['ratio'], bands=cfg['bands'], dtype=cfg['dtype'],
+                                   mu=cfg['mu'], seed=2 + rank, device=device, src_nodata=cfg['src_nodata'])
     npix = src_ra.array.numel()                      # source band-pixels per step
     model_config = dict(r2_inpaint_thresh=cfg['r2_inpaint_thresh'])
     fuse = RasterFuse(src_ra, ref_ra, proc_crs=ProcCrs(cfg['proc_crs']))
@@ -903,13 +941,28 @@ def main():
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_region0 = time.perf_counter()
-    start.record()
-    for _ in range(args.steps):
-        step()
-    end.record()
-    barrier()
+    if _small(cfg):
+        # inputs fit in L2: flush it between steps (a 512 MB fill) and time every step on its own
+        flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=device)
+        pairs = []
+        for i in range(args.steps):
+            flush_buf.fill_(i & 0xff)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step()
+            b.record()
+            pairs.append((a, b))
+        barrier()
+        elapsed_ms = sum(a.elapsed_time(b) for a, b in pairs)
+        del flush_buf
+    else:
+        start.record()
+        for _ in range(args.steps):
+            step()
+        end.record()
+        barrier()
+        elapsed_ms = start.elapsed_time(end)
     launches = lib.hb_launch_count()
-    elapsed_ms = start.elapsed_time(end)
     # per-launch kernel durations for the roofline: the same K steps again with the bands on ONE stream (concurrent
     # bands would overlap kernels and inflate each other's event-to-event durations)
     with KernelTimer() as timer:
@@ -1047,7 +1100,7 @@ def main():
         line = {
             'metric': 'fit+apply Mpix/s', 'value': round(value, 1), 'unit': 'Mpix/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(elapsed_ms / args.steps, 4),
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': _data(cfg),
             'config': _config(cfg), 'sharding': 'one source image per GPU, no collective',
             'clocks': _clocks_summary(samples, (t_region0, t_region1)), 'e2e': e2e, 'gpu_launches': int(launches),
             'roofline': roofline, 'parity': parity, 'cpu_baseline': cpu_baseline, 'row_band': row_band,
