@@ -38,7 +38,7 @@ extern "C" {
 #define HB_ABI_VERSION 7
 
 /* storage dtype of a source raster plane */
-enum { HB_U8 = 0, HB_U16 = 1, HB_F32 = 2, HB_I16 = 3 };   /* HB_I16: output of hb_convert_dtype only */
+enum { HB_U8 = 0, HB_U16 = 1, HB_F32 = 2, HB_I16 = 3 };   /* HB_I16: output dtypes only (out_dtype, hb_convert_dtype) */
 /* homonim.enums.Model (homonim/enums.py:22-42) */
 enum { HB_MODEL_GAIN = 0, HB_MODEL_GAIN_BLK_OFFSET = 1, HB_MODEL_GAIN_OFFSET = 2 };
 /* up-sampling methods of hb_resample_up */
