@@ -584,7 +584,8 @@ class RowBandJob:
         others' streaming kernels (``serial``: one stream, for per-kernel timing).  ``keep_band0``: tensor receiving band
         0's result. """
         torch, cfg = self.torch, self.cfg
-        main = torch.cuda.current_stream()
+        from homonim_b200.kernel_model import current_stream, on_stream
+        main = current_stream()
         for st in self.streams + self.hi_streams:
             st.wait_stream(main)
         ns = len(self.streams)
@@ -593,7 +594,7 @@ class RowBandJob:
                 for band in range(cfg['bands'])]
         if self.same_grid:
             for band in range(cfg['bands']):
-                with torch.cuda.stream(self.streams[pick(band)]):
+                with on_stream(self.streams[pick(band)]):
                     self.hd.fit_apply_same_grid_sharded(self.model, self.src[band], cfg['src_nodata'], self.ref[band],
                                                         NAN, self.bands, self.group, out=outs[band])
         else:
@@ -603,7 +604,7 @@ class RowBandJob:
             shards = {}
 
             def begin(band):
-                with torch.cuda.stream(self.streams[pick(band)]):
+                with on_stream(self.streams[pick(band)]):
                     src_local = self.RasterArray(self.src[band], self.crs, self.src_local_tf, nodata=cfg['src_nodata'])
                     ref_ra = self.RasterArray(self.ref[band], self.crs, self.ref_global_tf, nodata=NAN)
                     shards[band] = self.hd.fuse_refspace_sharded_begin(self.model, src_local, ref_ra, self.bands,
@@ -611,10 +612,10 @@ class RowBandJob:
 
             def end(band):
                 if serial or not self.stagger:
-                    with torch.cuda.stream(self.streams[pick(band)]):
+                    with on_stream(self.streams[pick(band)]):
                         self.hd.fuse_refspace_sharded_end(shards.pop(band), out=outs[band])
                 else:
-                    with torch.cuda.stream(self.hi_streams[pick(band)]):
+                    with on_stream(self.hi_streams[pick(band)]):
                         self.hd.fuse_refspace_sharded_end(shards.pop(band), out=outs[band],
                                                           apply_stream=self.streams[pick(band)])
 

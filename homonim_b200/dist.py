@@ -66,6 +66,18 @@ def _run_p2p(sends, recvs, group=None) -> None:
             t.copy_(buf)
 
 
+_RANKS = {}
+
+
+def _rank(group=None) -> int:
+    """ ``dist.get_rank(group)``, cached per group (25 us per call otherwise, several calls per band and step). """
+    key = id(group if group is not None else dist.group.WORLD)     # (a re-initialised default group is a new object)
+    r = _RANKS.get(key)
+    if r is None:
+        r = _RANKS[key] = dist.get_rank(group)
+    return r
+
+
 def shard_sources(n_sources: int, rank: int, world_size: int) -> List[int]:
     """ Indexes of the independent source images this rank processes (round-robin; SURVEY.md 8e batch mode). """
     return list(range(rank, n_sources, world_size))
@@ -365,7 +377,7 @@ def fuse_refspace_sharded_begin(model, src_local: RasterArray, ref_ra: RasterArr
     and exchanges of the second stages (with a slab of a few thousand rows per rank those are host-paced, not GPU-paced).
     """
     from homonim_b200 import kernel_model as km
-    rank = dist.get_rank(group)
+    rank = _rank(group)
     a, b = bands.band(rank)
     src_t = km._to_device(src_local.array)
     ref_t = km._as_f32_plane(km._to_device(ref_ra.array), ref_ra.nodata).contiguous()
@@ -374,7 +386,7 @@ def fuse_refspace_sharded_begin(model, src_local: RasterArray, ref_ra: RasterArr
     ds_done = None
     if src_ds_local.is_cuda:
         ds_done = torch.cuda.Event()
-        ds_done.record()
+        ds_done.record(km.current_stream())
     return _RefspaceShard(model, src_t, src_local, ref_ra, ref_t, bands, group, src_ds_local, ds_done)
 
 
@@ -389,13 +401,14 @@ def fuse_refspace_sharded_end(shard: _RefspaceShard, out=None, apply_stream=None
     kernel launched behind another band's streaming kernel only runs once that kernel has handed out all its CTAs
     (measured: the stages then simply add up); with priorities it slips in between.
     """
+    from homonim_b200 import kernel_model as km
     from homonim_b200.enums import Model
     model, src_t, src_local, ref_ra, ref_t, bands, group, src_ds_local, ds_done = shard
-    rank = dist.get_rank(group)
+    rank = _rank(group)
     a, b = bands.band(rank)
     nan = float('nan')
     if ds_done is not None:
-        cur = torch.cuda.current_stream()
+        cur = km.current_stream()
         cur.wait_event(ds_done)
         src_ds_local.record_stream(cur)
     # whole-block statistics from per-rank accumulators
@@ -416,10 +429,10 @@ def fuse_refspace_sharded_end(shard: _RefspaceShard, out=None, apply_stream=None
     src_ra = RasterArray(src_t, src_local.crs, src_local.transform, nodata=src_local.nodata)
     if apply_stream is not None and params.is_cuda:
         fitted = torch.cuda.Event()
-        fitted.record()
+        fitted.record(km.current_stream())
         apply_stream.wait_event(fitted)
         params.record_stream(apply_stream)
-        with torch.cuda.stream(apply_stream):
+        with km.on_stream(apply_stream):
             corr_local = model.apply(src_ra, param_ra, out=out)
     else:
         corr_local = model.apply(src_ra, param_ra, out=out)

@@ -25,7 +25,8 @@ from homonim_b200.enums import Model, ProcCrs
 from homonim_b200.errors import ConfigWarning, ImageContentError, IoError
 from homonim_b200.files import FilePair, is_path
 from homonim_b200.geometry import Affine
-from homonim_b200.kernel_model import KernelModel, RefSpaceModel, SrcSpaceModel, overlap_for_kernel
+from homonim_b200.kernel_model import (KernelModel, RefSpaceModel, SrcSpaceModel, current_stream, on_stream,
+                                       overlap_for_kernel)
 from homonim_b200.raster_array import RasterArray, is_tensor
 
 try:
@@ -349,12 +350,12 @@ class RasterFuse:
         # rasters, one band's host <-> device copies overlap the other bands' kernels.
         n_streams = min(n_bands, max(1, int(block_config['threads'])), 4)
         if n_streams > 1:
-            main = torch.cuda.current_stream()
+            main = current_stream()
             streams = _band_streams(n_streams)
             for st in streams:
                 st.wait_stream(main)
             for band_i in range(n_bands):              # bands outermost, raster_pair.py:379-381
-                with torch.cuda.stream(streams[band_i % n_streams]):
+                with on_stream(streams[band_i % n_streams]):
                     run_band(band_i)
             for st in streams:
                 main.wait_stream(st)
@@ -365,7 +366,7 @@ class RasterFuse:
             for band_i in range(n_bands):
                 run_band(band_i)
         if to_host:
-            torch.cuda.current_stream().synchronize()  # the host copies have landed
+            current_stream().synchronize()  # the host copies have landed
 
         corr_array = corr_all if (src_on_device or corr_out is not None or is_tensor(self._src.array)) \
             else corr_all.numpy()

@@ -78,7 +78,33 @@ def _require_torch():
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """ Raw cudaStream_t of torch's current stream on the current device.  (``torch.cuda.current_stream()`` without a
+    device index walks through ``is_available()`` / NVML checks: ~14 us per call, which at 36 native calls per row-band
+    step was a quarter of the host time of a step.) """
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+
+
+def current_stream():
+    """ torch's current stream on the current device, by explicit index (the cheap path of ``torch.cuda.current_stream``). """
+    return torch.cuda.current_stream(torch._C._cuda_getDevice())
+
+
+class on_stream:
+    """ ``with on_stream(s):`` -- what ``torch.cuda.stream(s)`` does for a stream of the current device, without its
+    per-entry device queries. """
+    __slots__ = ('stream', 'prev')
+
+    def __init__(self, stream):
+        self.stream = stream
+
+    def __enter__(self):
+        self.prev = current_stream()
+        torch.cuda.set_stream(self.stream)
+        return self.stream
+
+    def __exit__(self, *exc):
+        torch.cuda.set_stream(self.prev)
+        return False
 
 
 def _on_raster_device(method):
