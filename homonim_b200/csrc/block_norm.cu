@@ -114,6 +114,25 @@ __device__ __forceinline__ void warp_hist_add_fast(unsigned int *hist, unsigned 
     if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(hist + bin, (unsigned int)__popc(peers));
 }
 
+// LEVEL 0: `comp` = (src bin << 12) | ref bin of a valid pixel, 0xffffffff for an invalid one; adds `weight` per active
+// lane to hist_s[src bin] and hist_r[ref bin] with one match for the pair of histograms
+__device__ __forceinline__ void warp_hist_add_pair(unsigned int *hist_s, unsigned int *hist_r, unsigned int comp,
+                                                   unsigned int weight)
+{
+    const bool active = comp != 0xffffffffu;
+    const unsigned int amask = __ballot_sync(0xffffffffu, active);
+    if (amask == 0u || !active) return;
+    int same = 0;
+    __match_all_sync(amask, comp, &same);
+    unsigned int peers = amask;
+    if (!same) peers = __match_any_sync(amask, comp);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+        const unsigned int c = weight * (unsigned int)__popc(peers);
+        atomicAdd(hist_s + (comp >> 12), c);
+        atomicAdd(hist_r + (comp & 0xfffu), c);
+    }
+}
+
 __device__ __forceinline__ double block_sum(double v, double *s_red)
 {
 #pragma unroll
@@ -188,6 +207,8 @@ __device__ __forceinline__ void norm_level_pass(const float *__restrict__ src, c
     if (VEC) {
         // 4 consecutive pixels per thread and iteration (16-byte loads of both planes)
         const long n4 = n / 4, n4_round = ((n4 + 31) / 32) * 32;   // keep warps converged for the votes
+        // (measured: not load-latency bound -- a 3-deep prefetch ring and 3 CTAs per SM changed nothing; level 0 waits on
+        //  the shared-memory atomics / matches, level 1 is bound by integer-pipe issue, level 2 runs at 5.3 TB/s)
         for (long g = tid; g < n4_round; g += stride) {
             float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), r4 = s4;
             const bool in = g < n4;
@@ -196,10 +217,50 @@ __device__ __forceinline__ void norm_level_pass(const float *__restrict__ src, c
                 r4 = __ldg(reinterpret_cast<const float4 *>(ref) + g);
             }
             const float sv[4] = {s4.x, s4.y, s4.z, s4.w}, rv[4] = {r4.x, r4.y, r4.z, r4.w};
+            bool valid[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const bool valid = in && hb_valid(sv[k], nd_s) && hb_valid(rv[k], nd_r);
-                norm_pixel<LEVEL>(sv[k], rv[k], valid, s_hist, prefix, mean_s, mean_r, acc_s, acc_r, cnt);
+            for (int k = 0; k < 4; k++) valid[k] = in && hb_valid(sv[k], nd_s) && hb_valid(rv[k], nd_r);
+            // The warp collectives (vote / match) of the histogram updates dominate this loop, not the loads: do them
+            // once per 4-pixel group where the group allows it.
+            if (LEVEL == 0) {
+                // one composite key per pixel -- (src bin, ref bin) -- so that ONE match serves both histograms; when every
+                // lane's four pixels share their key (smooth imagery: the common case) one match serves all four
+                unsigned int comp[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    comp[k] = valid[k] ? (((float_key(sv[k]) >> 20) << 12) | (float_key(rv[k]) >> 20)) : 0xffffffffu;
+                    if (valid[k]) { acc_s += (double)sv[k]; acc_r += (double)rv[k]; cnt++; }
+                }
+                const bool uni = (comp[0] == comp[1]) && (comp[1] == comp[2]) && (comp[2] == comp[3]);
+                if (__all_sync(0xffffffffu, uni)) {
+                    warp_hist_add_pair(s_hist, s_hist + 2 * kBins, comp[0], 4u);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) warp_hist_add_pair(s_hist, s_hist + 2 * kBins, comp[k], 1u);
+                }
+            } else {
+                // levels 1 / 2: almost no pixel still matches a query's prefix -- one vote per group decides
+                constexpr int sh = (LEVEL == 1) ? 20 : 8;
+                bool any_match = false;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const unsigned int ks = float_key(sv[k]) >> sh, kr = float_key(rv[k]) >> sh;
+                    any_match = any_match || (valid[k] && (ks == prefix[0] || ks == prefix[1] || kr == prefix[2] || kr == prefix[3]));
+                }
+                if (__ballot_sync(0xffffffffu, any_match) == 0u) {
+                    if (LEVEL == 1) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if (valid[k]) {
+                                const double ds = (double)sv[k] - mean_s, dr = (double)rv[k] - mean_r;
+                                acc_s += ds * ds; acc_r += dr * dr;
+                            }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        norm_pixel<LEVEL>(sv[k], rv[k], valid[k], s_hist, prefix, mean_s, mean_r, acc_s, acc_r, cnt);
+                }
             }
         }
         done = n4 * 4;
