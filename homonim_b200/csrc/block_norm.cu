@@ -391,12 +391,20 @@ __device__ void norm_resolve(NormAccum *__restrict__ acc, NormState *__restrict_
             const unsigned long long excl = off + incl[qq] - local[qq];
             if (rank >= excl && rank < excl + local[qq]) {      // exactly one thread per query
                 const int hq = (LEVEL == 0) ? (qq & 2) : qq;
+                // (all of the thread's bins are fetched together -- one L2 round trip; a loop that stops at the winning
+                //  bin makes every iteration wait for its own load: ~10 us per level on a proc-grid block)
+                unsigned long long cbin[per_thread];
+#pragma unroll
+                for (int i = 0; i < per_thread; i++) cbin[i] = __ldcg(&acc->hist[hq][threadIdx.x * per_thread + i]);
                 unsigned long long below = excl;
                 int bin = threadIdx.x * per_thread;
+                bool found = false;
+#pragma unroll
                 for (int i = 0; i < per_thread; i++) {
-                    const unsigned long long c = __ldcg(&acc->hist[hq][threadIdx.x * per_thread + i]);
-                    if (rank < below + c) { bin = threadIdx.x * per_thread + i; break; }
-                    below += c;
+                    if (!found) {
+                        if (rank < below + cbin[i]) { bin = threadIdx.x * per_thread + i; found = true; }
+                        else below += cbin[i];
+                    }
                 }
                 const unsigned int old_prefix = pf[qq];
                 const unsigned int p = (LEVEL == 0) ? (unsigned int)bin
@@ -664,7 +672,16 @@ __device__ __forceinline__ void norm_leaf_one(const NormWs &ws, long j)
 #pragma unroll
         for (int k = 0; k < 8; k++) r[k] = term(start + k);
         long i = 8;
-        for (; i < len - (len % 8); i += 8) {
+        const long lim = len - (len % 8);
+        // (32 elements fetched together, added in numpy's order: a leaf is up to 16 dependent rounds of loads otherwise)
+        for (; i + 32 <= lim; i += 32) {
+            float2 v[32];
+#pragma unroll
+            for (int k = 0; k < 32; k++) v[k] = term(start + i + k);
+#pragma unroll
+            for (int k = 0; k < 32; k++) { r[k & 7].x = __fadd_rn(r[k & 7].x, v[k].x); r[k & 7].y = __fadd_rn(r[k & 7].y, v[k].y); }
+        }
+        for (; i < lim; i += 8) {
 #pragma unroll
             for (int k = 0; k < 8; k++) { const float2 v = term(start + i + k); r[k].x = __fadd_rn(r[k].x, v.x); r[k].y = __fadd_rn(r[k].y, v.y); }
         }
@@ -822,6 +839,12 @@ __device__ __forceinline__ void norm_grid_sync(unsigned int *counter, unsigned i
     __syncthreads();
 }
 
+#ifdef HB_NORM_PROF
+#define NORM_TS(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_ts[i])); } } while (0)
+#else
+#define NORM_TS(i) do { } while (0)
+#endif
+
 template <bool VEC>
 __global__ void __launch_bounds__(kNormThreads)
 norm_coop_kernel(const float *__restrict__ src, NoData nd_s, const float *__restrict__ ref, NoData nd_r, long n, NormWs ws,
@@ -834,6 +857,14 @@ norm_coop_kernel(const float *__restrict__ src, NoData nd_s, const float *__rest
     NormState *st = ws.st;
     unsigned int *counter = &st->grid_arrivals;            // (zeroed by the host before the launch)
     unsigned int epoch = 0;
+#ifdef HB_NORM_PROF
+    unsigned long long prof_ts[24];
+    int prof_n = 0;
+#define NORM_MARK() do { NORM_TS(prof_n); prof_n++; } while (0)
+#else
+#define NORM_MARK() do { } while (0)
+#endif
+    NORM_MARK();
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long gtid = (long)blockIdx.x * kNormThreads + t, gstride = (long)gridDim.x * kNormThreads;
     // ---- init; valid pixels per chunk of 8 pixels per thread (chunk = kNormThreads * 8 pixels, one CTA at a time) -------------
@@ -876,7 +907,9 @@ norm_coop_kernel(const float *__restrict__ src, NoData nd_s, const float *__rest
             }
         }
     }
+    NORM_MARK();                                           // [1] counted
     norm_grid_sync(counter, epoch);
+    NORM_MARK();                                           // [2] sync
     // ---- compaction in C order (every CTA sums the counts of the chunks before its own: there are few) -------------------------
     if (ws.exact) {
         for (long c = blockIdx.x; c < nchunks; c += gridDim.x) {
@@ -908,6 +941,7 @@ norm_coop_kernel(const float *__restrict__ src, NoData nd_s, const float *__rest
             }
         }
     }
+    NORM_MARK();                                           // [3] compacted
     // ---- the three levels ------------------------------------------------------------------------------------------------------
     auto level = [&](auto level_c) {
         constexpr int LEVEL = decltype(level_c)::value;
@@ -941,12 +975,17 @@ norm_coop_kernel(const float *__restrict__ src, NoData nd_s, const float *__rest
                 if (t == 0) atomicAdd(&acc->n, (unsigned long long)(tc + 0.5));
             }
         }
+        NORM_MARK();                                       // pass done
         norm_grid_sync(counter, epoch);
+        NORM_MARK();                                       // sync
         if (blockIdx.x == 0) {
             if (ws.exact && LEVEL > 0) norm_tree<LEVEL>(reinterpret_cast<const char *>(acc), ws.msg_bytes, st, nullptr, nullptr);
+            NORM_MARK();                                   // tree
             norm_resolve<LEVEL>(acc, st, norm);           // (also clears the histograms for the next level)
         }
-        norm_grid_sync(counter, epoch);
+        NORM_MARK();                                       // resolve
+        if (LEVEL < 2) norm_grid_sync(counter, epoch);     // (nothing follows the last level's resolve)
+        NORM_MARK();                                       // sync
     };
     auto leaves = [&](auto sq_c) {                         // numpy's pairwise-leaf sums of x / of (x - mean)^2
         constexpr bool SQDEV = decltype(sq_c)::value;
@@ -957,6 +996,13 @@ norm_coop_kernel(const float *__restrict__ src, NoData nd_s, const float *__rest
     level(std::integral_constant<int, 1>{});               // CTA 0: tree<1> -> numpy's means, then the level's resolve
     if (ws.exact) leaves(std::true_type{});
     level(std::integral_constant<int, 2>{});               // CTA 0: tree<2> -> numpy's standard deviations, final resolve
+#ifdef HB_NORM_PROF
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        printf("norm_coop n=%ld grid=%d:", n, (int)gridDim.x);
+        for (int i = 1; i < prof_n; i++) printf(" %llu", prof_ts[i] - prof_ts[i - 1]);
+        printf(" ns\n");
+    }
+#endif
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------------
@@ -1097,7 +1143,7 @@ extern "C" int hb_block_norm(const float *src_dev, int src_has_nodata, double sr
             return 0;
         });
         if (rc) return rc;
-        long ctas = (n + kNormThreads * 16 - 1) / (kNormThreads * 16);
+        long ctas = (n + kNormThreads * 8 - 1) / (kNormThreads * 8);      // (one 2048-pixel chunk per CTA and phase up to 131k px)
         if (ctas < 1) ctas = 1;
         if (ctas > kCoopMaxCtas) ctas = kCoopMaxCtas;
         HB_CUDA_OK(cudaMemsetAsync(&ws.st->grid_arrivals, 0, sizeof(unsigned int), st));
