@@ -938,6 +938,12 @@ def main():
                                daemon=True)
     if rank == 0:
         sampler.start()
+        # the timed region lasts a few milliseconds: wait until the sampler is up (NVML initialisation takes longer than
+        # that the first time) and keep the GPU under load meanwhile, so that its first samples are already "under load"
+        t_wait = time.perf_counter()
+        while not samples and time.perf_counter() - t_wait < 5.0:
+            step()
+            torch.cuda.synchronize()
     lib.hb_reset_launch_count()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
