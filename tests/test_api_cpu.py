@@ -194,6 +194,29 @@ def test_bench_reference_arm_contract():
     assert 'workload' in line['config'] and 'model' not in line['config']
 
 
+def test_bench_reference_arm_on_real_images_bounded():
+    """ BASELINE.json configs[0] (`--workload c1`: the reference's own test images, committed as a fixture) through the
+    reference arm, with a time budget small enough to force the bounded-sample path (fewer bands per step). """
+    import json
+    import os
+    import pathlib
+    import subprocess
+    import sys
+    repo = pathlib.Path(__file__).resolve().parent.parent
+    env = dict(os.environ, HB_REFERENCE_BUDGET_S='0.2')
+    out = subprocess.run([sys.executable, str(repo / 'bench.py'), '--impl', 'reference', '--workload', 'c1', '--steps',
+                          '2', '--warmup', '1'], capture_output=True, text=True, timeout=600, cwd=str(repo), env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith('{')][0])
+    assert line['data'].startswith('real') and line['config']['src_shape'] == [1421, 805]
+    assert line['config']['kernel_model'] == 'gain-blk-offset' and line['config']['bands'] == 3
+    assert 'bounded sample' in line['cpu_baseline']['sample'] and line['value'] > 0
+    import bench
+    assert bench._small(bench.WORKLOADS['c1']) and bench._small(bench.WORKLOADS['tiny'])
+    assert not bench._small(bench.WORKLOADS['c2']) and not bench._small(bench.WORKLOADS['c3'])
+    assert 'flush' in bench._config(bench.WORKLOADS['c1'])['l2'] or 'written between' in bench._config(bench.WORKLOADS['c1'])['l2']
+
+
 def test_raster_compare_host_logic():
     """ RasterCompare's host side (no GPU): configuration defaults, the closed-pair error, the statistics formed from
     the sums (same expressions as compare.py:145-187, checked against the oracle restatement) and the table. """
