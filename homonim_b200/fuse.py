@@ -328,6 +328,46 @@ class RasterFuse:
         # a float32 plane and a separate conversion
         fused_out = out_dtype in ('float32', 'uint8', 'uint16', 'int16')
 
+        # File -> file: the corrected image is encoded and written band by band WHILE the GPU works on the
+        # later bands -- the writer waits on a band stream that a small completion thread feeds as every band's device ->
+        # host copy lands.  (The reference's writer likewise runs inside its thread pool, fuse.py:254-293, 396-408.)
+        meta = dict(model=model_type, kernel_shape=tuple(kernel_shape), **model_config,
+                    **dict(block_config, max_block_mem='whole-band'))     # one block per band: recorded as applied
+        streaming = self._files is not None and is_path(corr_filename) and to_host and corr_out is None
+        band_stream = done_queue = writer = completer = None
+        writer_error: list = []
+        if streaming:
+            import queue
+            import types
+            from homonim_b200.geotiff import BandStream
+            band_stream = BandStream(corr_all.numpy())
+            done_queue = queue.Queue()
+
+            def _complete():
+                while True:
+                    item = done_queue.get()
+                    if item is None:
+                        return
+                    band_i, event = item
+                    try:
+                        event.synchronize()
+                        band_stream.set_ready(band_i)
+                    except BaseException as ex:      # noqa
+                        band_stream.fail(ex)
+                        return
+
+            def _write():
+                try:
+                    target = types.SimpleNamespace(array=band_stream, transform=self._src.transform, crs=self._src.crs)
+                    self._files.write_corrected(target, corr_filename, self.proc_crs, out_profile, overwrite=overwrite,
+                                                **meta)
+                except BaseException as ex:          # noqa
+                    writer_error.append(ex)
+            completer = threading.Thread(target=_complete, daemon=True)
+            writer = threading.Thread(target=_write, daemon=True)
+            completer.start()
+            writer.start()
+
         def run_band(band_i):
             want = param_filename is not None
             if fused_out:
@@ -343,12 +383,55 @@ class RasterFuse:
                 corr_all[band_i].copy_(plane, non_blocking=True)
             if param_ra is not None:
                 param_planes[band_i] = param_ra if (src_on_device or param_filename is None) else param_ra.to_host()
+            if streaming:
+                landed = torch.cuda.Event()
+                landed.record(current_stream())
+                done_queue.put((band_i, landed))
 
         # Bands are independent (the reference runs (band, block) jobs on a thread pool, fuse.py:396-408).  On the
         # GPU each band is enqueued on its own CUDA stream, so that the small latency-bound kernels of one band (fit
         # on the proc grid, in-painting) overlap the bandwidth-bound resampling kernels of the others -- and, for host
         # rasters, one band's host <-> device copies overlap the other bands' kernels.
         n_streams = min(n_bands, max(1, int(block_config['threads'])), 4)
+        try:
+            self._run_bands(run_band, n_bands, n_streams, corr_all, param_planes)
+        except BaseException as ex:
+            if streaming:
+                band_stream.fail(ex)
+                done_queue.put(None)
+                writer.join(timeout=60)
+            raise
+        if to_host:
+            current_stream().synchronize()  # the host copies have landed
+        if streaming:
+            done_queue.put(None)
+            completer.join()
+            writer.join()
+            if writer_error:
+                raise writer_error[0]
+
+        corr_array = corr_all if (src_on_device or corr_out is not None or is_tensor(self._src.array)) \
+            else corr_all.numpy()
+        corr = RasterArray(corr_array, self._src.crs, self._src.transform, nodata=out_nodata)
+        params = None
+        if param_filename is not None:
+            n_params = param_planes[0].count
+            planes = [param_planes[b].array[p] for p in range(n_params) for b in range(n_bands)]
+            stack = torch.stack if is_tensor(planes[0]) else np.stack
+            params = RasterArray(stack(planes), param_planes[0].crs, param_planes[0].transform, nodata=float('nan'))
+        if self._files is not None and is_path(corr_filename):
+            # a pair opened from files: write the outputs with the reference's metadata (fuse.py:264-293)
+            if not streaming:
+                self._files.write_corrected(corr.to_host(), corr_filename, self.proc_crs, out_profile,
+                                            overwrite=overwrite, **meta)
+            if params is not None and is_path(param_filename):
+                self._files.write_params(params.to_host(), param_filename, self.proc_crs, out_profile,
+                                         overwrite=overwrite, **meta)
+        return corr, params
+
+    @staticmethod
+    def _run_bands(run_band, n_bands, n_streams, corr_all, param_planes):
+        """ Enqueue every band, each on its own CUDA stream of the per-device pool (see `process`). """
         if n_streams > 1:
             main = current_stream()
             streams = _band_streams(n_streams)
@@ -365,29 +448,6 @@ class RasterFuse:
         else:
             for band_i in range(n_bands):
                 run_band(band_i)
-        if to_host:
-            current_stream().synchronize()  # the host copies have landed
-
-        corr_array = corr_all if (src_on_device or corr_out is not None or is_tensor(self._src.array)) \
-            else corr_all.numpy()
-        corr = RasterArray(corr_array, self._src.crs, self._src.transform, nodata=out_nodata)
-        params = None
-        if param_filename is not None:
-            n_params = param_planes[0].count
-            planes = [param_planes[b].array[p] for p in range(n_params) for b in range(n_bands)]
-            stack = torch.stack if is_tensor(planes[0]) else np.stack
-            params = RasterArray(stack(planes), param_planes[0].crs, param_planes[0].transform, nodata=float('nan'))
-        if self._files is not None and is_path(corr_filename):
-            # a pair opened from files: write the outputs with the reference's metadata (fuse.py:264-293)
-            # (every band is ONE block here: max_block_mem is recorded as what was applied, not what was asked for)
-            meta = dict(model=model_type, kernel_shape=tuple(kernel_shape), **model_config,
-                        **dict(block_config, max_block_mem='whole-band'))
-            self._files.write_corrected(corr.to_host(), corr_filename, self.proc_crs, out_profile,
-                                        overwrite=overwrite, **meta)
-            if params is not None and is_path(param_filename):
-                self._files.write_params(params.to_host(), param_filename, self.proc_crs, out_profile,
-                                         overwrite=overwrite, **meta)
-        return corr, params
 
 
 def _convert_dtype(ra: RasterArray, dtype: str, nodata):

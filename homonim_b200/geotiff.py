@@ -16,6 +16,7 @@ import math
 import os
 import pathlib
 import struct
+import threading
 import zlib
 from typing import Dict, List, Optional, Sequence, Tuple
 from xml.etree import ElementTree
@@ -417,6 +418,42 @@ def _gdal_metadata_xml(tags: Optional[Dict], band_tags: Optional[Sequence[Dict]]
     return '<GDALMetadata>\n' + '\n'.join(items) + '\n</GDALMetadata>\n'
 
 
+class BandStream:
+    """
+    A ``[bands, H, W]`` array whose bands become available one after the other -- what :func:`write_geotiff` takes to
+    encode band ``b`` while the GPU is still producing band ``b + 1``.  ``array`` is the (host) buffer
+    the producer fills; the producer calls ``set_ready(b)`` once band ``b`` is complete in it, or ``fail(exc)``.
+    """
+
+    def __init__(self, array: np.ndarray):
+        if array.ndim != 3:
+            raise ValueError('BandStream needs a [bands, H, W] buffer')
+        self.array = array
+        self.shape, self.dtype, self.ndim = array.shape, array.dtype, 3
+        self._ready = [threading.Event() for _ in range(array.shape[0])]
+        self._error: Optional[BaseException] = None
+
+    def set_ready(self, band: int) -> None:
+        self._ready[band].set()
+
+    def fail(self, exc: BaseException) -> None:
+        self._error = exc
+        for ev in self._ready:
+            ev.set()
+
+    def wait_band(self, band: int, timeout: float = 3600.0) -> np.ndarray:
+        if not self._ready[band].wait(timeout):
+            raise TimeoutError(f'band {band} was not produced within {timeout} s')
+        if self._error is not None:
+            raise RuntimeError('the producer of this band stream failed') from self._error
+        return self.array[band]
+
+    def wait_all(self) -> np.ndarray:
+        for b in range(self.shape[0]):
+            self.wait_band(b)
+        return self.array
+
+
 def write_geotiff(filename, array, transform, crs=None, nodata=None, descriptions=None, tags=None, band_tags=None,
                   geokeys=None, compress: Optional[str] = 'deflate', blocksize: int = 512, interleave: str = 'band',
                   photometric: Optional[str] = None, bigtiff: Optional[bool] = None, overwrite: bool = False,
@@ -431,14 +468,16 @@ def write_geotiff(filename, array, transform, crs=None, nodata=None, description
     path = pathlib.Path(filename)
     if path.exists() and not overwrite:
         raise FileExistsError(f"{path} exists and won't be overwritten without `overwrite`")
-    if torch is not None and isinstance(array, torch.Tensor):
-        array = array.detach().cpu().numpy()
-    array = np.asarray(array)
-    if array.ndim == 2:
-        array = array[None]
+    stream = array if isinstance(array, BandStream) else None
+    if stream is None:
+        if torch is not None and isinstance(array, torch.Tensor):
+            array = array.detach().cpu().numpy()
+        array = np.asarray(array)
+        if array.ndim == 2:
+            array = array[None]
     if array.ndim != 3:
         raise ValueError('`array` must be [bands, H, W] or [H, W]')
-    dtype = array.dtype.newbyteorder('=')
+    dtype = np.dtype(array.dtype).newbyteorder('=')
     sample = {v: k for k, v in _SAMPLE_DTYPES.items()}.get(dtype.str[1:])
     if sample is None:
         raise NotImplementedError(f'dtype {dtype} cannot be written')
@@ -461,10 +500,11 @@ def write_geotiff(filename, array, transform, crs=None, nodata=None, description
         tile = np.zeros((th, tw, 1 if planar == 2 else count), dtype=dtype)
         ys, xs = slice(by * th, min((by + 1) * th, height)), slice(bx * tw, min((bx + 1) * tw, width))
         if planar == 2:
-            part = array[plane, ys, xs]
+            # (a band stream: blocks until the producer has finished this band)
+            part = (stream.wait_band(plane) if stream is not None else array[plane])[ys, xs]
             tile[:part.shape[0], :part.shape[1], 0] = part
         else:
-            part = array[:, ys, xs]
+            part = (stream.wait_all() if stream is not None else array)[:, ys, xs]
             tile[:part.shape[1], :part.shape[2], :] = np.moveaxis(part, 0, 2)
         data = tile.tobytes()
         return zlib.compress(data, level) if deflate else data
@@ -474,91 +514,107 @@ def write_geotiff(filename, array, transform, crs=None, nodata=None, description
     off_fmt, off_type = ('Q', 16) if big else ('I', 4)
     tmp = path.with_name(path.name + '.part')
     offsets, counts = [], []
-    with open(tmp, 'wb') as fh:
-        fh.write(b'II' + (struct.pack('<HHHQ', 43, 8, 0, 0) if big else struct.pack('<HI', 42, 0)))
-        for data in _codec_pool().map(encode, jobs):
-            offsets.append(fh.tell())
-            counts.append(len(data))
-            fh.write(data)
+    try:
+        with open(tmp, 'wb') as fh:
+            fh.write(b'II' + (struct.pack('<HHHQ', 43, 8, 0, 0) if big else struct.pack('<HI', 42, 0)))
+            # (a band stream gets its own workers: its jobs block while they wait for the producer, and must not starve the
+            #  shared codec pool that readers decode on)
+            own_pool = concurrent.futures.ThreadPoolExecutor(max_workers=max(2, os.cpu_count() or 2)) if stream is not None \
+                else None
+            try:
+                for data in (own_pool if own_pool is not None else _codec_pool()).map(encode, jobs):
+                    offsets.append(fh.tell())
+                    counts.append(len(data))
+                    fh.write(data)
+                    if fh.tell() % 2:
+                        fh.write(b'\x00')
+            finally:
+                if own_pool is not None:
+                    own_pool.shutdown(wait=True, cancel_futures=True)
+            # ---- IFD ----
+            entries = []                                            # (tag, type, count, packed value bytes)
+
+            def add(tag, typ, values):
+                if typ == 2:
+                    data = str(values).encode('latin1', 'replace') + b'\x00'
+                    entries.append((tag, 2, len(data), data))
+                else:
+                    fmt = _FIELD[typ][0]
+                    values = list(values)
+                    entries.append((tag, typ, len(values), struct.pack(bo + fmt * len(values), *values)))
+
+            if photometric is None:
+                photometric = 'rgb' if (count == 3 and dtype.kind == 'u' and dtype.itemsize == 1) else 'minisblack'
+            base = 3 if photometric == 'rgb' else 1
+            add(256, 3 if width < 65536 else 4, [width])
+            add(257, 3 if height < 65536 else 4, [height])
+            add(258, 3, [sample[1]] * count)
+            add(259, 3, [8 if deflate else 1])
+            add(262, 3, [2 if photometric == 'rgb' else 1])
+            add(277, 3, [count])
+            add(284, 3, [planar])
+            add(322, 3, [tw])
+            add(323, 3, [th])
+            add(324, off_type, offsets)
+            add(325, off_type, counts)
+            if count > base:
+                add(338, 3, [0] * (count - base))
+            add(339, 3, [sample[0]] * count)
+            add(33550, 12, [abs(t.a), abs(t.e), 0.0])
+            add(33922, 12, [0.0, 0.0, 0.0, t.c, t.f, 0.0])
+            if geokeys is None:
+                geokeys = getattr(crs, 'raw_geokeys', None)         # a CRS read by GeoTiffReader carries its raw keys
+            if geokeys and geokeys[0]:
+                geokeys = _geokeys_pixel_is_area(geokeys)           # the tie point below is a pixel corner
+                add(34735, 3, geokeys[0])
+                if geokeys[1]:
+                    add(34736, 12, geokeys[1])
+                if geokeys[2]:
+                    add(34737, 2, geokeys[2])
+            xml = _gdal_metadata_xml(tags, band_tags, descriptions)
+            if xml:
+                add(42112, 2, xml)
+            if nodata is not None:
+                add(42113, 2, 'nan' if (isinstance(nodata, float) and math.isnan(nodata)) else repr(
+                    int(nodata) if float(nodata).is_integer() else float(nodata)))
+            entries.sort(key=lambda e: e[0])
             if fh.tell() % 2:
                 fh.write(b'\x00')
-        # ---- IFD ----
-        entries = []                                            # (tag, type, count, packed value bytes)
-
-        def add(tag, typ, values):
-            if typ == 2:
-                data = str(values).encode('latin1', 'replace') + b'\x00'
-                entries.append((tag, 2, len(data), data))
+            # out-of-line values first, then the directory
+            inline = 8 if big else 4
+            placed = []
+            for tag, typ, cnt, data in entries:
+                if len(data) <= inline:
+                    placed.append((tag, typ, cnt, data.ljust(inline, b'\x00')))
+                else:
+                    pos = fh.tell()
+                    fh.write(data)
+                    if fh.tell() % 2:
+                        fh.write(b'\x00')
+                    placed.append((tag, typ, cnt, struct.pack(bo + off_fmt, pos)))
+            ifd_pos = fh.tell()
+            if big:
+                fh.write(struct.pack('<Q', len(placed)))
+                for tag, typ, cnt, value in placed:
+                    fh.write(struct.pack('<HHQ', tag, typ, cnt) + value)
+                fh.write(struct.pack('<Q', 0))
+                fh.seek(8)
+                fh.write(struct.pack('<Q', ifd_pos))
             else:
-                fmt = _FIELD[typ][0]
-                values = list(values)
-                entries.append((tag, typ, len(values), struct.pack(bo + fmt * len(values), *values)))
-
-        if photometric is None:
-            photometric = 'rgb' if (count == 3 and dtype.kind == 'u' and dtype.itemsize == 1) else 'minisblack'
-        base = 3 if photometric == 'rgb' else 1
-        add(256, 3 if width < 65536 else 4, [width])
-        add(257, 3 if height < 65536 else 4, [height])
-        add(258, 3, [sample[1]] * count)
-        add(259, 3, [8 if deflate else 1])
-        add(262, 3, [2 if photometric == 'rgb' else 1])
-        add(277, 3, [count])
-        add(284, 3, [planar])
-        add(322, 3, [tw])
-        add(323, 3, [th])
-        add(324, off_type, offsets)
-        add(325, off_type, counts)
-        if count > base:
-            add(338, 3, [0] * (count - base))
-        add(339, 3, [sample[0]] * count)
-        add(33550, 12, [abs(t.a), abs(t.e), 0.0])
-        add(33922, 12, [0.0, 0.0, 0.0, t.c, t.f, 0.0])
-        if geokeys is None:
-            geokeys = getattr(crs, 'raw_geokeys', None)         # a CRS read by GeoTiffReader carries its raw keys
-        if geokeys and geokeys[0]:
-            geokeys = _geokeys_pixel_is_area(geokeys)           # the tie point below is a pixel corner
-            add(34735, 3, geokeys[0])
-            if geokeys[1]:
-                add(34736, 12, geokeys[1])
-            if geokeys[2]:
-                add(34737, 2, geokeys[2])
-        xml = _gdal_metadata_xml(tags, band_tags, descriptions)
-        if xml:
-            add(42112, 2, xml)
-        if nodata is not None:
-            add(42113, 2, 'nan' if (isinstance(nodata, float) and math.isnan(nodata)) else repr(
-                int(nodata) if float(nodata).is_integer() else float(nodata)))
-        entries.sort(key=lambda e: e[0])
-        if fh.tell() % 2:
-            fh.write(b'\x00')
-        # out-of-line values first, then the directory
-        inline = 8 if big else 4
-        placed = []
-        for tag, typ, cnt, data in entries:
-            if len(data) <= inline:
-                placed.append((tag, typ, cnt, data.ljust(inline, b'\x00')))
-            else:
-                pos = fh.tell()
-                fh.write(data)
-                if fh.tell() % 2:
-                    fh.write(b'\x00')
-                placed.append((tag, typ, cnt, struct.pack(bo + off_fmt, pos)))
-        ifd_pos = fh.tell()
-        if big:
-            fh.write(struct.pack('<Q', len(placed)))
-            for tag, typ, cnt, value in placed:
-                fh.write(struct.pack('<HHQ', tag, typ, cnt) + value)
-            fh.write(struct.pack('<Q', 0))
-            fh.seek(8)
-            fh.write(struct.pack('<Q', ifd_pos))
-        else:
-            if ifd_pos >= 2 ** 32:
-                raise ValueError('the image does not fit a classic TIFF: pass bigtiff=True')
-            fh.write(struct.pack('<H', len(placed)))
-            for tag, typ, cnt, value in placed:
-                fh.write(struct.pack('<HHI', tag, typ, cnt) + value)
-            fh.write(struct.pack('<I', 0))
-            fh.seek(4)
-            fh.write(struct.pack('<I', ifd_pos))
+                if ifd_pos >= 2 ** 32:
+                    raise ValueError('the image does not fit a classic TIFF: pass bigtiff=True')
+                fh.write(struct.pack('<H', len(placed)))
+                for tag, typ, cnt, value in placed:
+                    fh.write(struct.pack('<HHI', tag, typ, cnt) + value)
+                fh.write(struct.pack('<I', 0))
+                fh.seek(4)
+                fh.write(struct.pack('<I', ifd_pos))
+    except BaseException:
+        # (a failed write -- e.g. a band stream whose producer failed -- leaves no partial file behind)
+        try:
+            os.unlink(tmp)
+        except OSError:
+            pass
+        raise
     os.replace(tmp, path)
     return path

@@ -377,3 +377,45 @@ def test_internal_mask_ifd_is_refused(tmp_path):
     (tmp_path / 'a.tif.msk').write_bytes(b'')
     with pytest.raises(NotImplementedError, match='mask'):
         GeoTiffReader(path)
+
+
+def test_band_stream_writer_equals_eager_writer(tmp_path):
+    """ write_geotiff fed band by band (geotiff.BandStream: the file path's overlap of encoding with the GPU step,
+    SURVEY.md 8f-4) writes the same bytes as the eager call; a failing producer surfaces as an error, not a hang. """
+    import threading
+    import time
+    from homonim_b200.geometry import Affine
+    from homonim_b200.geotiff import BandStream, GeoTiffReader, write_geotiff
+    rng = np.random.default_rng(8)
+    data = rng.integers(0, 4000, (3, 300, 420)).astype('uint16')
+    tf = Affine(2.0, 0, 100.0, 0, -2.0, 900.0)
+    for compress in ('deflate', None):
+        eager = write_geotiff(tmp_path / f'eager_{compress}.tif', data, tf, nodata=0, compress=compress, blocksize=128)
+        buf = np.zeros_like(data)
+        stream = BandStream(buf)
+
+        def produce():
+            for b in (0, 1, 2):
+                time.sleep(0.05)
+                buf[b] = data[b]
+                stream.set_ready(b)
+        t = threading.Thread(target=produce)
+        t.start()
+        lazy = write_geotiff(tmp_path / f'lazy_{compress}.tif', stream, tf, nodata=0, compress=compress, blocksize=128)
+        t.join()
+        assert pathlib.Path(eager).read_bytes() == pathlib.Path(lazy).read_bytes()
+        with GeoTiffReader(lazy) as im:
+            assert np.array_equal(im.read(), data)
+    # pixel-interleaved output needs every band before the first tile: still correct
+    buf = np.zeros_like(data)
+    stream = BandStream(buf)
+    threading.Thread(target=lambda: [(buf.__setitem__(b, data[b]), stream.set_ready(b)) for b in range(3)]).start()
+    p = write_geotiff(tmp_path / 'pixel.tif', stream, tf, interleave='pixel', blocksize=128)
+    with GeoTiffReader(p) as im:
+        assert np.array_equal(im.read(), data)
+    # a producer that fails
+    stream = BandStream(np.zeros_like(data))
+    threading.Timer(0.05, lambda: stream.fail(ValueError('boom'))).start()
+    with pytest.raises(RuntimeError, match='producer'):
+        write_geotiff(tmp_path / 'fail.tif', stream, tf, blocksize=128)
+    assert not (tmp_path / 'fail.tif').exists() and not (tmp_path / 'fail.tif.part').exists()
